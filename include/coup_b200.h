@@ -1,0 +1,202 @@
+/* coup_b200.h -- C ABI of libcoup_b200.so, the B200-native batched Coup environment.
+ *
+ * This is the drop-in boundary for the Coup game of BStarcheus/open_spiel_coup
+ * (open_spiel/games/coup.{h,cc}). Conventions follow the reference's own pure-C API
+ * (open_spiel/rust/src/rust_open_spiel.h): opaque handles, scalar getters return int, tensors are
+ * written into caller-provided buffers with an explicit length. Differences, all forced by batching
+ * on a GPU: big buffers are DEVICE pointers, every call takes an explicit cudaStream_t (passed as
+ * void*), and instead of aborting the process on an illegal move (spiel_utils.cc:119-137) calls return
+ * a status code and the environment records a sticky per-env error bit.
+ *
+ * There is no CPU implementation behind this header: every entry point launches sm_100a kernels (or
+ * copies device memory). COUP_ERR_NO_DEVICE is returned when no CUDA device is usable.
+ *
+ * Action ids (coup.h:65-85):  0 Income 1 ForeignAid 2 Coup 3 Tax 4 Assassinate 5 Exchange 6 Steal
+ *   7 LoseCard1 8 LoseCard2 9 Pass 10 Block 11 Challenge 12..17 ExchangeReturn{12,13,14,23,24,34}
+ * Chance outcome ids = card types (coup.h:50-57): 0 Assassin 1 Ambassador 2 Captain 3 Contessa 4 Duke
+ */
+#ifndef COUP_B200_H_
+#define COUP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- game constants (CoupGame, coup.h:199-231, coup.cc:1104-1130) ------------------------------- */
+#define COUP_NUM_PLAYERS 2
+#define COUP_NUM_DISTINCT_ACTIONS 18
+#define COUP_MAX_CHANCE_OUTCOMES 5
+#define COUP_MAX_GAME_LENGTH 90
+#define COUP_MAX_CHANCE_NODES_IN_HISTORY 45
+#define COUP_INFO_STATE_SIZE 2492   /* player2 p1_cards20 p2_cards20 cur_move_player2 cards_state16 coins2 history135x18 */
+#define COUP_OBSERVATION_SIZE 98    /* ... same 62-float head ... last_action2x18 */
+#define COUP_MIN_UTILITY (-2)
+#define COUP_MAX_UTILITY 2
+#define COUP_CHANCE_PLAYER_ID (-1)   /* spiel_globals.h:28 */
+#define COUP_TERMINAL_PLAYER_ID (-4) /* spiel_globals.h:34 */
+
+/* ---- status codes ------------------------------------------------------------------------------ */
+enum {
+  COUP_OK = 0,
+  COUP_ERR_INVALID_ARG = 1,
+  COUP_ERR_CUDA = 2,        /* a CUDA runtime call failed; see coup_last_error() */
+  COUP_ERR_NO_DEVICE = 3,
+  COUP_ERR_ILLEGAL_ACTION = 4 /* at least one env was handed an action outside LegalActions() */
+};
+
+/* ---- packed device layout (documented so that callers can snapshot / inspect it) -----------------
+ * state: uint32[num_envs][4] (one 16-byte word per env)
+ *   w0, w1 = player 0 / player 1:
+ *     bits  0-15 hand: four 4-bit slots, slot = (card_value << 1) | face_up, 0xF = empty; always
+ *                sorted ascending, i.e. by (value, FaceDown < FaceUp) as CoupPlayer::SortCards
+ *                (coup.h:91-94, coup.cc:389-391)
+ *     bits 16-20 coins        bits 21-25 last_action (31 = kNone)        bit 26 lost_challenge
+ *   w2: bits 0-19 deck counts, 4 bits per card type (deck_, coup.h:164)
+ *       bit 20 cur_player_turn_  bit 21 cur_player_move_  bit 22 is_turn_begin_  bit 23 is_chance_
+ *       bits 24-26 number of queued deals (deal_card_to_)  bit 27 queue is the initial 0,1,0,1 deal
+ *       bit 28 player the queued deals go to (when bit 27 is clear)  bit 29 sticky illegal-action flag
+ *   w3: bits 0-6 move_number_  bits 7-13 turn_number_  bits 14-16 cur_rewards_[0] + 2
+ *       (cur_rewards_[1] == -cur_rewards_[0] always)
+ * history: uint32[num_envs][16]; move i of the episode is the 5-bit code at word i/6, bit 5*(i%6):
+ *   0..17 player action id, 18+c card c dealt to player 0, 23+c card c dealt to player 1.
+ *   Entries at index >= move_number_ are unspecified.
+ */
+#define COUP_STATE_WORDS 4
+#define COUP_HISTORY_WORDS 16
+
+/* ---- options ----------------------------------------------------------------------------------- */
+enum {
+  COUP_FLAG_AUTO_RESET = 1u << 0 /* vector_env.SyncVectorEnv.step(reset_if_done=True) semantics
+                                    (python/vector_env.py:40-66): an env whose step ends the episode
+                                    reports done/rewards/returns of the finished episode and is
+                                    re-dealt in the same call; legal mask / current player / tensors
+                                    then describe the first decision of the new episode */
+};
+
+typedef struct coup_vec_opts {
+  uint32_t num_envs;          /* environments owned by this handle (one handle per GPU) */
+  int32_t device;             /* CUDA device ordinal */
+  uint64_t seed;              /* Philox4x32-10 seed */
+  uint64_t global_env_offset; /* global id of env 0; Philox key = (seed, global_env_offset + i), so
+                                 trajectories do not depend on how envs are sharded over GPUs */
+  uint32_t flags;             /* COUP_FLAG_* */
+  uint32_t reserved;
+} coup_vec_opts;
+
+typedef struct coup_vec_env coup_vec_env; /* opaque */
+
+/* Which observer's view to encode. */
+enum {
+  COUP_PLAYER_0 = 0,
+  COUP_PLAYER_1 = 1,
+  COUP_PLAYER_CURRENT = 2, /* cur_player_move_ of each env (benchmark_game.cc:53-60 protocol) */
+  COUP_PLAYER_BOTH = 3     /* rows [env][player] (rl_environment.get_time_step, rl_environment.py:243-249) */
+};
+/* Element type of encoded tensors. Values are 0, 1 and coin counts <= 12: exact in all three. */
+enum { COUP_DTYPE_F32 = 0, COUP_DTYPE_U8 = 1, COUP_DTYPE_BF16 = 2 };
+
+/* Index of each counter in the statistics vector (uint64[COUP_STATS_LEN]). */
+enum {
+  COUP_STAT_DECISION_STEPS = 0, /* player actions applied */
+  COUP_STAT_CHANCE_MOVES = 1,   /* chance deals applied (incl. the 4 initial deals of every episode) */
+  COUP_STAT_EPISODES = 2,       /* episodes that reached a terminal state */
+  COUP_STAT_TRUNCATED = 3,      /* ... of which ended by move_number_ > MaxGameLength (coup.cc:990) */
+  COUP_STAT_EPISODE_MOVES = 4,  /* sum of move_number_ over finished episodes */
+  COUP_STAT_ILLEGAL = 5,        /* illegal actions rejected */
+  COUP_STAT_RETURN_HIST = 8,    /* [8..12]: finished episodes by Returns()[0] = -2..+2 */
+  COUP_STAT_LEGAL_HIST = 16,    /* [16..23]: decision steps by number of legal actions 0..7 */
+  COUP_STATS_LEN = 32
+};
+
+const char* coup_last_error(void);
+int coup_device_count(void);
+
+/* ---- lifecycle (GameNewInitialState / DeleteState, rust_open_spiel.h:41,48, batched) ----------- */
+int coup_vec_create(const coup_vec_opts* opts, coup_vec_env** out);
+int coup_vec_destroy(coup_vec_env* env);
+uint32_t coup_vec_num_envs(const coup_vec_env* env);
+
+/* ---- reset (CoupState ctor coup.cc:393-428 + the four initial deals; rl_environment.reset,
+ * python/rl_environment.py:324-367). d_reset_mask: uint8[num_envs] on the device or NULL for all.
+ * d_forced_deals: uint8[num_envs][4] card ids to deal instead of sampling (known-answer replay), or
+ * NULL; an entry 0xFF means "sample". */
+int coup_vec_reset(coup_vec_env* env, const uint8_t* d_reset_mask, const uint8_t* d_forced_deals,
+                   void* stream);
+
+/* ---- step (State::ApplyAction spiel.cc:322-332 + CoupState::DoApplyAction coup.cc:490-809, then
+ * every following chance node resolved as rl_environment._sample_external_events does,
+ * rl_environment.py:369-382). d_actions: uint8[num_envs] action ids on the device. d_forced_chance:
+ * uint8[num_envs][4] outcomes for the chance nodes that follow (0xFF = sample), or NULL.
+ * Envs that are already terminal ignore their action (rl_environment.py:301-302). After the call the
+ * per-env outputs below describe the new state. Returns COUP_ERR_ILLEGAL_ACTION only from
+ * coup_vec_check_errors (the launch itself is asynchronous). */
+int coup_vec_step(coup_vec_env* env, const uint8_t* d_actions, const uint8_t* d_forced_chance,
+                  void* stream);
+
+/* Uniform-random legal action per env (the policy of benchmark_game.cc:96-99), Philox-driven:
+ * writes uint8[num_envs] to d_actions_out (terminal envs get 0xFF). */
+int coup_vec_sample_uniform(coup_vec_env* env, uint8_t* d_actions_out, void* stream);
+
+/* Fused random rollout: n_steps x (sample uniform legal action, step, resolve chance, [auto-reset],
+ * encode). encode_player: COUP_PLAYER_* or -1 for no tensor. d_tensor_out: dtype[rows][2492] where
+ * rows = num_envs (x2 for COUP_PLAYER_BOTH); it is overwritten at every step (the consumer reads it
+ * between steps when n_steps == 1). */
+int coup_vec_rollout(coup_vec_env* env, int n_steps, int encode_player, int dtype, void* d_tensor_out,
+                     void* stream);
+
+/* ---- per-env outputs of the last reset/step (device pointers owned by the handle) --------------- */
+const uint32_t* coup_vec_legal_mask(const coup_vec_env* env);  /* LegalActions() as bit a, coup.cc:824-938 */
+const int8_t* coup_vec_current_player(const coup_vec_env* env); /* 0, 1 or -4 terminal, coup.cc:458-466 */
+const uint8_t* coup_vec_done(const coup_vec_env* env);          /* IsTerminal() of the state just stepped */
+const int8_t* coup_vec_rewards(const coup_vec_env* env);        /* [num_envs][2] Rewards(), coup.cc:1012-1014 */
+const int8_t* coup_vec_returns(const coup_vec_env* env);        /* [num_envs][2] Returns(), coup.cc:1016-1032 */
+uint32_t* coup_vec_state(coup_vec_env* env);                    /* [num_envs][4], layout above */
+uint32_t* coup_vec_history(coup_vec_env* env);                  /* [num_envs][16], layout above */
+
+/* ---- legal actions as a dense mask (State::LegalActionsMask, spiel.cc:371-377):
+ * uint8[num_envs][18] on the device, 1 where legal. */
+int coup_vec_legal_actions_mask(coup_vec_env* env, uint8_t* d_out, void* stream);
+
+/* ---- tensors (CoupState::InformationStateTensor / ObservationTensor, coup.cc:1044-1056, i.e.
+ * CoupObserver::WriteTensor coup.cc:248-287). d_out: dtype[rows][2492 or 98] on the device, fully
+ * overwritten (the reference's ContiguousAllocator zero-fills first, observer.h:175-177). */
+int coup_vec_information_state_tensor(coup_vec_env* env, int player, int dtype, void* d_out, void* stream);
+int coup_vec_observation_tensor(coup_vec_env* env, int player, int dtype, void* d_out, void* stream);
+
+/* ---- host-buffer convenience path (what a host-driven caller such as rl_environment would use):
+ * copies uint8[num_envs] actions from (pinned) host memory, steps, optionally encodes the current
+ * player's info-state into d_tensor_out (device; may be NULL) and copies legal_mask / current_player /
+ * done / rewards back into the host buffers (each may be NULL). Synchronises the stream. */
+int coup_vec_step_host(coup_vec_env* env, const uint8_t* h_actions, uint32_t* h_legal_mask,
+                       int8_t* h_current_player, uint8_t* h_done, int8_t* h_rewards, int dtype,
+                       void* d_tensor_out, void* stream);
+
+/* Host-side uniform-random POLICY for callers that keep their policy on the host (the host analogue of
+ * benchmark_game.cc:96-99): for every env picks the k-th set bit of h_legal_mask[i], k drawn from the same
+ * Philox stream coup_vec_sample_uniform would use at step counter `step`; 0xFF where the mask is 0.
+ * Pure bit selection on host memory with `threads` host threads -- no game rule is evaluated. */
+int coup_host_sample_uniform(const uint32_t* h_legal_mask, uint32_t n, uint64_t seed, uint64_t global_env_offset,
+                             uint64_t step, uint8_t* h_actions_out, int threads);
+
+/* ---- statistics, errors, verification ---------------------------------------------------------- */
+int coup_vec_stats(coup_vec_env* env, uint64_t* h_out /* [COUP_STATS_LEN] */, void* stream);
+uint64_t* coup_vec_stats_device(coup_vec_env* env); /* uint64[COUP_STATS_LEN] for an NCCL all-reduce */
+int coup_vec_clear_stats(coup_vec_env* env, void* stream);
+int coup_vec_check_errors(coup_vec_env* env, void* stream); /* COUP_OK or COUP_ERR_ILLEGAL_ACTION */
+/* 64-bit position-keyed hash of every row of a dense float tensor already in device memory
+ * (h = sum over non-zero t[i] of mix64(i << 32 | bits(t[i]))); used to compare 10^6-trajectory runs
+ * against the oracle without moving the tensors. d_hash_out: uint64[rows]. */
+int coup_tensor_row_hash(const void* d_tensor, int dtype, uint32_t rows, uint32_t row_len,
+                         uint64_t* d_hash_out, void* stream);
+
+/* Global step counter that keys the Philox streams (snapshot = state + history + this counter). */
+uint64_t coup_vec_step_counter(const coup_vec_env* env);
+int coup_vec_set_step_counter(coup_vec_env* env, uint64_t value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COUP_B200_H_ */

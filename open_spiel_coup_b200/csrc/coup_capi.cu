@@ -1,0 +1,338 @@
+// coup_capi.cu -- C ABI (include/coup_b200.h) of the batched Coup environment: host runtime that owns
+// the device slab of one GPU and launches the sm_100a kernels in coup_kernels.cuh. No game rule is
+// evaluated on the host anywhere in this file.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <algorithm>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "coup_kernels.cuh"
+
+using namespace coup;
+
+struct coup_vec_env {
+  coup_vec_opts opts;
+  EnvArrays A;
+  uint8_t* d_actions;   // staging for coup_vec_step_host
+  uint64_t step_counter;
+};
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(int code, const std::string& msg) {
+  g_error = msg;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                   \
+  do {                                                                                   \
+    cudaError_t err__ = (expr);                                                          \
+    if (err__ != cudaSuccess)                                                            \
+      return fail(COUP_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(err__)); \
+  } while (0)
+
+// Makes the handle's device current for the duration of a call and restores the caller's.
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+    if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+  }
+};
+
+inline cudaStream_t S(void* stream) { return static_cast<cudaStream_t>(stream); }
+inline unsigned blocks_for(size_t threads) { return static_cast<unsigned>((threads + kBlockThreads - 1) / kBlockThreads); }
+
+int launch_status(const char* what) {
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return fail(COUP_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(err));
+  return COUP_OK;
+}
+
+bool valid_player_sel(int p) { return p >= COUP_PLAYER_0 && p <= COUP_PLAYER_BOTH; }
+bool valid_dtype(int d) { return d == COUP_DTYPE_F32 || d == COUP_DTYPE_U8 || d == COUP_DTYPE_BF16; }
+
+template <typename T>
+int rollout_typed(coup_vec_env* env, int n_steps, int encode_player, void* d_out, cudaStream_t st) {
+  const unsigned grid = blocks_for(env->A.n);
+  for (int i = 0; i < n_steps; ++i) {
+    if (encode_player >= 0)
+      k_rollout<T, true><<<grid, kBlockThreads, 0, st>>>(env->A, env->step_counter, encode_player, static_cast<T*>(d_out));
+    else
+      k_rollout<T, false><<<grid, kBlockThreads, 0, st>>>(env->A, env->step_counter, 0, static_cast<T*>(nullptr));
+    env->step_counter++;
+  }
+  return launch_status("k_rollout");
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* coup_last_error(void) { return g_error.c_str(); }
+
+int coup_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int coup_vec_create(const coup_vec_opts* opts, coup_vec_env** out) {
+  if (!opts || !out || opts->num_envs == 0) return fail(COUP_ERR_INVALID_ARG, "coup_vec_create: bad arguments");
+  *out = nullptr;
+  int ndev = coup_device_count();
+  if (ndev == 0) return fail(COUP_ERR_NO_DEVICE, "no CUDA device: this library has no CPU path");
+  if (opts->device < 0 || opts->device >= ndev) return fail(COUP_ERR_INVALID_ARG, "coup_vec_create: bad device ordinal");
+  DeviceGuard guard(opts->device);
+  if (!guard.ok) return fail(COUP_ERR_CUDA, "cudaSetDevice failed");
+  coup_vec_env* env = new (std::nothrow) coup_vec_env();
+  if (!env) return fail(COUP_ERR_INVALID_ARG, "out of host memory");
+  env->opts = *opts;
+  env->step_counter = 0;
+  const size_t n = opts->num_envs;
+  EnvArrays& A = env->A;
+  std::memset(&A, 0, sizeof(A));
+  A.n = opts->num_envs;
+  A.flags = opts->flags;
+  A.seed = opts->seed;
+  A.global_env_offset = opts->global_env_offset;
+  cudaError_t err = cudaSuccess;
+  auto alloc = [&](void** p, size_t bytes) { if (err == cudaSuccess) err = cudaMalloc(p, bytes); };
+  alloc(reinterpret_cast<void**>(&A.state), n * sizeof(uint4));
+  alloc(reinterpret_cast<void**>(&A.history), n * kHistoryWords * sizeof(uint32_t));
+  alloc(reinterpret_cast<void**>(&A.legal), n * sizeof(uint32_t));
+  alloc(reinterpret_cast<void**>(&A.cur_player), n);
+  alloc(reinterpret_cast<void**>(&A.done), n);
+  alloc(reinterpret_cast<void**>(&A.rewards), n * 2);
+  alloc(reinterpret_cast<void**>(&A.returns), n * 2);
+  alloc(reinterpret_cast<void**>(&A.stats), COUP_STATS_LEN * sizeof(unsigned long long));
+  alloc(reinterpret_cast<void**>(&env->d_actions), n);
+  if (err == cudaSuccess) err = cudaMemset(A.stats, 0, COUP_STATS_LEN * sizeof(unsigned long long));
+  if (err == cudaSuccess) err = cudaMemset(A.history, 0, n * kHistoryWords * sizeof(uint32_t));
+  if (err != cudaSuccess) {
+    std::string msg = std::string("coup_vec_create: ") + cudaGetErrorString(err);
+    coup_vec_destroy(env);
+    return fail(COUP_ERR_CUDA, msg);
+  }
+  *out = env;
+  // Every env starts as a freshly dealt episode.
+  int rc = coup_vec_reset(env, nullptr, nullptr, nullptr);
+  if (rc == COUP_OK && cudaStreamSynchronize(nullptr) != cudaSuccess) rc = fail(COUP_ERR_CUDA, "initial reset failed");
+  if (rc != COUP_OK) { coup_vec_destroy(env); *out = nullptr; }
+  return rc;
+}
+
+int coup_vec_destroy(coup_vec_env* env) {
+  if (!env) return COUP_OK;
+  DeviceGuard guard(env->opts.device);
+  cudaFree(env->A.state); cudaFree(env->A.history); cudaFree(env->A.legal); cudaFree(env->A.cur_player);
+  cudaFree(env->A.done); cudaFree(env->A.rewards); cudaFree(env->A.returns); cudaFree(env->A.stats);
+  cudaFree(env->d_actions);
+  delete env;
+  return COUP_OK;
+}
+
+uint32_t coup_vec_num_envs(const coup_vec_env* env) { return env ? env->A.n : 0; }
+
+int coup_vec_reset(coup_vec_env* env, const uint8_t* d_reset_mask, const uint8_t* d_forced_deals, void* stream) {
+  if (!env) return fail(COUP_ERR_INVALID_ARG, "null handle");
+  DeviceGuard guard(env->opts.device);
+  k_reset<<<blocks_for(env->A.n), kBlockThreads, 0, S(stream)>>>(env->A, d_reset_mask, d_forced_deals, env->step_counter);
+  env->step_counter++;
+  return launch_status("k_reset");
+}
+
+int coup_vec_step(coup_vec_env* env, const uint8_t* d_actions, const uint8_t* d_forced_chance, void* stream) {
+  if (!env || !d_actions) return fail(COUP_ERR_INVALID_ARG, "coup_vec_step: null argument");
+  DeviceGuard guard(env->opts.device);
+  k_step<<<blocks_for(env->A.n), kBlockThreads, 0, S(stream)>>>(env->A, d_actions, d_forced_chance, env->step_counter);
+  env->step_counter++;
+  return launch_status("k_step");
+}
+
+int coup_vec_sample_uniform(coup_vec_env* env, uint8_t* d_actions_out, void* stream) {
+  if (!env || !d_actions_out) return fail(COUP_ERR_INVALID_ARG, "coup_vec_sample_uniform: null argument");
+  DeviceGuard guard(env->opts.device);
+  // Uses the x word of the Philox block the NEXT step will consume (same counter, not advanced), so
+  // sample_uniform + step reproduces exactly what coup_vec_rollout does in one kernel.
+  k_sample_uniform<<<blocks_for(env->A.n), kBlockThreads, 0, S(stream)>>>(env->A, d_actions_out, env->step_counter);
+  return launch_status("k_sample_uniform");
+}
+
+int coup_vec_rollout(coup_vec_env* env, int n_steps, int encode_player, int dtype, void* d_tensor_out, void* stream) {
+  if (!env || n_steps < 0) return fail(COUP_ERR_INVALID_ARG, "coup_vec_rollout: bad arguments");
+  if (encode_player >= 0 && (!valid_player_sel(encode_player) || !valid_dtype(dtype) || !d_tensor_out))
+    return fail(COUP_ERR_INVALID_ARG, "coup_vec_rollout: bad encode arguments");
+  DeviceGuard guard(env->opts.device);
+  if (encode_player < 0) return rollout_typed<float>(env, n_steps, -1, nullptr, S(stream));
+  switch (dtype) {
+    case COUP_DTYPE_F32: return rollout_typed<float>(env, n_steps, encode_player, d_tensor_out, S(stream));
+    case COUP_DTYPE_U8: return rollout_typed<uint8_t>(env, n_steps, encode_player, d_tensor_out, S(stream));
+    default: return rollout_typed<__nv_bfloat16>(env, n_steps, encode_player, d_tensor_out, S(stream));
+  }
+}
+
+const uint32_t* coup_vec_legal_mask(const coup_vec_env* env) { return env ? env->A.legal : nullptr; }
+const int8_t* coup_vec_current_player(const coup_vec_env* env) { return env ? env->A.cur_player : nullptr; }
+const uint8_t* coup_vec_done(const coup_vec_env* env) { return env ? env->A.done : nullptr; }
+const int8_t* coup_vec_rewards(const coup_vec_env* env) { return env ? env->A.rewards : nullptr; }
+const int8_t* coup_vec_returns(const coup_vec_env* env) { return env ? env->A.returns : nullptr; }
+uint32_t* coup_vec_state(coup_vec_env* env) { return env ? reinterpret_cast<uint32_t*>(env->A.state) : nullptr; }
+uint32_t* coup_vec_history(coup_vec_env* env) { return env ? env->A.history : nullptr; }
+
+int coup_vec_legal_actions_mask(coup_vec_env* env, uint8_t* d_out, void* stream) {
+  if (!env || !d_out) return fail(COUP_ERR_INVALID_ARG, "coup_vec_legal_actions_mask: null argument");
+  DeviceGuard guard(env->opts.device);
+  k_legal_actions_mask<<<blocks_for(static_cast<size_t>(env->A.n) * kNumActions), kBlockThreads, 0, S(stream)>>>(
+      env->A.legal, d_out, env->A.n);
+  return launch_status("k_legal_actions_mask");
+}
+
+int coup_vec_information_state_tensor(coup_vec_env* env, int player, int dtype, void* d_out, void* stream) {
+  if (!env || !d_out || !valid_player_sel(player) || !valid_dtype(dtype))
+    return fail(COUP_ERR_INVALID_ARG, "coup_vec_information_state_tensor: bad arguments");
+  DeviceGuard guard(env->opts.device);
+  const unsigned grid = (env->A.n + 32 * kWarpsPerBlock - 1) / (32 * kWarpsPerBlock);
+  switch (dtype) {
+    case COUP_DTYPE_F32:
+      k_encode_info<float><<<grid, kBlockThreads, 0, S(stream)>>>(env->A.state, env->A.history, env->A.n, player, static_cast<float*>(d_out));
+      break;
+    case COUP_DTYPE_U8:
+      k_encode_info<uint8_t><<<grid, kBlockThreads, 0, S(stream)>>>(env->A.state, env->A.history, env->A.n, player, static_cast<uint8_t*>(d_out));
+      break;
+    default:
+      k_encode_info<__nv_bfloat16><<<grid, kBlockThreads, 0, S(stream)>>>(env->A.state, env->A.history, env->A.n, player, static_cast<__nv_bfloat16*>(d_out));
+      break;
+  }
+  return launch_status("k_encode_info");
+}
+
+int coup_vec_observation_tensor(coup_vec_env* env, int player, int dtype, void* d_out, void* stream) {
+  if (!env || !d_out || !valid_player_sel(player) || !valid_dtype(dtype))
+    return fail(COUP_ERR_INVALID_ARG, "coup_vec_observation_tensor: bad arguments");
+  DeviceGuard guard(env->opts.device);
+  const unsigned grid = (env->A.n + 32 * kWarpsPerBlock - 1) / (32 * kWarpsPerBlock);
+  switch (dtype) {
+    case COUP_DTYPE_F32:
+      k_encode_obs<float><<<grid, kBlockThreads, 0, S(stream)>>>(env->A.state, env->A.n, player, static_cast<float*>(d_out));
+      break;
+    case COUP_DTYPE_U8:
+      k_encode_obs<uint8_t><<<grid, kBlockThreads, 0, S(stream)>>>(env->A.state, env->A.n, player, static_cast<uint8_t*>(d_out));
+      break;
+    default:
+      k_encode_obs<__nv_bfloat16><<<grid, kBlockThreads, 0, S(stream)>>>(env->A.state, env->A.n, player, static_cast<__nv_bfloat16*>(d_out));
+      break;
+  }
+  return launch_status("k_encode_obs");
+}
+
+int coup_vec_step_host(coup_vec_env* env, const uint8_t* h_actions, uint32_t* h_legal_mask, int8_t* h_current_player,
+                       uint8_t* h_done, int8_t* h_rewards, int dtype, void* d_tensor_out, void* stream) {
+  if (!env || !h_actions) return fail(COUP_ERR_INVALID_ARG, "coup_vec_step_host: null argument");
+  DeviceGuard guard(env->opts.device);
+  cudaStream_t st = S(stream);
+  const size_t n = env->A.n;
+  CUDA_TRY(cudaMemcpyAsync(env->d_actions, h_actions, n, cudaMemcpyHostToDevice, st));
+  int rc = coup_vec_step(env, env->d_actions, nullptr, stream);
+  if (rc != COUP_OK) return rc;
+  if (d_tensor_out) {
+    rc = coup_vec_information_state_tensor(env, COUP_PLAYER_CURRENT, dtype, d_tensor_out, stream);
+    if (rc != COUP_OK) return rc;
+  }
+  if (h_legal_mask) CUDA_TRY(cudaMemcpyAsync(h_legal_mask, env->A.legal, n * 4, cudaMemcpyDeviceToHost, st));
+  if (h_current_player) CUDA_TRY(cudaMemcpyAsync(h_current_player, env->A.cur_player, n, cudaMemcpyDeviceToHost, st));
+  if (h_done) CUDA_TRY(cudaMemcpyAsync(h_done, env->A.done, n, cudaMemcpyDeviceToHost, st));
+  if (h_rewards) CUDA_TRY(cudaMemcpyAsync(h_rewards, env->A.rewards, n * 2, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return COUP_OK;
+}
+
+int coup_host_sample_uniform(const uint32_t* h_legal_mask, uint32_t n, uint64_t seed, uint64_t global_env_offset,
+                             uint64_t step, uint8_t* h_actions_out, int threads) {
+  if (!h_legal_mask || !h_actions_out) return fail(COUP_ERR_INVALID_ARG, "coup_host_sample_uniform: null argument");
+  threads = threads < 1 ? 1 : threads;
+  auto work = [=](uint32_t lo, uint32_t hi) {
+    for (uint32_t i = lo; i < hi; ++i) {
+      const uint32_t legal = h_legal_mask[i];
+      if (legal == 0) { h_actions_out[i] = 0xFF; continue; }
+      const uint32_t x = env_random(seed, global_env_offset + i, step, 0).x;
+      uint32_t k = mulhi32(x, static_cast<uint32_t>(__builtin_popcount(legal)));
+      uint32_t m = legal;
+      while (k--) m &= m - 1;  // drop the k lowest set bits
+      h_actions_out[i] = static_cast<uint8_t>(__builtin_ctz(m));
+    }
+  };
+  if (threads == 1 || n < 4096) { work(0, n); return COUP_OK; }
+  std::vector<std::thread> pool;
+  const uint32_t chunk = (n + threads - 1) / threads;
+  for (int t = 0; t < threads; ++t) {
+    const uint32_t lo = std::min<uint64_t>(n, static_cast<uint64_t>(t) * chunk), hi = std::min<uint64_t>(n, static_cast<uint64_t>(lo) + chunk);
+    if (lo < hi) pool.emplace_back(work, lo, hi);
+  }
+  for (auto& th : pool) th.join();
+  return COUP_OK;
+}
+
+int coup_vec_stats(coup_vec_env* env, uint64_t* h_out, void* stream) {
+  if (!env || !h_out) return fail(COUP_ERR_INVALID_ARG, "coup_vec_stats: null argument");
+  DeviceGuard guard(env->opts.device);
+  CUDA_TRY(cudaMemcpyAsync(h_out, env->A.stats, COUP_STATS_LEN * sizeof(uint64_t), cudaMemcpyDeviceToHost, S(stream)));
+  CUDA_TRY(cudaStreamSynchronize(S(stream)));
+  return COUP_OK;
+}
+
+uint64_t* coup_vec_stats_device(coup_vec_env* env) { return env ? reinterpret_cast<uint64_t*>(env->A.stats) : nullptr; }
+
+int coup_vec_clear_stats(coup_vec_env* env, void* stream) {
+  if (!env) return fail(COUP_ERR_INVALID_ARG, "null handle");
+  DeviceGuard guard(env->opts.device);
+  CUDA_TRY(cudaMemsetAsync(env->A.stats, 0, COUP_STATS_LEN * sizeof(uint64_t), S(stream)));
+  return COUP_OK;
+}
+
+int coup_vec_check_errors(coup_vec_env* env, void* stream) {
+  uint64_t stats[COUP_STATS_LEN];
+  int rc = coup_vec_stats(env, stats, stream);
+  if (rc != COUP_OK) return rc;
+  if (stats[COUP_STAT_ILLEGAL] != 0)
+    return fail(COUP_ERR_ILLEGAL_ACTION, std::to_string(stats[COUP_STAT_ILLEGAL]) + " illegal action(s) rejected");
+  return COUP_OK;
+}
+
+int coup_tensor_row_hash(const void* d_tensor, int dtype, uint32_t rows, uint32_t row_len, uint64_t* d_hash_out, void* stream) {
+  if (!d_tensor || !d_hash_out || !valid_dtype(dtype)) return fail(COUP_ERR_INVALID_ARG, "coup_tensor_row_hash: bad arguments");
+  const unsigned grid = (rows + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  switch (dtype) {
+    case COUP_DTYPE_F32:
+      k_row_hash<float><<<grid, kBlockThreads, 0, S(stream)>>>(static_cast<const float*>(d_tensor), rows, row_len, d_hash_out);
+      break;
+    case COUP_DTYPE_U8:
+      k_row_hash<uint8_t><<<grid, kBlockThreads, 0, S(stream)>>>(static_cast<const uint8_t*>(d_tensor), rows, row_len, d_hash_out);
+      break;
+    default:
+      k_row_hash<__nv_bfloat16><<<grid, kBlockThreads, 0, S(stream)>>>(static_cast<const __nv_bfloat16*>(d_tensor), rows, row_len, d_hash_out);
+      break;
+  }
+  return launch_status("k_row_hash");
+}
+
+uint64_t coup_vec_step_counter(const coup_vec_env* env) { return env ? env->step_counter : 0; }
+int coup_vec_set_step_counter(coup_vec_env* env, uint64_t value) {
+  if (!env) return fail(COUP_ERR_INVALID_ARG, "null handle");
+  env->step_counter = value;
+  return COUP_OK;
+}
+
+}  // extern "C"

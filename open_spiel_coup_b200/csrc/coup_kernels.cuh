@@ -1,0 +1,453 @@
+// coup_kernels.cuh -- sm_100a kernels of the batched Coup environment.
+//
+// Thread mapping: one thread per environment for the rules (16-byte state load/store, coalesced),
+// one warp per 32 consecutive environments for the tensor encoders (the 32 rows of a warp are one
+// contiguous span of the output, written with full-width vector stores). No tensor cores: there is no
+// contraction anywhere on this path; every kernel is bounded by HBM traffic or instruction issue.
+#pragma once
+#include <cuda_bf16.h>
+
+#include "coup_device.cuh"
+#include "../../include/coup_b200.h"
+
+namespace coup {
+
+constexpr int kBlockThreads = 256;
+constexpr int kWarpsPerBlock = kBlockThreads / 32;
+constexpr int kUnitsPerInfoRow = kInfoStateSize / 4;  // 623 four-element units (16 B in fp32)
+constexpr int kRecWords = 21;                         // per-env encoder record in shared memory
+
+struct EnvArrays {
+  uint4* state;        // [n]
+  uint32_t* history;   // [n][16]
+  uint32_t* legal;     // [n]
+  int8_t* cur_player;  // [n]
+  uint8_t* done;       // [n]
+  int8_t* rewards;     // [n][2]
+  int8_t* returns;     // [n][2]
+  unsigned long long* stats;  // [COUP_STATS_LEN]
+  uint32_t n;
+  uint32_t flags;
+  uint64_t seed;
+  uint64_t global_env_offset;
+};
+
+__device__ __forceinline__ Env load_env(const uint4* p) {
+  uint4 v = *p;
+  Env s;
+  s.p[0] = v.x; s.p[1] = v.y; s.g = v.z; s.c = v.w;
+  return s;
+}
+__device__ __forceinline__ void store_env(uint4* p, const Env& s) { *p = make_uint4(s.p[0], s.p[1], s.g, s.c); }
+
+// ---- statistics: warp ballots -> shared counters -> one global atomic per counter per block ------
+struct BlockStats {
+  uint32_t* sm;  // [COUP_STATS_LEN] in shared memory
+  __device__ __forceinline__ void init(uint32_t* shared) {
+    sm = shared;
+    for (int i = threadIdx.x; i < COUP_STATS_LEN; i += blockDim.x) sm[i] = 0;
+    __syncthreads();
+  }
+  // All 32 lanes of the warp must call these (inactive envs pass pred=false / value 0).
+  __device__ __forceinline__ void count(int idx, bool pred) {
+    uint32_t b = __ballot_sync(0xffffffffu, pred);
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(&sm[idx], __popc(b));
+  }
+  __device__ __forceinline__ void sum(int idx, uint32_t v) {
+    v = __reduce_add_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(&sm[idx], v);
+  }
+  // Histogram over `nb` bins of a value known to be < nb for lanes with pred set.
+  __device__ __forceinline__ void hist(int base, int nb, uint32_t value, bool pred) {
+    for (int b = 0; b < nb; ++b) count(base + b, pred && value == static_cast<uint32_t>(b));
+  }
+  __device__ __forceinline__ void flush(unsigned long long* global) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < COUP_STATS_LEN; i += blockDim.x)
+      if (sm[i]) atomicAdd(&global[i], static_cast<unsigned long long>(sm[i]));
+  }
+};
+
+// ---- the per-env step, shared by k_step and k_rollout --------------------------------------------
+struct StepResult {
+  uint32_t legal;     // legal mask of the state left in `s`
+  int cur_player;     // 0/1/-4
+  bool done;          // the state reached by this step was terminal (reported even if auto-reset)
+  int reward0;        // Rewards()[0] of the stepped state
+  int return0;        // Returns()[0] of the stepped state
+  bool stepped;       // a player action was applied
+  bool illegal;
+  uint32_t n_legal_before;
+  uint32_t chance_moves;
+  bool finished;      // an episode ended in this call
+  bool truncated;
+  uint32_t final_moves;
+};
+
+// Re-deal a fresh episode into `s` (CoupState ctor + the 4 initial chance nodes).
+__device__ __forceinline__ uint32_t deal_new_episode(Env& s, uint32_t* hist_row, const uint4& rnd,
+                                                     const uint8_t* forced) {
+  s = initial_state();
+  HistoryWriter hw(hist_row);
+  uint32_t k = resolve_chance(s, rnd, 0, forced, hw);
+  hw.flush();
+  return k;
+}
+
+template <bool kSample>
+__device__ __forceinline__ StepResult step_env(Env& s, uint32_t* hist_row, uint32_t action_in,
+                                               const uint8_t* forced, const EnvArrays& A, uint32_t e,
+                                               uint64_t step) {
+  StepResult r;
+  r.stepped = false; r.illegal = false; r.n_legal_before = 0; r.chance_moves = 0;
+  r.finished = false; r.truncated = false; r.final_moves = 0;
+  const uint64_t genv = A.global_env_offset + e;
+  bool term = is_terminal(s);
+  if (!term) {
+    const uint32_t legal = legal_mask_decision(s);
+    const uint4 rnd = env_random(A.seed, genv, step, 0);
+    uint32_t a = kSample ? sample_action(legal, rnd.x) : action_in;
+    r.n_legal_before = __popc(legal);
+    if (a < 18u && ((legal >> a) & 1u)) {
+      HistoryWriter hw(hist_row);
+      apply_player_action(s, a, hw);
+      r.chance_moves = resolve_chance(s, rnd, 1, forced, hw);
+      hw.flush();
+      r.stepped = true;
+      term = is_terminal(s);
+      if (term) {
+        r.finished = true;
+        r.final_moves = c_moves(s.c);
+        r.truncated = r.final_moves > kMaxGameLength;
+      }
+    } else {
+      s.g |= kBitError;  // sticky; the reference would SpielFatalError / raise (rl_environment.py:270-280)
+      r.illegal = true;
+    }
+  }
+  r.done = term;
+  r.reward0 = c_reward0(s.c);
+  r.return0 = returns_p0(s);
+  if (r.finished && (A.flags & COUP_FLAG_AUTO_RESET)) {
+    const uint4 rr = env_random(A.seed, genv, step, 1);
+    r.chance_moves += deal_new_episode(s, hist_row, rr, nullptr);
+    term = false;
+  }
+  r.legal = term ? 0u : legal_mask_decision(s);
+  r.cur_player = term ? COUP_TERMINAL_PLAYER_ID : static_cast<int>(g_mover(s.g));
+  return r;
+}
+
+__device__ __forceinline__ void write_outputs(const EnvArrays& A, uint32_t e, const StepResult& r) {
+  A.legal[e] = r.legal;
+  A.cur_player[e] = static_cast<int8_t>(r.cur_player);
+  A.done[e] = r.done ? 1 : 0;
+  reinterpret_cast<char2*>(A.rewards)[e] = make_char2(static_cast<signed char>(r.reward0), static_cast<signed char>(-r.reward0));
+  reinterpret_cast<char2*>(A.returns)[e] = make_char2(static_cast<signed char>(r.return0), static_cast<signed char>(-r.return0));
+}
+
+__device__ __forceinline__ void account(BlockStats& st, const StepResult& r, bool active) {
+  st.count(COUP_STAT_DECISION_STEPS, active && r.stepped);
+  st.sum(COUP_STAT_CHANCE_MOVES, active ? r.chance_moves : 0u);
+  st.count(COUP_STAT_EPISODES, active && r.finished);
+  st.count(COUP_STAT_TRUNCATED, active && r.truncated);
+  st.sum(COUP_STAT_EPISODE_MOVES, active ? r.final_moves : 0u);
+  st.count(COUP_STAT_ILLEGAL, active && r.illegal);
+  st.hist(COUP_STAT_RETURN_HIST, 5, static_cast<uint32_t>(r.return0 + 2), active && r.finished);
+  st.hist(COUP_STAT_LEGAL_HIST, 8, min(r.n_legal_before, 7u), active && r.stepped);
+}
+
+// ---- reset -------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlockThreads)
+k_reset(EnvArrays A, const uint8_t* __restrict__ mask, const uint8_t* __restrict__ forced, uint64_t step) {
+  __shared__ uint32_t s_stats[COUP_STATS_LEN];
+  BlockStats st;
+  st.init(s_stats);
+  const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = e < A.n && (mask == nullptr || mask[e] != 0);
+  uint32_t dealt = 0;
+  if (active) {
+    Env s;
+    const uint4 rnd = env_random(A.seed, A.global_env_offset + e, step, 1);
+    dealt = deal_new_episode(s, A.history + static_cast<size_t>(e) * kHistoryWords, rnd,
+                             forced ? forced + static_cast<size_t>(e) * 4 : nullptr);
+    store_env(A.state + e, s);
+    StepResult r;
+    r.legal = legal_mask_decision(s);
+    r.cur_player = static_cast<int>(g_mover(s.g));
+    r.done = false; r.reward0 = 0; r.return0 = 0;
+    write_outputs(A, e, r);
+  }
+  st.sum(COUP_STAT_CHANCE_MOVES, dealt);
+  st.flush(A.stats);
+}
+
+// ---- step with caller-provided actions --------------------------------------------------------------
+__global__ void __launch_bounds__(kBlockThreads)
+k_step(EnvArrays A, const uint8_t* __restrict__ actions, const uint8_t* __restrict__ forced, uint64_t step) {
+  __shared__ uint32_t s_stats[COUP_STATS_LEN];
+  BlockStats st;
+  st.init(s_stats);
+  const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = e < A.n;
+  StepResult r = {};
+  if (active) {
+    Env s = load_env(A.state + e);
+    r = step_env<false>(s, A.history + static_cast<size_t>(e) * kHistoryWords, actions[e],
+                        forced ? forced + static_cast<size_t>(e) * 4 : nullptr, A, e, step);
+    store_env(A.state + e, s);
+    write_outputs(A, e, r);
+  }
+  account(st, r, active);
+  st.flush(A.stats);
+}
+
+// ---- uniform-random legal action (same draw the fused rollout would use at this step counter) ------
+__global__ void __launch_bounds__(kBlockThreads)
+k_sample_uniform(EnvArrays A, uint8_t* __restrict__ actions_out, uint64_t step) {
+  const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= A.n) return;
+  const Env s = load_env(A.state + e);
+  uint32_t a = 0xFFu;
+  if (!is_terminal(s)) {
+    const uint4 rnd = env_random(A.seed, A.global_env_offset + e, step, 0);
+    a = sample_action(legal_mask_decision(s), rnd.x);
+  }
+  actions_out[e] = static_cast<uint8_t>(a);
+}
+
+// ---- dense legal mask: uint8[n][18] (State::LegalActionsMask, spiel.cc:371-377) ----------------------
+__global__ void __launch_bounds__(kBlockThreads)
+k_legal_actions_mask(const uint32_t* __restrict__ legal, uint8_t* __restrict__ out, uint32_t n) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<size_t>(n) * kNumActions) return;
+  const uint32_t e = static_cast<uint32_t>(i / kNumActions), a = static_cast<uint32_t>(i - static_cast<size_t>(e) * kNumActions);
+  out[i] = (legal[e] >> a) & 1u;
+}
+
+// ---- tensor element types ------------------------------------------------------------------------
+template <typename T> struct Unit4;  // four consecutive tensor elements
+template <> struct Unit4<float> {
+  using type = float4;
+  static __device__ __forceinline__ type make(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    return make_float4(static_cast<float>(a), static_cast<float>(b), static_cast<float>(c), static_cast<float>(d));
+  }
+};
+template <> struct Unit4<uint8_t> {
+  using type = uint32_t;
+  static __device__ __forceinline__ type make(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    return a | (b << 8) | (c << 16) | (d << 24);
+  }
+};
+template <> struct Unit4<__nv_bfloat16> {
+  using type = uint2;
+  // bf16 of a small non-negative integer = the top half of its fp32 encoding (exact for 0..255).
+  static __device__ __forceinline__ uint32_t bits(uint32_t v) { return __float_as_uint(static_cast<float>(v)) >> 16; }
+  static __device__ __forceinline__ type make(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    return make_uint2(bits(a) | (bits(b) << 16), bits(c) | (bits(d) << 16));
+  }
+};
+
+// ---- info-state encoder ----------------------------------------------------------------------------
+// Shared-memory record of one env, filled by the lane that owns the env:
+//   [0,16) history words  [16,18) head mask of view A  [18,20) head mask of view B
+//   [20] len | coins0<<8 | coins1<<16 | viewA_observer<<24 | viewB_observer<<25
+__device__ __forceinline__ void fill_record(uint32_t* rec, const Env& s, const uint32_t* hist_row,
+                                            int player_sel) {
+  const uint4* h4 = reinterpret_cast<const uint4*>(hist_row);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    uint4 v = h4[k];
+    rec[4 * k + 0] = v.x; rec[4 * k + 1] = v.y; rec[4 * k + 2] = v.z; rec[4 * k + 3] = v.w;
+  }
+  const bool term = is_terminal(s);
+  const uint32_t obs_a = player_sel == COUP_PLAYER_1 ? 1u
+                        : player_sel == COUP_PLAYER_CURRENT ? g_mover(s.g) : 0u;
+  const uint32_t obs_b = 1u;
+  const uint64_t ma = head_mask(s, obs_a, term);
+  rec[16] = static_cast<uint32_t>(ma); rec[17] = static_cast<uint32_t>(ma >> 32);
+  if (player_sel == COUP_PLAYER_BOTH) {
+    const uint64_t mb = head_mask(s, obs_b, term);
+    rec[18] = static_cast<uint32_t>(mb); rec[19] = static_cast<uint32_t>(mb >> 32);
+  }
+  rec[20] = c_moves(s.c) | (pw_coins(s.p[0]) << 8) | (pw_coins(s.p[1]) << 16) | (obs_a << 24) | (obs_b << 25);
+}
+
+// Value of info-state element `p` (0..2491) of a record/view. Small non-negative integer.
+__device__ __forceinline__ uint32_t info_value(const uint32_t* rec, uint64_t mask, uint32_t meta,
+                                               uint32_t observer, uint32_t p) {
+  if (p < 60u) return static_cast<uint32_t>(mask >> p) & 1u;
+  if (p < 62u) return (meta >> (8u + 8u * (p - 60u))) & 255u;        // WriteCoins, 207-213
+  const uint32_t i = (p - 62u) / 18u, a = (p - 62u) - 18u * i;       // WriteActionHistory, 230-245
+  if (i >= (meta & 255u)) return 0u;
+  const uint32_t w = i / 6u;
+  const uint32_t code = (rec[w] >> (5u * (i - 6u * w))) & 31u;
+  return history_column(code, observer) == a ? 1u : 0u;
+}
+
+// The warp writes `nrows` consecutive rows (row r of the warp -> record r>>both, view r&both) starting at
+// out_row0. Rows are 623 units of four elements; within a row lane l handles units l, l+32, ...
+template <typename T>
+__device__ __forceinline__ void warp_encode_info(const uint32_t* recs, int nrec, bool both,
+                                                 typename Unit4<T>::type* out_units, int lane) {
+  using U = typename Unit4<T>::type;
+  const int nrows = both ? 2 * nrec : nrec;
+  for (int r = 0; r < nrows; ++r) {
+    const uint32_t* rec = recs + (both ? (r >> 1) : r) * kRecWords;
+    const int view = both ? (r & 1) : 0;
+    const uint32_t meta = rec[20];
+    const uint32_t observer = (meta >> (24 + view)) & 1u;
+    const uint64_t mask = static_cast<uint64_t>(rec[16 + 2 * view]) | (static_cast<uint64_t>(rec[17 + 2 * view]) << 32);
+    const int len = static_cast<int>(meta & 255u);
+    // units [0, nz_end) can hold non-zeros: the 62-float head plus `len` history rows of 18
+    const int nz_end = min(kUnitsPerInfoRow, (62 + 18 * len + 3) >> 2);
+    U* row = out_units + static_cast<size_t>(r) * kUnitsPerInfoRow;
+    int q = lane;
+    for (; q < nz_end; q += 32) {
+      const uint32_t p0 = 4u * q;
+      U v;
+      if (p0 + 3u < 60u) {
+        const uint32_t b = static_cast<uint32_t>(mask >> p0);
+        v = Unit4<T>::make(b & 1u, (b >> 1) & 1u, (b >> 2) & 1u, (b >> 3) & 1u);
+      } else {
+        v = Unit4<T>::make(info_value(rec, mask, meta, observer, p0), info_value(rec, mask, meta, observer, p0 + 1u),
+                           info_value(rec, mask, meta, observer, p0 + 2u), info_value(rec, mask, meta, observer, p0 + 3u));
+      }
+      row[q] = v;
+    }
+    const U zero = Unit4<T>::make(0, 0, 0, 0);
+#pragma unroll 4
+    for (; q < kUnitsPerInfoRow; q += 32) row[q] = zero;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kBlockThreads)
+k_encode_info(const uint4* __restrict__ state, const uint32_t* __restrict__ history, uint32_t n,
+              int player_sel, T* __restrict__ out) {
+  __shared__ uint32_t s_rec[kWarpsPerBlock][32 * kRecWords];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t e0 = (blockIdx.x * kWarpsPerBlock + warp) * 32u;
+  if (e0 >= n) return;
+  const uint32_t e = e0 + lane;
+  if (e < n) {
+    const Env s = load_env(state + e);
+    fill_record(&s_rec[warp][lane * kRecWords], s, history + static_cast<size_t>(e) * kHistoryWords, player_sel);
+  }
+  __syncwarp();
+  const int nrec = static_cast<int>(min(32u, n - e0));
+  const bool both = player_sel == COUP_PLAYER_BOTH;
+  using U = typename Unit4<T>::type;
+  U* out_units = reinterpret_cast<U*>(out) + static_cast<size_t>(e0) * (both ? 2 : 1) * kUnitsPerInfoRow;
+  warp_encode_info<T>(s_rec[warp], nrec, both, out_units, lane);
+}
+
+// ---- observation encoder (98 elements per row): one element per thread step, rows of a warp contiguous --
+template <typename T> __device__ __forceinline__ T elem_from(uint32_t v);
+template <> __device__ __forceinline__ float elem_from<float>(uint32_t v) { return static_cast<float>(v); }
+template <> __device__ __forceinline__ uint8_t elem_from<uint8_t>(uint32_t v) { return static_cast<uint8_t>(v); }
+template <> __device__ __forceinline__ __nv_bfloat16 elem_from<__nv_bfloat16>(uint32_t v) { return __float2bfloat16(static_cast<float>(v)); }
+
+template <typename T>
+__global__ void __launch_bounds__(kBlockThreads)
+k_encode_obs(const uint4* __restrict__ state, uint32_t n, int player_sel, T* __restrict__ out) {
+  // per record: head mask A (2 words), head mask B (2), last-action mask (2), coins (1)
+  __shared__ uint32_t s_rec[kWarpsPerBlock][32 * 7];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t e0 = (blockIdx.x * kWarpsPerBlock + warp) * 32u;
+  if (e0 >= n) return;
+  const uint32_t e = e0 + lane;
+  const bool both = player_sel == COUP_PLAYER_BOTH;
+  if (e < n) {
+    const Env s = load_env(state + e);
+    const bool term = is_terminal(s);
+    const uint32_t obs_a = player_sel == COUP_PLAYER_1 ? 1u : player_sel == COUP_PLAYER_CURRENT ? g_mover(s.g) : 0u;
+    uint32_t* rec = &s_rec[warp][lane * 7];
+    const uint64_t ma = head_mask(s, obs_a, term);
+    const uint64_t mb = both ? head_mask(s, 1u, term) : 0ull;
+    const uint64_t la = last_action_mask(s);
+    rec[0] = static_cast<uint32_t>(ma); rec[1] = static_cast<uint32_t>(ma >> 32);
+    rec[2] = static_cast<uint32_t>(mb); rec[3] = static_cast<uint32_t>(mb >> 32);
+    rec[4] = static_cast<uint32_t>(la); rec[5] = static_cast<uint32_t>(la >> 32);
+    rec[6] = pw_coins(s.p[0]) | (pw_coins(s.p[1]) << 8);
+  }
+  __syncwarp();
+  const int nrec = static_cast<int>(min(32u, n - e0));
+  const int nrows = both ? 2 * nrec : nrec;
+  T* base = out + static_cast<size_t>(e0) * (both ? 2 : 1) * kObservationSize;
+  const int total = nrows * kObservationSize;
+  for (int g = lane; g < total; g += 32) {
+    const int r = g / kObservationSize, p = g - r * kObservationSize;
+    const uint32_t* rec = &s_rec[warp][(both ? (r >> 1) : r) * 7];
+    const int view = both ? (r & 1) : 0;
+    uint32_t v;
+    if (p < 60) {
+      const uint64_t m = static_cast<uint64_t>(rec[2 * view]) | (static_cast<uint64_t>(rec[2 * view + 1]) << 32);
+      v = static_cast<uint32_t>(m >> p) & 1u;
+    } else if (p < 62) {
+      v = (rec[6] >> (8 * (p - 60))) & 255u;
+    } else {
+      const uint64_t m = static_cast<uint64_t>(rec[4]) | (static_cast<uint64_t>(rec[5]) << 32);
+      v = static_cast<uint32_t>(m >> (p - 62)) & 1u;
+    }
+    base[g] = elem_from<T>(v);
+  }
+}
+
+// ---- fused random rollout step: sample -> step -> chance -> [auto-reset] -> outputs -> encode -------
+template <typename T, bool kEncode>
+__global__ void __launch_bounds__(kBlockThreads)
+k_rollout(EnvArrays A, uint64_t step, int player_sel, T* __restrict__ out) {
+  __shared__ uint32_t s_stats[COUP_STATS_LEN];
+  __shared__ uint32_t s_rec[kEncode ? kWarpsPerBlock : 1][kEncode ? 32 * kRecWords : 1];
+  BlockStats st;
+  st.init(s_stats);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t e0 = (blockIdx.x * kWarpsPerBlock + warp) * 32u;
+  const uint32_t e = e0 + lane;
+  const bool active = e < A.n;
+  StepResult r = {};
+  if (active) {
+    Env s = load_env(A.state + e);
+    uint32_t* hist_row = A.history + static_cast<size_t>(e) * kHistoryWords;
+    r = step_env<true>(s, hist_row, 0, nullptr, A, e, step);
+    store_env(A.state + e, s);
+    write_outputs(A, e, r);
+    if (kEncode) fill_record(&s_rec[warp][lane * kRecWords], s, hist_row, player_sel);
+  }
+  account(st, r, active);
+  if (kEncode && e0 < A.n) {
+    __syncwarp();
+    const int nrec = static_cast<int>(min(32u, A.n - e0));
+    const bool both = player_sel == COUP_PLAYER_BOTH;
+    using U = typename Unit4<T>::type;
+    U* out_units = reinterpret_cast<U*>(out) + static_cast<size_t>(e0) * (both ? 2 : 1) * kUnitsPerInfoRow;
+    warp_encode_info<T>(s_rec[warp], nrec, both, out_units, lane);
+  }
+  st.flush(A.stats);
+}
+
+// ---- verification: position-keyed 64-bit hash of every row of a dense tensor -------------------------
+template <typename T> __device__ __forceinline__ float to_float(T v);
+template <> __device__ __forceinline__ float to_float<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_float<uint8_t>(uint8_t v) { return static_cast<float>(v); }
+template <> __device__ __forceinline__ float to_float<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename T>
+__global__ void __launch_bounds__(kBlockThreads)
+k_row_hash(const T* __restrict__ t, uint32_t rows, uint32_t row_len, uint64_t* __restrict__ out) {
+  const uint32_t row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const T* p = t + static_cast<size_t>(row) * row_len;
+  uint64_t h = 0;
+  for (uint32_t i = lane; i < row_len; i += 32) {
+    const uint32_t bits = __float_as_uint(to_float<T>(p[i]));
+    if (bits != 0) h += mix64((static_cast<uint64_t>(i) << 32) | bits);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
+  if (lane == 0) out[row] = h;
+}
+
+}  // namespace coup

@@ -1,0 +1,262 @@
+"""Batched Coup VectorEnv over the C ABI (include/coup_b200.h).
+
+Semantics follow the reference's `rl_environment.Environment.reset/step`
+(open_spiel/python/rl_environment.py:282-382) applied per env and batched like
+`vector_env.SyncVectorEnv` (open_spiel/python/vector_env.py:40-78): one `step` = one player action +
+every following chance node, then legal mask / current player / rewards / done (+ tensors) for the next
+decision. All rules run in CUDA kernels; PyTorch is only used here to own device buffers and streams.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import (DTYPE_BF16, DTYPE_F32, DTYPE_U8, FLAG_AUTO_RESET, HISTORY_WORDS, INFO_STATE_SIZE,
+                   NUM_DISTINCT_ACTIONS, OBSERVATION_SIZE, PLAYER_0, PLAYER_1, PLAYER_BOTH, PLAYER_CURRENT,
+                   STATE_WORDS, STATS_LEN, CoupError, check)
+
+_TORCH_TO_DTYPE = {torch.float32: DTYPE_F32, torch.uint8: DTYPE_U8, torch.bfloat16: DTYPE_BF16}
+
+
+class _DevPtr:
+    """Exposes a raw device pointer through __cuda_array_interface__ so torch can view it zero-copy."""
+
+    def __init__(self, ptr, shape, typestr, owner):
+        self.__cuda_array_interface__ = {
+            "shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2, "strides": None,
+        }
+        self._owner = owner  # keeps the handle alive as long as a view exists
+
+
+def _view(ptr, shape, typestr, device, owner):
+    return torch.as_tensor(_DevPtr(ptr, shape, typestr, owner), device=device)
+
+
+def _stream_ptr(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class CoupVectorEnv:
+    """`num_envs` independent 2-player Coup games resident on one GPU."""
+
+    num_players = 2
+    num_actions = NUM_DISTINCT_ACTIONS
+    info_state_size = INFO_STATE_SIZE
+    observation_size = OBSERVATION_SIZE
+
+    def __init__(self, num_envs, seed=1234, device=0, global_env_offset=0, auto_reset=False):
+        self._lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise CoupError("CoupVectorEnv needs a CUDA device (there is no CPU fallback)")
+        self.device = torch.device("cuda", device if isinstance(device, int) else torch.device(device).index or 0)
+        torch.cuda.init()
+        with torch.cuda.device(self.device):
+            torch.zeros(1, device=self.device)  # make sure the primary context exists
+        self.num_envs = int(num_envs)
+        opts = _lib.VecOpts(self.num_envs, self.device.index, seed, global_env_offset,
+                            FLAG_AUTO_RESET if auto_reset else 0, 0)
+        self._h = C.c_void_p()
+        check(self._lib.coup_vec_create(C.byref(opts), C.byref(self._h)))
+        n, L, d = self.num_envs, self._lib, self.device
+        self.legal_mask = _view(L.coup_vec_legal_mask(self._h), (n,), "<i4", d, self)
+        self.current_player = _view(L.coup_vec_current_player(self._h), (n,), "|i1", d, self)
+        self.done = _view(L.coup_vec_done(self._h), (n,), "|u1", d, self)
+        self.rewards = _view(L.coup_vec_rewards(self._h), (n, 2), "|i1", d, self)
+        self.returns = _view(L.coup_vec_returns(self._h), (n, 2), "|i1", d, self)
+        self.state = _view(L.coup_vec_state(self._h), (n, STATE_WORDS), "<i4", d, self)
+        self.history = _view(L.coup_vec_history(self._h), (n, HISTORY_WORDS), "<i4", d, self)
+        self.stats_device = _view(L.coup_vec_stats_device(self._h), (STATS_LEN,), "<i8", d, self)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.coup_vec_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self):
+        return self.num_envs
+
+    # ---- helpers --------------------------------------------------------------------------------
+    def _u8(self, t, shape, name):
+        if t is None:
+            return None
+        if not torch.is_tensor(t):
+            t = torch.as_tensor(np.asarray(t, dtype=np.uint8))
+        t = t.to(device=self.device, dtype=torch.uint8).contiguous()
+        if tuple(t.shape) != tuple(shape):
+            raise ValueError(f"{name} must have shape {tuple(shape)}, got {tuple(t.shape)}")
+        return t
+
+    @staticmethod
+    def _ptr(t):
+        return None if t is None else C.c_void_p(t.data_ptr())
+
+    def _rows(self, player):
+        return self.num_envs * (2 if player == PLAYER_BOTH else 1)
+
+    # ---- reset / step ---------------------------------------------------------------------------
+    def reset(self, envs_to_reset=None, forced_deals=None):
+        """vector_env.SyncVectorEnv.reset(envs_to_reset) (vector_env.py:68-78)."""
+        m = self._u8(envs_to_reset, (self.num_envs,), "envs_to_reset")
+        f = self._u8(forced_deals, (self.num_envs, 4), "forced_deals")
+        check(self._lib.coup_vec_reset(self._h, self._ptr(m), self._ptr(f), _stream_ptr(self.device)))
+
+    def step(self, actions, forced_chance=None):
+        """One player action per env + all following chance nodes (rl_environment.py:282-322)."""
+        a = self._u8(actions, (self.num_envs,), "actions")
+        f = self._u8(forced_chance, (self.num_envs, 4), "forced_chance")
+        check(self._lib.coup_vec_step(self._h, self._ptr(a), self._ptr(f), _stream_ptr(self.device)))
+
+    def sample_uniform(self, out=None):
+        if out is None:
+            out = torch.empty(self.num_envs, dtype=torch.uint8, device=self.device)
+        check(self._lib.coup_vec_sample_uniform(self._h, self._ptr(out), _stream_ptr(self.device)))
+        return out
+
+    def rollout(self, n_steps, encode_player=None, out=None, dtype=torch.float32):
+        """n_steps fused (uniform-random action, step, chance, [auto-reset], encode) kernels."""
+        if encode_player is None:
+            check(self._lib.coup_vec_rollout(self._h, n_steps, -1, 0, None, _stream_ptr(self.device)))
+            return None
+        if out is None:
+            out = torch.empty((self._rows(encode_player), INFO_STATE_SIZE), dtype=dtype, device=self.device)
+        check(self._lib.coup_vec_rollout(self._h, n_steps, encode_player, _TORCH_TO_DTYPE[out.dtype],
+                                         self._ptr(out), _stream_ptr(self.device)))
+        return out
+
+    def step_host(self, h_actions, h_legal_mask=None, h_current_player=None, h_done=None, h_rewards=None,
+                  tensor_out=None):
+        """Host-buffer path: numpy/pinned-torch buffers in and out, tensors stay on the device."""
+        def hp(x):
+            if x is None:
+                return None
+            return C.c_void_p(x.data_ptr() if torch.is_tensor(x) else x.ctypes.data)
+        dt = _TORCH_TO_DTYPE[tensor_out.dtype] if tensor_out is not None else 0
+        check(self._lib.coup_vec_step_host(self._h, hp(h_actions), hp(h_legal_mask), hp(h_current_player),
+                                           hp(h_done), hp(h_rewards), dt, self._ptr(tensor_out),
+                                           _stream_ptr(self.device)))
+
+    # ---- observations ---------------------------------------------------------------------------
+    def information_state_tensor(self, player=PLAYER_CURRENT, out=None, dtype=torch.float32):
+        """CoupState::InformationStateTensor (coup.cc:1044-1049) for every env; [rows, 2492]."""
+        if out is None:
+            out = torch.empty((self._rows(player), INFO_STATE_SIZE), dtype=dtype, device=self.device)
+        check(self._lib.coup_vec_information_state_tensor(self._h, player, _TORCH_TO_DTYPE[out.dtype],
+                                                          self._ptr(out), _stream_ptr(self.device)))
+        return out
+
+    def observation_tensor(self, player=PLAYER_CURRENT, out=None, dtype=torch.float32):
+        """CoupState::ObservationTensor (coup.cc:1051-1056) for every env; [rows, 98]."""
+        if out is None:
+            out = torch.empty((self._rows(player), OBSERVATION_SIZE), dtype=dtype, device=self.device)
+        check(self._lib.coup_vec_observation_tensor(self._h, player, _TORCH_TO_DTYPE[out.dtype],
+                                                    self._ptr(out), _stream_ptr(self.device)))
+        return out
+
+    def legal_actions_mask(self, out=None):
+        """State::LegalActionsMask (spiel.cc:371-377): uint8 [num_envs, 18]."""
+        if out is None:
+            out = torch.empty((self.num_envs, NUM_DISTINCT_ACTIONS), dtype=torch.uint8, device=self.device)
+        check(self._lib.coup_vec_legal_actions_mask(self._h, self._ptr(out), _stream_ptr(self.device)))
+        return out
+
+    def tensor_row_hash(self, t):
+        t = t.contiguous()
+        rows = t.shape[0]
+        out = torch.empty(rows, dtype=torch.int64, device=self.device)
+        check(self._lib.coup_tensor_row_hash(self._ptr(t), _TORCH_TO_DTYPE[t.dtype], rows, t.shape[1],
+                                             self._ptr(out), _stream_ptr(self.device)))
+        return out
+
+    # ---- statistics -----------------------------------------------------------------------------
+    def stats(self):
+        buf = np.zeros(STATS_LEN, np.uint64)
+        check(self._lib.coup_vec_stats(self._h, C.c_void_p(buf.ctypes.data), _stream_ptr(self.device)))
+        return stats_dict(buf)
+
+    def clear_stats(self):
+        check(self._lib.coup_vec_clear_stats(self._h, _stream_ptr(self.device)))
+
+    def check_errors(self):
+        check(self._lib.coup_vec_check_errors(self._h, _stream_ptr(self.device)))
+
+    @property
+    def step_counter(self):
+        return int(self._lib.coup_vec_step_counter(self._h))
+
+    @step_counter.setter
+    def step_counter(self, v):
+        check(self._lib.coup_vec_set_step_counter(self._h, int(v)))
+
+    # ---- trajectory export (host side, for replay through the oracle) -----------------------------
+    def move_numbers(self):
+        return (self.state[:, 3] & 127).to(torch.int64)
+
+    def trajectories(self):
+        """Decodes the device history into per-env action lists (chance outcomes included), i.e. the
+        reference's serialisation of a state (State::Serialize, spiel.cc:297-311)."""
+        hist = self.history.cpu().numpy().view(np.uint32)
+        lens = self.move_numbers().cpu().numpy()
+        return decode_history(hist, lens)
+
+
+def decode_history(hist_words, lens):
+    """uint32 [n,16] packed 5-bit codes -> list of (actions uint8[len], deal_target int8[len])."""
+    n = hist_words.shape[0]
+    idx = np.arange(96)
+    codes = (hist_words[:, idx // 6] >> (5 * (idx % 6)).astype(np.uint32)) & 31
+    out = []
+    for e in range(n):
+        c = codes[e, : lens[e]].astype(np.int64)
+        is_chance = c >= 18
+        target = np.where(is_chance, (c - 18) // 5, -1).astype(np.int8)
+        action = np.where(is_chance, (c - 18) % 5, c).astype(np.uint8)
+        out.append((action, target))
+    return out
+
+
+def stats_dict(buf):
+    buf = [int(x) for x in buf]
+    return {
+        "decision_steps": buf[_lib.STAT_DECISION_STEPS],
+        "chance_moves": buf[_lib.STAT_CHANCE_MOVES],
+        "episodes": buf[_lib.STAT_EPISODES],
+        "truncated": buf[_lib.STAT_TRUNCATED],
+        "episode_moves": buf[_lib.STAT_EPISODE_MOVES],
+        "illegal": buf[_lib.STAT_ILLEGAL],
+        "returns_hist_p0": buf[_lib.STAT_RETURN_HIST:_lib.STAT_RETURN_HIST + 5],
+        "legal_count_hist": buf[_lib.STAT_LEGAL_HIST:_lib.STAT_LEGAL_HIST + 8],
+    }
+
+
+def unpack_states(state_words):
+    """Decodes packed state words (uint32 [n,4], layout in include/coup_b200.h) into plain numpy fields
+    for inspection and tests. hands[n,2,4] holds (value<<1 | face_up) per slot, 15 = empty."""
+    w = np.asarray(state_words).view(np.uint32).reshape(-1, 4)
+    out = {}
+    pw = w[:, :2]
+    out["hands"] = np.stack([(pw >> (4 * i)) & 15 for i in range(4)], axis=-1).astype(np.int64)
+    out["num_cards"] = (out["hands"] != 15).sum(-1)
+    out["coins"] = ((pw >> 16) & 31).astype(np.int64)
+    last = ((pw >> 21) & 31).astype(np.int64)
+    out["last_action"] = np.where(last == 31, -1, last)
+    out["lost_challenge"] = ((pw >> 26) & 1).astype(np.int64)
+    g = w[:, 2]
+    out["deck"] = np.stack([(g >> (4 * c)) & 15 for c in range(5)], axis=-1).astype(np.int64)
+    out["cur_player_turn"] = ((g >> 20) & 1).astype(np.int64)
+    out["cur_player_move"] = ((g >> 21) & 1).astype(np.int64)
+    out["is_turn_begin"] = ((g >> 22) & 1).astype(np.int64)
+    out["is_chance"] = ((g >> 23) & 1).astype(np.int64)
+    out["queued_deals"] = ((g >> 24) & 7).astype(np.int64)
+    out["error"] = ((g >> 29) & 1).astype(np.int64)
+    c = w[:, 3]
+    out["move_number"] = (c & 127).astype(np.int64)
+    out["turn_number"] = ((c >> 7) & 127).astype(np.int64)
+    out["reward0"] = ((c >> 14) & 7).astype(np.int64) - 2
+    return out

@@ -126,6 +126,8 @@ class Oracle:
         L.oc_trace.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.oc_trace_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.oc_state_from_actions.argtypes = [P(OcState), C.c_void_p, C.c_int]
+        L.oc_final_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.oc_final_tensors_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.oc_batch_init.argtypes = [C.c_void_p, C.c_int]
         L.oc_batch_apply.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.oc_batch_info_state.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
@@ -219,6 +221,26 @@ class Oracle:
         out = np.zeros(len(a) + n_traj, TRACE_DTYPE)
         bad = self.lib.oc_trace_batch(a.ctypes.data, off.ctypes.data, n_traj, out.ctypes.data)
         return out, bad
+
+    def final_batch(self, actions, offsets):
+        """Record of the last state of each trajectory; rejected trajectories have cur_player 127."""
+        a = _u8(actions)
+        off = np.ascontiguousarray(offsets, np.int64)
+        n_traj = len(off) - 1
+        out = np.zeros(n_traj, TRACE_DTYPE)
+        bad = self.lib.oc_final_batch(a.ctypes.data, off.ctypes.data, n_traj, out.ctypes.data)
+        return out, bad
+
+    def final_tensors_batch(self, actions, offsets, info=True, obs=True):
+        a = _u8(actions)
+        off = np.ascontiguousarray(offsets, np.int64)
+        n_traj = len(off) - 1
+        ti = np.zeros((n_traj, 2, INFO_SIZE), np.float32) if info else None
+        to = np.zeros((n_traj, 2, OBS_SIZE), np.float32) if obs else None
+        bad = self.lib.oc_final_tensors_batch(
+            a.ctypes.data, off.ctypes.data, n_traj,
+            ti.ctypes.data if info else None, to.ctypes.data if obs else None)
+        return ti, to, bad
 
     # -- batches ------------------------------------------------------------------------------
     def batch_new(self, n):

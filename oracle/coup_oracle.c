@@ -673,6 +673,39 @@ int oc_trace_batch(const uint8_t* actions, const int64_t* offsets, int n_traj, o
   return bad;
 }
 
+/* Only the record of the LAST state of each trajectory (out[t]); a rejected trajectory gets
+ * cur_player = 127. Returns the number of rejected trajectories. */
+int oc_final_batch(const uint8_t* actions, const int64_t* offsets, int n_traj, oc_trace_rec* out) {
+  int bad = 0;
+  for (int t = 0; t < n_traj; ++t) {
+    oc_state s;
+    int n = (int)(offsets[t + 1] - offsets[t]);
+    if (oc_state_from_actions(&s, actions + offsets[t], n) != OC_OK) {
+      memset(&out[t], 0, sizeof(out[t]));
+      out[t].cur_player = 127;
+      bad++;
+    } else {
+      fill_rec(&s, &out[t]);
+    }
+  }
+  return bad;
+}
+
+/* Dense tensors of the last state of each trajectory: info[t][2][2492], obs[t][2][98] (either may be NULL). */
+int oc_final_tensors_batch(const uint8_t* actions, const int64_t* offsets, int n_traj, float* info, float* obs) {
+  int bad = 0;
+  for (int t = 0; t < n_traj; ++t) {
+    oc_state s;
+    int n = (int)(offsets[t + 1] - offsets[t]);
+    if (oc_state_from_actions(&s, actions + offsets[t], n) != OC_OK) { bad++; continue; }
+    for (int p = 0; p < 2; ++p) {
+      if (info) oc_information_state_tensor(&s, p, info + ((size_t)t * 2 + p) * OC_INFO_STATE_SIZE);
+      if (obs) oc_observation_tensor(&s, p, obs + ((size_t)t * 2 + p) * OC_OBSERVATION_SIZE);
+    }
+  }
+  return bad;
+}
+
 int oc_state_from_actions(oc_state* s, const uint8_t* actions, int n_actions) {
   oc_init(s);
   for (int i = 0; i < n_actions; ++i) {

@@ -125,6 +125,8 @@ typedef struct {
 int oc_trace(const uint8_t* actions, int n_actions, oc_trace_rec* out);
 int oc_trace_batch(const uint8_t* actions, const int64_t* offsets, int n_traj, oc_trace_rec* out);
 int oc_state_from_actions(oc_state* s, const uint8_t* actions, int n_actions);
+int oc_final_batch(const uint8_t* actions, const int64_t* offsets, int n_traj, oc_trace_rec* out);
+int oc_final_tensors_batch(const uint8_t* actions, const int64_t* offsets, int n_traj, float* info, float* obs);
 
 /* Batched helpers over an array of states (used by the GPU parity tests). */
 void oc_batch_init(oc_state* s, int n);
