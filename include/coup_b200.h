@@ -169,7 +169,9 @@ int coup_vec_observation_tensor(coup_vec_env* env, int player, int dtype, void* 
 /* ---- host-buffer convenience path (what a host-driven caller such as rl_environment would use):
  * copies uint8[num_envs] actions from (pinned) host memory, steps, optionally encodes the current
  * player's info-state into d_tensor_out (device; may be NULL) and copies legal_mask / current_player /
- * done / rewards back into the host buffers (each may be NULL). Synchronises the stream. */
+ * done / rewards back into the host buffers (each may be NULL). Returns once the host buffers are filled;
+ * the tensor is complete in stream order (work queued on `stream` afterwards sees it), so the host can
+ * choose the next actions while the encoder is still writing. */
 int coup_vec_step_host(coup_vec_env* env, const uint8_t* h_actions, uint32_t* h_legal_mask,
                        int8_t* h_current_player, uint8_t* h_done, int8_t* h_rewards, int dtype,
                        void* d_tensor_out, void* stream);

@@ -19,6 +19,7 @@ struct coup_vec_env {
   coup_vec_opts opts;
   EnvArrays A;
   uint8_t* d_actions;   // staging for coup_vec_step_host
+  cudaEvent_t host_outputs_ready;
   uint64_t step_counter;
 };
 
@@ -64,6 +65,13 @@ int launch_status(const char* what) {
 bool valid_player_sel(int p) { return p >= COUP_PLAYER_0 && p <= COUP_PLAYER_BOTH; }
 bool valid_dtype(int d) { return d == COUP_DTYPE_F32 || d == COUP_DTYPE_U8 || d == COUP_DTYPE_BF16; }
 
+// First Philox word of `count` consecutive envs (host side of coup_host_sample_uniform). Straight-line
+// arithmetic so that the host compiler can vectorise it; cloned per ISA and dispatched at load time.
+__attribute__((target_clones("avx512f", "avx2", "default")))
+void philox_x_batch(uint64_t seed, uint64_t first_env, uint64_t step, uint32_t count, uint32_t* out) {
+  for (uint32_t i = 0; i < count; ++i) out[i] = env_random(seed, first_env + i, step, 0).x;
+}
+
 template <typename T>
 int rollout_typed(coup_vec_env* env, int n_steps, int encode_player, void* d_out, cudaStream_t st) {
   const unsigned grid = blocks_for(env->A.n);
@@ -101,6 +109,8 @@ int coup_vec_create(const coup_vec_opts* opts, coup_vec_env** out) {
   if (!env) return fail(COUP_ERR_INVALID_ARG, "out of host memory");
   env->opts = *opts;
   env->step_counter = 0;
+  env->host_outputs_ready = nullptr;
+  env->d_actions = nullptr;
   const size_t n = opts->num_envs;
   EnvArrays& A = env->A;
   std::memset(&A, 0, sizeof(A));
@@ -119,6 +129,7 @@ int coup_vec_create(const coup_vec_opts* opts, coup_vec_env** out) {
   alloc(reinterpret_cast<void**>(&A.returns), n * 2);
   alloc(reinterpret_cast<void**>(&A.stats), COUP_STATS_LEN * sizeof(unsigned long long));
   alloc(reinterpret_cast<void**>(&env->d_actions), n);
+  if (err == cudaSuccess) err = cudaEventCreateWithFlags(&env->host_outputs_ready, cudaEventDisableTiming);
   if (err == cudaSuccess) err = cudaMemset(A.stats, 0, COUP_STATS_LEN * sizeof(unsigned long long));
   if (err == cudaSuccess) err = cudaMemset(A.history, 0, n * kHistoryWords * sizeof(uint32_t));
   if (err != cudaSuccess) {
@@ -140,6 +151,7 @@ int coup_vec_destroy(coup_vec_env* env) {
   cudaFree(env->A.state); cudaFree(env->A.history); cudaFree(env->A.legal); cudaFree(env->A.cur_player);
   cudaFree(env->A.done); cudaFree(env->A.rewards); cudaFree(env->A.returns); cudaFree(env->A.stats);
   cudaFree(env->d_actions);
+  if (env->host_outputs_ready) cudaEventDestroy(env->host_outputs_ready);
   delete env;
   return COUP_OK;
 }
@@ -247,15 +259,18 @@ int coup_vec_step_host(coup_vec_env* env, const uint8_t* h_actions, uint32_t* h_
   CUDA_TRY(cudaMemcpyAsync(env->d_actions, h_actions, n, cudaMemcpyHostToDevice, st));
   int rc = coup_vec_step(env, env->d_actions, nullptr, stream);
   if (rc != COUP_OK) return rc;
-  if (d_tensor_out) {
-    rc = coup_vec_information_state_tensor(env, COUP_PLAYER_CURRENT, dtype, d_tensor_out, stream);
-    if (rc != COUP_OK) return rc;
-  }
+  // Host outputs first, then the tensor: the call returns as soon as the host buffers are filled, while
+  // the encoder is still running. The tensor is complete in stream order (its consumer is on the device).
   if (h_legal_mask) CUDA_TRY(cudaMemcpyAsync(h_legal_mask, env->A.legal, n * 4, cudaMemcpyDeviceToHost, st));
   if (h_current_player) CUDA_TRY(cudaMemcpyAsync(h_current_player, env->A.cur_player, n, cudaMemcpyDeviceToHost, st));
   if (h_done) CUDA_TRY(cudaMemcpyAsync(h_done, env->A.done, n, cudaMemcpyDeviceToHost, st));
   if (h_rewards) CUDA_TRY(cudaMemcpyAsync(h_rewards, env->A.rewards, n * 2, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaStreamSynchronize(st));
+  CUDA_TRY(cudaEventRecord(env->host_outputs_ready, st));
+  if (d_tensor_out) {
+    rc = coup_vec_information_state_tensor(env, COUP_PLAYER_CURRENT, dtype, d_tensor_out, stream);
+    if (rc != COUP_OK) return rc;
+  }
+  CUDA_TRY(cudaEventSynchronize(env->host_outputs_ready));
   return COUP_OK;
 }
 
@@ -264,14 +279,19 @@ int coup_host_sample_uniform(const uint32_t* h_legal_mask, uint32_t n, uint64_t 
   if (!h_legal_mask || !h_actions_out) return fail(COUP_ERR_INVALID_ARG, "coup_host_sample_uniform: null argument");
   threads = threads < 1 ? 1 : threads;
   auto work = [=](uint32_t lo, uint32_t hi) {
-    for (uint32_t i = lo; i < hi; ++i) {
-      const uint32_t legal = h_legal_mask[i];
-      if (legal == 0) { h_actions_out[i] = 0xFF; continue; }
-      const uint32_t x = env_random(seed, global_env_offset + i, step, 0).x;
-      uint32_t k = mulhi32(x, static_cast<uint32_t>(__builtin_popcount(legal)));
-      uint32_t m = legal;
-      while (k--) m &= m - 1;  // drop the k lowest set bits
-      h_actions_out[i] = static_cast<uint8_t>(__builtin_ctz(m));
+    constexpr uint32_t kTile = 1024;
+    uint32_t x[kTile];
+    for (uint32_t base = lo; base < hi; base += kTile) {
+      const uint32_t cnt = std::min(kTile, hi - base);
+      philox_x_batch(seed, global_env_offset + base, step, cnt, x);  // SIMD-friendly pass
+      for (uint32_t j = 0; j < cnt; ++j) {
+        const uint32_t legal = h_legal_mask[base + j];
+        if (legal == 0) { h_actions_out[base + j] = 0xFF; continue; }
+        uint32_t k = mulhi32(x[j], static_cast<uint32_t>(__builtin_popcount(legal)));
+        uint32_t m = legal;
+        while (k--) m &= m - 1;  // drop the k lowest set bits
+        h_actions_out[base + j] = static_cast<uint8_t>(__builtin_ctz(m));
+      }
     }
   };
   if (threads == 1 || n < 4096) { work(0, n); return COUP_OK; }
