@@ -51,6 +51,8 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline sample budget")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra-contracts", action="store_true")
+    ap.add_argument("--encoder", default="staged", choices=["staged", "plain"],
+                    help="info-state encoder: shared-memory staging + bulk (TMA) stores, or per-lane vector stores")
     return ap.parse_args()
 
 
@@ -195,7 +197,8 @@ def main():
     n, K, W = args.envs, args.steps, max(args.warmup, 3)
     contract = args.contract
     torch_dtype = {"d32": torch.float32, "bf16": torch.bfloat16, "d8": torch.uint8, "env": None}[contract]
-    env = CoupVectorEnv(n, seed=args.seed, device=local, global_env_offset=rank * n, auto_reset=True)
+    env = CoupVectorEnv(n, seed=args.seed, device=local, global_env_offset=rank * n, auto_reset=True,
+                        plain_store_encoder=(args.encoder == "plain"))
     out = None if torch_dtype is None else torch.empty((n, 2492), dtype=torch_dtype, device=dev)
     sel = None if out is None else _lib.PLAYER_CURRENT
 
@@ -299,7 +302,8 @@ def main():
         peak, peak_src = measured_peak()
         bytes_per_launch = BYTES_PER_STEP[contract] * n
         achieved = bytes_per_launch / per_launch_s / 1e9
-        kernel = {"d32": "k_rollout<float,true>", "bf16": "k_rollout<__nv_bfloat16,true>", "d8": "k_rollout<uint8_t,true>",
+        kname = "k_rollout_tma<%s>" if args.encoder == "staged" else "k_rollout<%s,true>"
+        kernel = {"d32": kname % "float", "bf16": kname % "__nv_bfloat16", "d8": kname % "uint8_t",
                   "env": "k_rollout<float,false>"}[contract]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -308,7 +312,7 @@ def main():
             "config": {
                 "workload": "2-player Coup uniform-random rollouts, 2^20 envs per GPU, legal mask + dense info-state tensor "
                             "(2492 x %s, player to move) per decision step, auto-reset, Philox4x32-10 chance (BASELINE.json configs[1])" % CONTRACT_DTYPE[contract],
-                "envs_per_gpu": n, "contract": contract, "bytes_per_step": BYTES_PER_STEP[contract],
+                "envs_per_gpu": n, "contract": contract, "bytes_per_step": BYTES_PER_STEP[contract], "encoder": args.encoder,
                 "parallelism": f"env-slab x{world} (no data-path collective; NCCL all-reduce of the stats vector only)",
                 "l2": "per-step working set (%.2f GB written + 80 MB state/history) >> 126 MB L2, no flush needed" % (bytes_per_launch / 1e9)
                       if contract != "env" else "state+history 80 MiB/GPU is L2-resident by design (env-only contract)",

@@ -74,6 +74,8 @@ enum {
                                     reports done/rewards/returns of the finished episode and is
                                     re-dealt in the same call; legal mask / current player / tensors
                                     then describe the first decision of the new episode */
+  , COUP_FLAG_PLAIN_STORE_ENCODER = 1u << 1 /* info-state rows written with per-lane vector stores instead
+                                    of the default shared-memory staging + bulk (TMA) stores; same bytes */
 };
 
 typedef struct coup_vec_opts {

@@ -72,17 +72,39 @@ void philox_x_batch(uint64_t seed, uint64_t first_env, uint64_t step, uint32_t c
   for (uint32_t i = 0; i < count; ++i) out[i] = env_random(seed, first_env + i, step, 0).x;
 }
 
+bool use_staged_encoder(const coup_vec_env* env) { return (env->opts.flags & COUP_FLAG_PLAIN_STORE_ENCODER) == 0; }
+
 template <typename T>
 int rollout_typed(coup_vec_env* env, int n_steps, int encode_player, void* d_out, cudaStream_t st) {
   const unsigned grid = blocks_for(env->A.n);
+  const bool staged = encode_player >= 0 && use_staged_encoder(env);
+  if (staged) {
+    cudaError_t err = cudaFuncSetAttribute(k_rollout_tma<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmemBytes);
+    if (err != cudaSuccess) return fail(COUP_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(err));
+  }
   for (int i = 0; i < n_steps; ++i) {
-    if (encode_player >= 0)
+    if (staged)
+      k_rollout_tma<T><<<grid, kTmaBlockThreads, kTmaSmemBytes, st>>>(env->A, env->step_counter, encode_player, static_cast<T*>(d_out));
+    else if (encode_player >= 0)
       k_rollout<T, true><<<grid, kBlockThreads, 0, st>>>(env->A, env->step_counter, encode_player, static_cast<T*>(d_out));
     else
       k_rollout<T, false><<<grid, kBlockThreads, 0, st>>>(env->A, env->step_counter, 0, static_cast<T*>(nullptr));
     env->step_counter++;
   }
   return launch_status("k_rollout");
+}
+
+template <typename T>
+int encode_info_typed(coup_vec_env* env, int player, void* d_out, cudaStream_t st) {
+  const unsigned grid = (env->A.n + 32 * kWarpsPerBlock - 1) / (32 * kWarpsPerBlock);
+  if (use_staged_encoder(env)) {
+    cudaError_t err = cudaFuncSetAttribute(k_encode_info_tma<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmemBytes);
+    if (err != cudaSuccess) return fail(COUP_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(err));
+    k_encode_info_tma<T><<<grid, kTmaBlockThreads, kTmaSmemBytes, st>>>(env->A.state, env->A.history, env->A.n, player, static_cast<T*>(d_out));
+  } else {
+    k_encode_info<T><<<grid, kBlockThreads, 0, st>>>(env->A.state, env->A.history, env->A.n, player, static_cast<T*>(d_out));
+  }
+  return launch_status("k_encode_info");
 }
 
 }  // namespace
@@ -216,19 +238,11 @@ int coup_vec_information_state_tensor(coup_vec_env* env, int player, int dtype, 
   if (!env || !d_out || !valid_player_sel(player) || !valid_dtype(dtype))
     return fail(COUP_ERR_INVALID_ARG, "coup_vec_information_state_tensor: bad arguments");
   DeviceGuard guard(env->opts.device);
-  const unsigned grid = (env->A.n + 32 * kWarpsPerBlock - 1) / (32 * kWarpsPerBlock);
   switch (dtype) {
-    case COUP_DTYPE_F32:
-      k_encode_info<float><<<grid, kBlockThreads, 0, S(stream)>>>(env->A.state, env->A.history, env->A.n, player, static_cast<float*>(d_out));
-      break;
-    case COUP_DTYPE_U8:
-      k_encode_info<uint8_t><<<grid, kBlockThreads, 0, S(stream)>>>(env->A.state, env->A.history, env->A.n, player, static_cast<uint8_t*>(d_out));
-      break;
-    default:
-      k_encode_info<__nv_bfloat16><<<grid, kBlockThreads, 0, S(stream)>>>(env->A.state, env->A.history, env->A.n, player, static_cast<__nv_bfloat16*>(d_out));
-      break;
+    case COUP_DTYPE_F32: return encode_info_typed<float>(env, player, d_out, S(stream));
+    case COUP_DTYPE_U8: return encode_info_typed<uint8_t>(env, player, d_out, S(stream));
+    default: return encode_info_typed<__nv_bfloat16>(env, player, d_out, S(stream));
   }
-  return launch_status("k_encode_info");
 }
 
 int coup_vec_observation_tensor(coup_vec_env* env, int player, int dtype, void* d_out, void* stream) {

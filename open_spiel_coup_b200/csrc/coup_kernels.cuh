@@ -342,6 +342,125 @@ k_encode_info(const uint4* __restrict__ state, const uint32_t* __restrict__ hist
   warp_encode_info<T>(s_rec[warp], nrec, both, out_units, lane);
 }
 
+// ---- info-state encoder, staged variant: rows are composed in shared memory and written with bulk
+// (TMA) stores. A dense row is >97 % zeros, so instead of computing and storing 623 units per row the warp
+// keeps an all-zero 9 968-byte staging buffer in shared memory, pokes the ~30 non-zeros of a row into it,
+// hands the buffer to the TMA engine (cp.async.bulk shared -> global, 1 instruction, SASS UBLKCP), waits
+// for the engine to have READ the buffer, and un-pokes the same positions. 9 968 B = one f32 row = two
+// bf16 rows = four u8 rows, always a multiple of 16 B and 16-B aligned in the output.
+constexpr int kStageBytes = kInfoStateSize * 4;                  // 9968
+constexpr int kTmaWarpsPerBlock = 8;
+constexpr int kTmaBlockThreads = kTmaWarpsPerBlock * 32;
+constexpr int kTmaSmemPerWarp = kStageBytes + 32 * kRecWords * 4;  // staging buffer + 32 records
+constexpr int kTmaSmemBytes = kTmaWarpsPerBlock * kTmaSmemPerWarp + COUP_STATS_LEN * 4;
+
+template <typename T> struct Elem;
+template <> struct Elem<float> { static __device__ __forceinline__ float from(uint32_t v) { return static_cast<float>(v); } };
+template <> struct Elem<uint8_t> { static __device__ __forceinline__ uint8_t from(uint32_t v) { return static_cast<uint8_t>(v); } };
+template <> struct Elem<__nv_bfloat16> {
+  static __device__ __forceinline__ __nv_bfloat16 from(uint32_t v) { return __float2bfloat16(static_cast<float>(v)); }
+};
+
+__device__ __forceinline__ void tma_store_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tma_bulk_store(void* gptr, const void* smem, uint32_t bytes) {
+  const uint32_t saddr = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gptr), "r"(saddr), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// Writes (set=true) or erases (set=false) the non-zeros of one row into its place in the staging buffer.
+template <typename T>
+__device__ __forceinline__ void poke_row(T* row, const uint32_t* rec, int view, bool set, int lane) {
+  const uint32_t meta = rec[20];
+  const uint32_t observer = (meta >> (24 + view)) & 1u;
+  const uint32_t lo = rec[16 + 2 * view], hi = rec[17 + 2 * view];
+  const T one = Elem<T>::from(set ? 1u : 0u);
+  if ((lo >> lane) & 1u) row[lane] = one;                                  // elements 0..31
+  if ((hi >> lane) & 1u) row[32 + lane] = one;                             // elements 32..59 (hi has 28 bits)
+  if (lane >= 28 && lane < 30)                                             // elements 60, 61: raw coin counts
+    row[32 + lane] = Elem<T>::from(set ? (meta >> (8u + 8u * (lane - 28))) & 255u : 0u);
+  const uint32_t len = meta & 255u;
+  for (uint32_t i = lane; i < len; i += 32) {                              // history rows
+    const uint32_t w = i / 6u;
+    const uint32_t col = history_column((rec[w] >> (5u * (i - 6u * w))) & 31u, observer);
+    if (col != 31u) row[62u + 18u * i + col] = one;
+  }
+}
+
+// Full warp (32 records): nrows = 32 or 64 rows, in groups of G = 4/sizeof(T) rows per bulk store.
+template <typename T>
+__device__ __forceinline__ void warp_encode_info_tma(const uint32_t* recs, bool both, T* stage,
+                                                     unsigned char* out_bytes, int lane) {
+  constexpr int G = 4 / static_cast<int>(sizeof(T));
+  const int ngroups = (both ? 64 : 32) / G;
+  for (int g = 0; g < ngroups; ++g) {
+#pragma unroll
+    for (int k = 0; k < G; ++k) {
+      const int r = g * G + k;
+      poke_row<T>(stage + k * kInfoStateSize, recs + (both ? (r >> 1) : r) * kRecWords, both ? (r & 1) : 0, true, lane);
+    }
+    tma_store_fence();   // generic-proxy writes -> visible to the async proxy
+    __syncwarp();
+    if (lane == 0) {
+      tma_bulk_store(out_bytes + static_cast<size_t>(g) * kStageBytes, stage, kStageBytes);
+      tma_wait_read_all();  // the engine has read the buffer (the global write itself is still in flight)
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < G; ++k) {
+      const int r = g * G + k;
+      poke_row<T>(stage + k * kInfoStateSize, recs + (both ? (r >> 1) : r) * kRecWords, both ? (r & 1) : 0, false, lane);
+    }
+  }
+}
+
+// Carves the dynamic shared memory of a staged kernel: per warp [stage 9968 B][32 records], then stats.
+struct TmaSmem {
+  unsigned char* stage;
+  uint32_t* recs;
+  uint32_t* stats;
+  __device__ __forceinline__ TmaSmem(unsigned char* base, int warp) {
+    stage = base + static_cast<size_t>(warp) * kStageBytes;
+    recs = reinterpret_cast<uint32_t*>(base + static_cast<size_t>(kTmaWarpsPerBlock) * kStageBytes) + warp * 32 * kRecWords;
+    stats = reinterpret_cast<uint32_t*>(base + static_cast<size_t>(kTmaWarpsPerBlock) * kTmaSmemPerWarp);
+  }
+};
+__device__ __forceinline__ void zero_stage(unsigned char* stage, int lane) {
+  uint4* p = reinterpret_cast<uint4*>(stage);
+  for (int q = lane; q < kStageBytes / 16; q += 32) p[q] = make_uint4(0, 0, 0, 0);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kTmaBlockThreads, 2)
+k_encode_info_tma(const uint4* __restrict__ state, const uint32_t* __restrict__ history, uint32_t n,
+                  int player_sel, T* __restrict__ out) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  TmaSmem sm(smem_raw, warp);
+  const uint32_t e0 = (blockIdx.x * kTmaWarpsPerBlock + warp) * 32u;
+  if (e0 >= n) return;
+  const uint32_t e = e0 + lane;
+  const bool full = e0 + 32u <= n;
+  if (full) zero_stage(sm.stage, lane);
+  if (e < n) {
+    const Env s = load_env(state + e);
+    fill_record(sm.recs + lane * kRecWords, s, history + static_cast<size_t>(e) * kHistoryWords, player_sel);
+  }
+  __syncwarp();
+  const bool both = player_sel == COUP_PLAYER_BOTH;
+  const size_t row0 = static_cast<size_t>(e0) * (both ? 2 : 1);
+  if (full) {
+    warp_encode_info_tma<T>(sm.recs, both, reinterpret_cast<T*>(sm.stage),
+                            reinterpret_cast<unsigned char*>(out) + row0 * kInfoStateSize * sizeof(T), lane);
+    if (lane == 0) tma_wait_all();
+  } else {  // ragged last warp: plain vector stores
+    using U = typename Unit4<T>::type;
+    warp_encode_info<T>(sm.recs, static_cast<int>(n - e0), both, reinterpret_cast<U*>(out) + row0 * kUnitsPerInfoRow, lane);
+  }
+}
+
 // ---- observation encoder (98 elements per row): one element per thread step, rows of a warp contiguous --
 template <typename T> __device__ __forceinline__ T elem_from(uint32_t v);
 template <> __device__ __forceinline__ float elem_from<float>(uint32_t v) { return static_cast<float>(v); }
@@ -423,6 +542,46 @@ k_rollout(EnvArrays A, uint64_t step, int player_sel, T* __restrict__ out) {
     using U = typename Unit4<T>::type;
     U* out_units = reinterpret_cast<U*>(out) + static_cast<size_t>(e0) * (both ? 2 : 1) * kUnitsPerInfoRow;
     warp_encode_info<T>(s_rec[warp], nrec, both, out_units, lane);
+  }
+  st.flush(A.stats);
+}
+
+// Same fused step, with the staged (shared memory + bulk store) encoder.
+template <typename T>
+__global__ void __launch_bounds__(kTmaBlockThreads, 2)
+k_rollout_tma(EnvArrays A, uint64_t step, int player_sel, T* __restrict__ out) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  TmaSmem sm(smem_raw, warp);
+  BlockStats st;
+  st.init(sm.stats);
+  const uint32_t e0 = (blockIdx.x * kTmaWarpsPerBlock + warp) * 32u;
+  const uint32_t e = e0 + lane;
+  const bool active = e < A.n;
+  const bool full = e0 + 32u <= A.n;
+  if (full) zero_stage(sm.stage, lane);
+  StepResult r = {};
+  if (active) {
+    Env s = load_env(A.state + e);
+    uint32_t* hist_row = A.history + static_cast<size_t>(e) * kHistoryWords;
+    r = step_env<true>(s, hist_row, 0, nullptr, A, e, step);
+    store_env(A.state + e, s);
+    write_outputs(A, e, r);
+    fill_record(sm.recs + lane * kRecWords, s, hist_row, player_sel);
+  }
+  account(st, r, active);
+  if (e0 < A.n) {
+    __syncwarp();
+    const bool both = player_sel == COUP_PLAYER_BOTH;
+    const size_t row0 = static_cast<size_t>(e0) * (both ? 2 : 1);
+    if (full) {
+      warp_encode_info_tma<T>(sm.recs, both, reinterpret_cast<T*>(sm.stage),
+                              reinterpret_cast<unsigned char*>(out) + row0 * kInfoStateSize * sizeof(T), lane);
+      if (lane == 0) tma_wait_all();
+    } else {
+      using U = typename Unit4<T>::type;
+      warp_encode_info<T>(sm.recs, static_cast<int>(A.n - e0), both, reinterpret_cast<U*>(out) + row0 * kUnitsPerInfoRow, lane);
+    }
   }
   st.flush(A.stats);
 }

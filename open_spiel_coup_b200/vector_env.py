@@ -45,7 +45,8 @@ class CoupVectorEnv:
     info_state_size = INFO_STATE_SIZE
     observation_size = OBSERVATION_SIZE
 
-    def __init__(self, num_envs, seed=1234, device=0, global_env_offset=0, auto_reset=False):
+    def __init__(self, num_envs, seed=1234, device=0, global_env_offset=0, auto_reset=False,
+                 plain_store_encoder=False):
         self._lib = _lib.load()
         if not torch.cuda.is_available():
             raise CoupError("CoupVectorEnv needs a CUDA device (there is no CPU fallback)")
@@ -55,7 +56,8 @@ class CoupVectorEnv:
             torch.zeros(1, device=self.device)  # make sure the primary context exists
         self.num_envs = int(num_envs)
         opts = _lib.VecOpts(self.num_envs, self.device.index, seed, global_env_offset,
-                            FLAG_AUTO_RESET if auto_reset else 0, 0)
+                            (FLAG_AUTO_RESET if auto_reset else 0)
+                            | (_lib.FLAG_PLAIN_STORE_ENCODER if plain_store_encoder else 0), 0)
         self._h = C.c_void_p()
         check(self._lib.coup_vec_create(C.byref(opts), C.byref(self._h)))
         n, L, d = self.num_envs, self._lib, self.device

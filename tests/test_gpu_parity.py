@@ -72,8 +72,9 @@ def check_env_against_oracle(oracle, env, dense_rows=128, expect_done=True):
     return rec
 
 
-def test_sample_step_until_all_done(oracle):
-    env = CoupVectorEnv(2048, seed=7)
+@pytest.mark.parametrize("plain", [False, True], ids=["staged-tma", "plain-stores"])
+def test_sample_step_until_all_done(oracle, plain):
+    env = CoupVectorEnv(2048, seed=7, plain_store_encoder=plain)
     check_env_against_oracle(oracle, env)
     for step in range(100):
         a = env.sample_uniform()
@@ -92,9 +93,10 @@ def test_sample_step_until_all_done(oracle):
     env.check_errors()
 
 
-def test_fused_rollout_equals_sample_then_step(oracle):
-    a_env = CoupVectorEnv(4096 + 37, seed=99, auto_reset=True)   # ragged tail: not a multiple of 32
-    b_env = CoupVectorEnv(4096 + 37, seed=99, auto_reset=True)
+@pytest.mark.parametrize("plain", [False, True], ids=["staged-tma", "plain-stores"])
+def test_fused_rollout_equals_sample_then_step(oracle, plain):
+    a_env = CoupVectorEnv(4096 + 37, seed=99, auto_reset=True, plain_store_encoder=not plain)   # ragged tail
+    b_env = CoupVectorEnv(4096 + 37, seed=99, auto_reset=True, plain_store_encoder=plain)
     out = torch.empty((a_env.num_envs, INFO), dtype=torch.float32, device=a_env.device)
     for step in range(80):
         acts = a_env.sample_uniform()
@@ -344,8 +346,9 @@ def test_playthrough_forced_replay(oracle, playthrough):
     env.check_errors()
 
 
-def test_dtypes_agree(oracle):
-    env = CoupVectorEnv(1000, seed=21, auto_reset=True)
+@pytest.mark.parametrize("plain", [False, True], ids=["staged-tma", "plain-stores"])
+def test_dtypes_agree(oracle, plain):
+    env = CoupVectorEnv(1000, seed=21, auto_reset=True, plain_store_encoder=plain)
     env.rollout(25)
     for sel in (_lib.PLAYER_CURRENT, _lib.PLAYER_BOTH):
         f32 = env.information_state_tensor(sel)
@@ -359,7 +362,7 @@ def test_dtypes_agree(oracle):
         assert torch.equal(env.observation_tensor(sel, dtype=torch.bfloat16).float(), o32)
     assert f32.max() > 1  # coin counts are raw values, not one-hot (coup.cc:207-213)
     # fused rollout with u8 / bf16 output
-    e2 = CoupVectorEnv(1000, seed=21, auto_reset=True)
+    e2 = CoupVectorEnv(1000, seed=21, auto_reset=True, plain_store_encoder=not plain)
     e2.rollout(25)
     a = env.rollout(1, _lib.PLAYER_CURRENT, dtype=torch.uint8)
     b = e2.rollout(1, _lib.PLAYER_CURRENT, dtype=torch.bfloat16)
@@ -493,7 +496,7 @@ def test_philox_stream_matches_specification():
 
 @pytest.mark.parametrize("n", [1, 31, 33, 255, 257])
 def test_ragged_sizes(oracle, n):
-    env = CoupVectorEnv(n, seed=n, auto_reset=True)
+    env = CoupVectorEnv(n, seed=n, auto_reset=True, plain_store_encoder=(n % 2 == 0))
     for _ in range(12):
         out = env.rollout(1, _lib.PLAYER_BOTH)
     assert out.shape == (2 * n, INFO)
