@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline sample budget")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra-contracts", action="store_true")
+    ap.add_argument("--e2e-slabs", type=int, default=4, help="sub-slabs (handles/streams) of the host-buffer leg")
     ap.add_argument("--encoder", default="staged", choices=["staged", "plain"],
                     help="info-state encoder: shared-memory staging + bulk (TMA) stores, or per-lane vector stores")
     return ap.parse_args()
@@ -258,26 +259,39 @@ def main():
         torch.cuda.empty_cache()
 
     # ---- end to end through the host-buffer C-ABI call -------------------------------------------
+    # The slab is driven as `args.e2e_slabs` sub-slabs, each with its own handle, stream and pinned host
+    # buffers, so that the host-side policy and the PCIe copies of one sub-slab overlap the encoder
+    # of the other (what a host-driven caller does to keep the GPU busy). Same total number of envs.
     lib = _lib.load()
     threads = max(1, (os.cpu_count() or 1) // world)
-    h_act = torch.empty(n, dtype=torch.uint8).pin_memory()
-    h_legal = torch.empty(n, dtype=torch.int32).pin_memory()
-    h_cur = torch.empty(n, dtype=torch.int8).pin_memory()
-    h_done = torch.empty(n, dtype=torch.uint8).pin_memory()
-    h_rew = torch.empty((n, 2), dtype=torch.int8).pin_memory()
-    h_legal.copy_(env.legal_mask)
+    S_ = max(1, args.e2e_slabs)
+    ns = n // S_
+    del env
+    torch.cuda.empty_cache()
+    slabs = []
+    for i in range(S_):
+        ev = CoupVectorEnv(ns, seed=args.seed, device=local, global_env_offset=rank * n + i * ns, auto_reset=True,
+                           plain_store_encoder=(args.encoder == "plain"))
+        ev.rollout(100)
+        h_act = torch.empty(ns, dtype=torch.uint8).pin_memory()
+        h_words = torch.empty(ns, dtype=torch.int32).pin_memory()
+        h_words.copy_(ev.step_word)
+        t_out = None if out is None else out[i * ns:(i + 1) * ns]
+        slabs.append((ev, h_act, h_words, t_out, torch.cuda.Stream(device=dev), rank * n + i * ns))
     torch.cuda.synchronize()
 
     def e2e_steps(k):
         for _ in range(k):
-            rc = lib.coup_host_sample_uniform(C.c_void_p(h_legal.data_ptr()), n, args.seed, rank * n,
-                                              env.step_counter, C.c_void_p(h_act.data_ptr()), threads)
-            assert rc == 0
-            env.step_host(h_act, h_legal, h_cur, h_done, h_rew, tensor_out=out)
+            for ev, h_act, h_words, t_out, stream, offset in slabs:
+                rc = lib.coup_host_sample_uniform(C.c_void_p(h_words.data_ptr()), ns, args.seed, offset,
+                                                  ev.step_counter, C.c_void_p(h_act.data_ptr()), threads)
+                assert rc == 0
+                ev.step_host_packed(h_act, h_words, tensor_out=t_out, stream=stream)
 
-    Ke = max(3, min(K, 100))
+    Ke = max(3, min(K, 200))
     e2e_steps(3)
-    env.clear_stats()
+    for sl in slabs:
+        sl[0].clear_stats()
     barrier()
     t0 = time.perf_counter()
     e2e_steps(Ke)
@@ -285,11 +299,11 @@ def main():
     e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    st2 = env.stats_device.clone()
+    st2 = sum(sl[0].stats_device.clone() for sl in slabs)
     if world > 1:
         dist.all_reduce(st2, op=dist.ReduceOp.SUM)
     st2 = [int(x) for x in st2.cpu()]
-    assert st2[_lib.STAT_DECISION_STEPS] == Ke * n * world and st2[_lib.STAT_ILLEGAL] == 0
+    assert st2[_lib.STAT_DECISION_STEPS] == Ke * ns * S_ * world and st2[_lib.STAT_ILLEGAL] == 0
     e2e_value = st2[_lib.STAT_DECISION_STEPS] / float(e2e_s.item())
 
     clocks = sampler.stop() if rank == 0 else None
@@ -320,10 +334,12 @@ def main():
             "roofline": {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic(contract), "peak_source": peak_src,
                          "bytes_per_launch": bytes_per_launch, "launch_ms": per_launch_s * 1e3},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n, "d2h_bytes_per_step": 8 * n,
-                    "steps": Ke, "host_policy_threads": threads,
-                    "note": "coup_vec_step_host: actions from pinned host memory in, legal mask/current player/done/rewards "
-                            "to pinned host memory out, every step; info-state tensor encoded every step and left in HBM for the on-device consumer"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": ns * S_, "d2h_bytes_per_step": 4 * ns * S_,
+                    "steps": Ke, "host_policy_threads": threads, "sub_slabs": S_,
+                    "note": "coup_vec_step_host_packed on %d sub-slabs (own stream each): uint8 actions from pinned host memory in, "
+                            "one uint32 step word per env (legal mask, current player, done, reward, return) to pinned host memory out, "
+                            "every step; the host policy (coup_host_sample_uniform) picks the next actions from those words; the "
+                            "info-state tensor is encoded every step and left in HBM for the on-device consumer" % S_},
             "gpu_launches": K,
             "clocks": clocks,
             "contracts": extra,

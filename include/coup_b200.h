@@ -155,6 +155,14 @@ const int8_t* coup_vec_current_player(const coup_vec_env* env); /* 0, 1 or -4 te
 const uint8_t* coup_vec_done(const coup_vec_env* env);          /* IsTerminal() of the state just stepped */
 const int8_t* coup_vec_rewards(const coup_vec_env* env);        /* [num_envs][2] Rewards(), coup.cc:1012-1014 */
 const int8_t* coup_vec_returns(const coup_vec_env* env);        /* [num_envs][2] Returns(), coup.cc:1016-1032 */
+/* One word per env with everything a host-side policy needs: bits 0-17 legal mask, 18 current player,
+ * 19 state is terminal, 20 done (an episode ended in this step), 21-23 Rewards()[0]+2, 24-26 Returns()[0]+2. */
+const uint32_t* coup_vec_step_word(const coup_vec_env* env);
+#define COUP_WORD_LEGAL(w) ((w) & 0x3FFFFu)
+#define COUP_WORD_CURRENT_PLAYER(w) (((w) >> 19) & 1u ? COUP_TERMINAL_PLAYER_ID : (int)(((w) >> 18) & 1u))
+#define COUP_WORD_DONE(w) (((w) >> 20) & 1u)
+#define COUP_WORD_REWARD0(w) ((int)(((w) >> 21) & 7u) - 2)
+#define COUP_WORD_RETURN0(w) ((int)(((w) >> 24) & 7u) - 2)
 uint32_t* coup_vec_state(coup_vec_env* env);                    /* [num_envs][4], layout above */
 uint32_t* coup_vec_history(coup_vec_env* env);                  /* [num_envs][16], layout above */
 
@@ -178,9 +186,14 @@ int coup_vec_step_host(coup_vec_env* env, const uint8_t* h_actions, uint32_t* h_
                        int8_t* h_current_player, uint8_t* h_done, int8_t* h_rewards, int dtype,
                        void* d_tensor_out, void* stream);
 
+/* Same, with ONE device->host copy: h_step_words receives coup_vec_step_word() (uint32[num_envs]). */
+int coup_vec_step_host_packed(coup_vec_env* env, const uint8_t* h_actions, uint32_t* h_step_words, int dtype,
+                              void* d_tensor_out, void* stream);
+
 /* Host-side uniform-random POLICY for callers that keep their policy on the host (the host analogue of
  * benchmark_game.cc:96-99): for every env picks the k-th set bit of h_legal_mask[i], k drawn from the same
  * Philox stream coup_vec_sample_uniform would use at step counter `step`; 0xFF where the mask is 0.
+ * Only bits 0-17 of each word are read, so packed step words can be passed directly.
  * Pure bit selection on host memory with `threads` host threads -- no game rule is evaluated. */
 int coup_host_sample_uniform(const uint32_t* h_legal_mask, uint32_t n, uint64_t seed, uint64_t global_env_offset,
                              uint64_t step, uint8_t* h_actions_out, int threads);

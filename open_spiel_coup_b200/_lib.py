@@ -37,8 +37,8 @@ EXPORTED_SYMBOLS = [
     "coup_last_error", "coup_device_count", "coup_vec_create", "coup_vec_destroy", "coup_vec_num_envs",
     "coup_vec_reset", "coup_vec_step", "coup_vec_sample_uniform", "coup_vec_rollout",
     "coup_vec_legal_mask", "coup_vec_current_player", "coup_vec_done", "coup_vec_rewards",
-    "coup_vec_returns", "coup_vec_state", "coup_vec_history", "coup_vec_legal_actions_mask",
-    "coup_vec_information_state_tensor", "coup_vec_observation_tensor", "coup_vec_step_host",
+    "coup_vec_returns", "coup_vec_step_word", "coup_vec_state", "coup_vec_history", "coup_vec_legal_actions_mask",
+    "coup_vec_information_state_tensor", "coup_vec_observation_tensor", "coup_vec_step_host", "coup_vec_step_host_packed",
     "coup_host_sample_uniform", "coup_vec_stats", "coup_vec_stats_device", "coup_vec_clear_stats", "coup_vec_check_errors",
     "coup_tensor_row_hash", "coup_vec_step_counter", "coup_vec_set_step_counter",
 ]
@@ -85,13 +85,14 @@ def load():
     lib.coup_vec_sample_uniform.argtypes = [vp, u8p, vp]
     lib.coup_vec_rollout.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp]
     for name in ("coup_vec_legal_mask", "coup_vec_current_player", "coup_vec_done", "coup_vec_rewards",
-                 "coup_vec_returns", "coup_vec_state", "coup_vec_history", "coup_vec_stats_device"):
+                 "coup_vec_returns", "coup_vec_state", "coup_vec_history", "coup_vec_stats_device", "coup_vec_step_word"):
         getattr(lib, name).argtypes = [vp]
         getattr(lib, name).restype = vp
     lib.coup_vec_legal_actions_mask.argtypes = [vp, vp, vp]
     lib.coup_vec_information_state_tensor.argtypes = [vp, C.c_int, C.c_int, vp, vp]
     lib.coup_vec_observation_tensor.argtypes = [vp, C.c_int, C.c_int, vp, vp]
     lib.coup_vec_step_host.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int, vp, vp]
+    lib.coup_vec_step_host_packed.argtypes = [vp, vp, vp, C.c_int, vp, vp]
     lib.coup_host_sample_uniform.argtypes = [vp, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64, vp, C.c_int]
     lib.coup_vec_stats.argtypes = [vp, vp, vp]
     lib.coup_vec_clear_stats.argtypes = [vp, vp]

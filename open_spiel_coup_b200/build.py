@@ -11,7 +11,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcoup_b200.so")
 SOURCES = ["coup_capi.cu"]
-HEADERS = ["coup_device.cuh", "coup_kernels.cuh", os.path.join("..", "..", "include", "coup_b200.h")]
+HOST_SOURCES = ["coup_host_policy.cc"]   # host compiler only (AVX2 path picked at run time)
+HEADERS = ["coup_host_policy.cc", "coup_device.cuh", "coup_kernels.cuh", os.path.join("..", "..", "include", "coup_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
@@ -31,7 +32,16 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    objs = []
+    for src in HOST_SOURCES:
+        obj = os.path.join(HERE, "build", src + ".o")
+        os.makedirs(os.path.dirname(obj), exist_ok=True)
+        cc = [os.environ.get("CXX", "g++"), "-std=c++17", "-O3", "-fPIC", "-pthread", "-c", os.path.join(CSRC, src), "-o", obj]
+        res = subprocess.run(cc, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("host compile failed:\n" + " ".join(cc) + "\n" + res.stdout + res.stderr)
+        objs.append(obj)
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES] + objs
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)

@@ -8,12 +8,15 @@
 #include <new>
 #include <algorithm>
 #include <string>
-#include <thread>
-#include <vector>
 
 #include "coup_kernels.cuh"
 
 using namespace coup;
+
+namespace coup_host {  // coup_host_policy.cc
+void sample_uniform(const uint32_t* words, uint32_t n, uint64_t seed, uint64_t global_env_offset, uint64_t step,
+                    uint8_t* actions, int threads);
+}
 
 struct coup_vec_env {
   coup_vec_opts opts;
@@ -64,13 +67,6 @@ int launch_status(const char* what) {
 
 bool valid_player_sel(int p) { return p >= COUP_PLAYER_0 && p <= COUP_PLAYER_BOTH; }
 bool valid_dtype(int d) { return d == COUP_DTYPE_F32 || d == COUP_DTYPE_U8 || d == COUP_DTYPE_BF16; }
-
-// First Philox word of `count` consecutive envs (host side of coup_host_sample_uniform). Straight-line
-// arithmetic so that the host compiler can vectorise it; cloned per ISA and dispatched at load time.
-__attribute__((target_clones("avx512f", "avx2", "default")))
-void philox_x_batch(uint64_t seed, uint64_t first_env, uint64_t step, uint32_t count, uint32_t* out) {
-  for (uint32_t i = 0; i < count; ++i) out[i] = env_random(seed, first_env + i, step, 0).x;
-}
 
 bool use_staged_encoder(const coup_vec_env* env) { return (env->opts.flags & COUP_FLAG_PLAIN_STORE_ENCODER) == 0; }
 
@@ -149,6 +145,7 @@ int coup_vec_create(const coup_vec_opts* opts, coup_vec_env** out) {
   alloc(reinterpret_cast<void**>(&A.done), n);
   alloc(reinterpret_cast<void**>(&A.rewards), n * 2);
   alloc(reinterpret_cast<void**>(&A.returns), n * 2);
+  alloc(reinterpret_cast<void**>(&A.step_word), n * sizeof(uint32_t));
   alloc(reinterpret_cast<void**>(&A.stats), COUP_STATS_LEN * sizeof(unsigned long long));
   alloc(reinterpret_cast<void**>(&env->d_actions), n);
   if (err == cudaSuccess) err = cudaEventCreateWithFlags(&env->host_outputs_ready, cudaEventDisableTiming);
@@ -172,6 +169,7 @@ int coup_vec_destroy(coup_vec_env* env) {
   DeviceGuard guard(env->opts.device);
   cudaFree(env->A.state); cudaFree(env->A.history); cudaFree(env->A.legal); cudaFree(env->A.cur_player);
   cudaFree(env->A.done); cudaFree(env->A.rewards); cudaFree(env->A.returns); cudaFree(env->A.stats);
+  cudaFree(env->A.step_word);
   cudaFree(env->d_actions);
   if (env->host_outputs_ready) cudaEventDestroy(env->host_outputs_ready);
   delete env;
@@ -223,6 +221,7 @@ const int8_t* coup_vec_current_player(const coup_vec_env* env) { return env ? en
 const uint8_t* coup_vec_done(const coup_vec_env* env) { return env ? env->A.done : nullptr; }
 const int8_t* coup_vec_rewards(const coup_vec_env* env) { return env ? env->A.rewards : nullptr; }
 const int8_t* coup_vec_returns(const coup_vec_env* env) { return env ? env->A.returns : nullptr; }
+const uint32_t* coup_vec_step_word(const coup_vec_env* env) { return env ? env->A.step_word : nullptr; }
 uint32_t* coup_vec_state(coup_vec_env* env) { return env ? reinterpret_cast<uint32_t*>(env->A.state) : nullptr; }
 uint32_t* coup_vec_history(coup_vec_env* env) { return env ? env->A.history : nullptr; }
 
@@ -288,34 +287,29 @@ int coup_vec_step_host(coup_vec_env* env, const uint8_t* h_actions, uint32_t* h_
   return COUP_OK;
 }
 
+int coup_vec_step_host_packed(coup_vec_env* env, const uint8_t* h_actions, uint32_t* h_step_words, int dtype,
+                              void* d_tensor_out, void* stream) {
+  if (!env || !h_actions || !h_step_words) return fail(COUP_ERR_INVALID_ARG, "coup_vec_step_host_packed: null argument");
+  DeviceGuard guard(env->opts.device);
+  cudaStream_t st = S(stream);
+  const size_t n = env->A.n;
+  CUDA_TRY(cudaMemcpyAsync(env->d_actions, h_actions, n, cudaMemcpyHostToDevice, st));
+  int rc = coup_vec_step(env, env->d_actions, nullptr, stream);
+  if (rc != COUP_OK) return rc;
+  CUDA_TRY(cudaMemcpyAsync(h_step_words, env->A.step_word, n * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaEventRecord(env->host_outputs_ready, st));
+  if (d_tensor_out) {
+    rc = coup_vec_information_state_tensor(env, COUP_PLAYER_CURRENT, dtype, d_tensor_out, stream);
+    if (rc != COUP_OK) return rc;
+  }
+  CUDA_TRY(cudaEventSynchronize(env->host_outputs_ready));
+  return COUP_OK;
+}
+
 int coup_host_sample_uniform(const uint32_t* h_legal_mask, uint32_t n, uint64_t seed, uint64_t global_env_offset,
                              uint64_t step, uint8_t* h_actions_out, int threads) {
   if (!h_legal_mask || !h_actions_out) return fail(COUP_ERR_INVALID_ARG, "coup_host_sample_uniform: null argument");
-  threads = threads < 1 ? 1 : threads;
-  auto work = [=](uint32_t lo, uint32_t hi) {
-    constexpr uint32_t kTile = 1024;
-    uint32_t x[kTile];
-    for (uint32_t base = lo; base < hi; base += kTile) {
-      const uint32_t cnt = std::min(kTile, hi - base);
-      philox_x_batch(seed, global_env_offset + base, step, cnt, x);  // SIMD-friendly pass
-      for (uint32_t j = 0; j < cnt; ++j) {
-        const uint32_t legal = h_legal_mask[base + j];
-        if (legal == 0) { h_actions_out[base + j] = 0xFF; continue; }
-        uint32_t k = mulhi32(x[j], static_cast<uint32_t>(__builtin_popcount(legal)));
-        uint32_t m = legal;
-        while (k--) m &= m - 1;  // drop the k lowest set bits
-        h_actions_out[base + j] = static_cast<uint8_t>(__builtin_ctz(m));
-      }
-    }
-  };
-  if (threads == 1 || n < 4096) { work(0, n); return COUP_OK; }
-  std::vector<std::thread> pool;
-  const uint32_t chunk = (n + threads - 1) / threads;
-  for (int t = 0; t < threads; ++t) {
-    const uint32_t lo = std::min<uint64_t>(n, static_cast<uint64_t>(t) * chunk), hi = std::min<uint64_t>(n, static_cast<uint64_t>(lo) + chunk);
-    if (lo < hi) pool.emplace_back(work, lo, hi);
-  }
-  for (auto& th : pool) th.join();
+  coup_host::sample_uniform(h_legal_mask, n, seed, global_env_offset, step, h_actions_out, threads);
   return COUP_OK;
 }
 

@@ -25,6 +25,7 @@ struct EnvArrays {
   uint8_t* done;       // [n]
   int8_t* rewards;     // [n][2]
   int8_t* returns;     // [n][2]
+  uint32_t* step_word; // [n] everything a host-side policy needs in one word (COUP_WORD_* in coup_b200.h)
   unsigned long long* stats;  // [COUP_STATS_LEN]
   uint32_t n;
   uint32_t flags;
@@ -144,6 +145,9 @@ __device__ __forceinline__ void write_outputs(const EnvArrays& A, uint32_t e, co
   A.done[e] = r.done ? 1 : 0;
   reinterpret_cast<char2*>(A.rewards)[e] = make_char2(static_cast<signed char>(r.reward0), static_cast<signed char>(-r.reward0));
   reinterpret_cast<char2*>(A.returns)[e] = make_char2(static_cast<signed char>(r.return0), static_cast<signed char>(-r.return0));
+  A.step_word[e] = r.legal | (r.cur_player == 1 ? 1u << 18 : 0u) | (r.cur_player < 0 ? 1u << 19 : 0u) |
+                   (r.done ? 1u << 20 : 0u) | (static_cast<uint32_t>(r.reward0 + 2) << 21) |
+                   (static_cast<uint32_t>(r.return0 + 2) << 24);
 }
 
 __device__ __forceinline__ void account(BlockStats& st, const StepResult& r, bool active) {

@@ -68,6 +68,7 @@ class CoupVectorEnv:
         self.returns = _view(L.coup_vec_returns(self._h), (n, 2), "|i1", d, self)
         self.state = _view(L.coup_vec_state(self._h), (n, STATE_WORDS), "<i4", d, self)
         self.history = _view(L.coup_vec_history(self._h), (n, HISTORY_WORDS), "<i4", d, self)
+        self.step_word = _view(L.coup_vec_step_word(self._h), (n,), "<i4", d, self)
         self.stats_device = _view(L.coup_vec_stats_device(self._h), (STATS_LEN,), "<i8", d, self)
 
     def close(self):
@@ -143,6 +144,13 @@ class CoupVectorEnv:
         check(self._lib.coup_vec_step_host(self._h, hp(h_actions), hp(h_legal_mask), hp(h_current_player),
                                            hp(h_done), hp(h_rewards), dt, self._ptr(tensor_out),
                                            _stream_ptr(self.device)))
+
+    def step_host_packed(self, h_actions, h_step_words, tensor_out=None, stream=None):
+        """Host-buffer path with one D2H copy: h_step_words (int32 [n], pinned) receives `step_word`."""
+        dt = _TORCH_TO_DTYPE[tensor_out.dtype] if tensor_out is not None else 0
+        sp = _stream_ptr(self.device) if stream is None else C.c_void_p(stream.cuda_stream)
+        check(self._lib.coup_vec_step_host_packed(self._h, C.c_void_p(h_actions.data_ptr()),
+                                                  C.c_void_p(h_step_words.data_ptr()), dt, self._ptr(tensor_out), sp))
 
     # ---- observations ---------------------------------------------------------------------------
     def information_state_tensor(self, player=PLAYER_CURRENT, out=None, dtype=torch.float32):

@@ -429,6 +429,41 @@ def test_step_host_path():
         assert torch.equal(tensor, ref.information_state_tensor(_lib.PLAYER_CURRENT))
 
 
+def test_step_host_packed_and_host_policy():
+    """One-copy host path: the packed step word carries legal mask / current player / done / rewards /
+    returns, and the host-side uniform policy draws exactly what the device sampler draws."""
+    import ctypes as C
+    n = 5000
+    lib = _lib.load()
+    seed, offset = 4242, 1 << 20
+    env = CoupVectorEnv(n, seed=seed, auto_reset=True, global_env_offset=offset)
+    ref = CoupVectorEnv(n, seed=seed, auto_reset=True, global_env_offset=offset)
+    h_act = torch.empty(n, dtype=torch.uint8).pin_memory()
+    h_words = torch.empty(n, dtype=torch.int32).pin_memory()
+    h_words.copy_(env.step_word.cpu())
+    tensor = torch.empty((n, INFO), dtype=torch.float32, device=env.device)
+    side = torch.cuda.Stream()
+    for it in range(40):
+        dev_acts = ref.sample_uniform()
+        rc = lib.coup_host_sample_uniform(C.c_void_p(h_words.data_ptr()), n, seed, offset, env.step_counter,
+                                          C.c_void_p(h_act.data_ptr()), 3 if it % 2 else 1)
+        assert rc == 0
+        assert torch.equal(h_act, dev_acts.cpu()), "host policy and device sampler disagree"
+        env.step_host_packed(h_act, h_words, tensor_out=tensor, stream=side if it % 3 == 0 else None)
+        ref.step(dev_acts)
+        w = h_words.numpy().view(np.uint32)
+        np.testing.assert_array_equal(w & 0x3FFFF, ref.legal_mask.cpu().numpy().view(np.uint32))
+        cur = np.where((w >> 19) & 1, -4, (w >> 18) & 1)
+        np.testing.assert_array_equal(cur, ref.current_player.cpu().numpy())
+        np.testing.assert_array_equal((w >> 20) & 1, ref.done.cpu().numpy())
+        np.testing.assert_array_equal(((w >> 21) & 7).astype(np.int64) - 2, ref.rewards.cpu().numpy()[:, 0])
+        np.testing.assert_array_equal(((w >> 24) & 7).astype(np.int64) - 2, ref.returns.cpu().numpy()[:, 0])
+        side.synchronize()
+        assert torch.equal(tensor, ref.information_state_tensor(_lib.PLAYER_CURRENT))
+        assert torch.equal(env.step_word, ref.step_word)
+    assert env.stats() == ref.stats()
+
+
 def test_statistical_parity_with_reference_workload():
     """SURVEY.md section 6 (1.6 M reference episodes): 21.20 moves/episode = 15.03 decisions + 6.17 chance;
     mean legal actions 3.59; P0 returns -2/-1/0/+1/+2 = 30.4/20.5/0/20.0/29.1 %."""
