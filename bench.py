@@ -185,9 +185,8 @@ def main():
     from open_spiel_coup_b200 import _lib
     from open_spiel_coup_b200.vector_env import CoupVectorEnv
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    from open_spiel_coup_b200.distributed import reduce_stats, shard_envs, world_from_env
+    rank, local, world = world_from_env()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the Coup environment has no CPU fallback")
     torch.cuda.set_device(local)
@@ -196,9 +195,11 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     n, K, W = args.envs, args.steps, max(args.warmup, 3)
+    slab_offset, slab_count = shard_envs(n * world, world, rank)   # weak scaling: n envs per GPU
+    assert slab_count == n
     contract = args.contract
     torch_dtype = {"d32": torch.float32, "bf16": torch.bfloat16, "d8": torch.uint8, "env": None}[contract]
-    env = CoupVectorEnv(n, seed=args.seed, device=local, global_env_offset=rank * n, auto_reset=True,
+    env = CoupVectorEnv(n, seed=args.seed, device=local, global_env_offset=slab_offset, auto_reset=True,
                         plain_store_encoder=(args.encoder == "plain"))
     out = None if torch_dtype is None else torch.empty((n, 2492), dtype=torch_dtype, device=dev)
     sel = None if out is None else _lib.PLAYER_CURRENT
@@ -231,9 +232,7 @@ def main():
     env.rollout(W, sel, out=out)
     env.clear_stats()
     ms = timed(lambda k: env.rollout(k, sel, out=out), K)
-    stats = env.stats_device.clone()
-    if world > 1:
-        dist.all_reduce(stats, op=dist.ReduceOp.SUM)      # the one collective: NCCL sum of the stats vector
+    stats = reduce_stats(env.stats_device)               # the one collective: NCCL sum of the stats vector
     stats = [int(x) for x in stats.cpu()]
     steps_done = stats[_lib.STAT_DECISION_STEPS]
     assert steps_done == K * n * world and stats[_lib.STAT_ILLEGAL] == 0, (steps_done, K * n * world, stats[_lib.STAT_ILLEGAL])
@@ -270,14 +269,14 @@ def main():
     torch.cuda.empty_cache()
     slabs = []
     for i in range(S_):
-        ev = CoupVectorEnv(ns, seed=args.seed, device=local, global_env_offset=rank * n + i * ns, auto_reset=True,
+        ev = CoupVectorEnv(ns, seed=args.seed, device=local, global_env_offset=slab_offset + i * ns, auto_reset=True,
                            plain_store_encoder=(args.encoder == "plain"))
         ev.rollout(100)
         h_act = torch.empty(ns, dtype=torch.uint8).pin_memory()
         h_words = torch.empty(ns, dtype=torch.int32).pin_memory()
         h_words.copy_(ev.step_word)
         t_out = None if out is None else out[i * ns:(i + 1) * ns]
-        slabs.append((ev, h_act, h_words, t_out, torch.cuda.Stream(device=dev), rank * n + i * ns))
+        slabs.append((ev, h_act, h_words, t_out, torch.cuda.Stream(device=dev), slab_offset + i * ns))
     torch.cuda.synchronize()
 
     def e2e_steps(k):
@@ -299,9 +298,7 @@ def main():
     e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    st2 = sum(sl[0].stats_device.clone() for sl in slabs)
-    if world > 1:
-        dist.all_reduce(st2, op=dist.ReduceOp.SUM)
+    st2 = reduce_stats(sum(sl[0].stats_device.clone() for sl in slabs))
     st2 = [int(x) for x in st2.cpu()]
     assert st2[_lib.STAT_DECISION_STEPS] == Ke * ns * S_ * world and st2[_lib.STAT_ILLEGAL] == 0
     e2e_value = st2[_lib.STAT_DECISION_STEPS] / float(e2e_s.item())

@@ -128,6 +128,7 @@ class Oracle:
         L.oc_state_from_actions.argtypes = [P(OcState), C.c_void_p, C.c_int]
         L.oc_final_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.oc_final_tensors_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.oc_replay_digest_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.oc_batch_init.argtypes = [C.c_void_p, C.c_int]
         L.oc_batch_apply.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.oc_batch_info_state.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
@@ -242,6 +243,16 @@ class Oracle:
             ti.ctypes.data if info else None, to.ctypes.data if obs else None)
         return ti, to, bad
 
+    def replay_digest_batch(self, actions, offsets, threads=1):
+        """(digests uint64[n], reports int32[n], rejected) -- see ref_replay_digest in ref_harness.cc."""
+        a = _u8(actions)
+        off = np.ascontiguousarray(offsets, np.int64)
+        n_traj = len(off) - 1
+        dig = np.zeros(n_traj, np.uint64)
+        rep = np.zeros(n_traj, np.int32)
+        bad = self.lib.oc_replay_digest_batch(a.ctypes.data, off.ctypes.data, n_traj, dig.ctypes.data, rep.ctypes.data)
+        return dig, rep, bad
+
     # -- batches ------------------------------------------------------------------------------
     def batch_new(self, n):
         arr = (OcState * n)()
@@ -336,6 +347,7 @@ class Reference:
         L.ref_tensor_hash.restype = C.c_uint64
         L.ref_trace.argtypes = [vp, C.c_int, vp]
         L.ref_trace_batch.argtypes = [vp, vp, C.c_int, vp, C.c_int]
+        L.ref_replay_digest_batch.argtypes = [vp, vp, C.c_int, vp, vp, C.c_int]
         L.ref_state_from_actions.argtypes = [vp, C.c_int]
         L.ref_state_from_actions.restype = vp
         L.ref_bench.argtypes = [C.c_int, C.c_int, C.c_long, C.c_uint32, vp]
@@ -491,6 +503,16 @@ class Reference:
         out = np.zeros(len(a) + n_traj, TRACE_DTYPE)
         bad = self.lib.ref_trace_batch(a.ctypes.data, off.ctypes.data, n_traj, out.ctypes.data, threads)
         return out, bad
+
+    def replay_digest_batch(self, actions, offsets, threads=8):
+        a = _u8(actions)
+        off = np.ascontiguousarray(offsets, np.int64)
+        n_traj = len(off) - 1
+        dig = np.zeros(n_traj, np.uint64)
+        rep = np.zeros(n_traj, np.int32)
+        bad = self.lib.ref_replay_digest_batch(a.ctypes.data, off.ctypes.data, n_traj, dig.ctypes.data,
+                                               rep.ctypes.data, threads)
+        return dig, rep, bad
 
     def bench(self, mode, threads, episodes, seed=1234):
         out = np.zeros(21, np.float64)

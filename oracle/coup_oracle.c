@@ -715,6 +715,55 @@ int oc_state_from_actions(oc_state* s, const uint8_t* actions, int n_actions) {
   return OC_OK;
 }
 
+/* Replay digest: same definition as ref_replay_digest in oracle/ref_harness.cc (see there). */
+static void fold(uint64_t* d, uint64_t v) { *d = *d * 0x9E3779B97F4A7C15ULL + v + 1; }
+
+int oc_replay_digest(const uint8_t* actions, int n_actions, uint64_t* digest_out) {
+  float info[OC_INFO_STATE_SIZE];
+  float obs[OC_OBSERVATION_SIZE];
+  oc_state s;
+  uint64_t d = 0;
+  int reports = 0;
+  oc_init(&s);
+  for (int i = 0; i < n_actions; ++i) {
+    if (oc_apply_action(&s, actions[i]) != OC_OK) return -(i + 1);
+    if (!oc_is_chance_node(&s)) {
+      int term = oc_is_terminal(&s);
+      double rew[2], ret[2];
+      fold(&d, term ? 0u : oc_legal_mask(&s));
+      fold(&d, (uint64_t)oc_current_player(&s) & 0xFF);
+      fold(&d, (uint64_t)term);
+      oc_rewards(&s, rew);
+      oc_returns(&s, ret);
+      fold(&d, (uint64_t)((int)rew[0] + 2));
+      fold(&d, (uint64_t)((int)rew[1] + 2));
+      fold(&d, (uint64_t)((int)ret[0] + 2));
+      fold(&d, (uint64_t)((int)ret[1] + 2));
+      for (int p = 0; p < 2; ++p) {
+        oc_information_state_tensor(&s, p, info);
+        fold(&d, oc_tensor_hash(info, OC_INFO_STATE_SIZE));
+      }
+      for (int p = 0; p < 2; ++p) {
+        oc_observation_tensor(&s, p, obs);
+        fold(&d, oc_tensor_hash(obs, OC_OBSERVATION_SIZE));
+      }
+      reports++;
+    }
+  }
+  *digest_out = d;
+  return reports;
+}
+
+int oc_replay_digest_batch(const uint8_t* actions, const int64_t* offsets, int n_traj, uint64_t* digests,
+                           int32_t* reports) {
+  int bad = 0;
+  for (int t = 0; t < n_traj; ++t) {
+    reports[t] = oc_replay_digest(actions + offsets[t], (int)(offsets[t + 1] - offsets[t]), &digests[t]);
+    if (reports[t] < 0) bad++;
+  }
+  return bad;
+}
+
 /* ------------------------------------------------------------------------------------------------
  * Batched helpers
  * ---------------------------------------------------------------------------------------------- */

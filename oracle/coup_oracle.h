@@ -128,6 +128,10 @@ int oc_state_from_actions(oc_state* s, const uint8_t* actions, int n_actions);
 int oc_final_batch(const uint8_t* actions, const int64_t* offsets, int n_traj, oc_trace_rec* out);
 int oc_final_tensors_batch(const uint8_t* actions, const int64_t* offsets, int n_traj, float* info, float* obs);
 
+int oc_replay_digest(const uint8_t* actions, int n_actions, uint64_t* digest_out);
+int oc_replay_digest_batch(const uint8_t* actions, const int64_t* offsets, int n_traj, uint64_t* digests,
+                           int32_t* reports);
+
 /* Batched helpers over an array of states (used by the GPU parity tests). */
 void oc_batch_init(oc_state* s, int n);
 /* Applies actions[i] to state i when do_mask is NULL or do_mask[i] != 0. Returns #errors. */

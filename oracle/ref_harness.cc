@@ -312,6 +312,84 @@ void* ref_state_from_actions(const uint8_t* actions, int n_actions) {
   return st.release();
 }
 
+// ---- replay digests (BASELINE config 5: bit-exactness replay of GPU trajectories) -------------------
+// For one trajectory (action ids incl. chance outcomes) walks the reference and, at every state a
+// batched env REPORTS -- the first decision node after the initial deals, then the decision/terminal
+// node reached after each player action once the following chance nodes are resolved -- folds
+//   legal mask, current player (& 0xFF), is_terminal, rewards+2, returns+2, hash(info-state P0), hash(info-state P1),
+//   hash(observation P0), hash(observation P1)
+// into D = D * 0x9E3779B97F4A7C15 + v + 1 (mod 2^64). The GPU side folds the same fields in the same order
+// (scripts/replay_check.py), so equal digests <=> identical legal sets, tensors, terminal flags, rewards, returns
+// at every step of the trajectory. Returns the number of reported states, or -(i+1) if move i raised.
+static inline void Fold(uint64_t& d, uint64_t v) { d = d * 0x9E3779B97F4A7C15ULL + v + 1; }
+
+static void FoldState(const State& st, uint64_t& d, std::vector<float>& info, std::vector<float>& obs) {
+  uint32_t m = 0;
+  const bool term = st.IsTerminal();
+  if (!term) for (Action a : st.LegalActions()) m |= 1u << a;
+  Fold(d, m);
+  Fold(d, static_cast<uint64_t>(st.CurrentPlayer()) & 0xFF);
+  Fold(d, term ? 1 : 0);
+  auto rew = st.Rewards();
+  auto ret = st.Returns();
+  Fold(d, static_cast<uint64_t>(static_cast<int>(rew[0]) + 2));
+  Fold(d, static_cast<uint64_t>(static_cast<int>(rew[1]) + 2));
+  Fold(d, static_cast<uint64_t>(static_cast<int>(ret[0]) + 2));
+  Fold(d, static_cast<uint64_t>(static_cast<int>(ret[1]) + 2));
+  for (int p = 0; p < 2; ++p) {
+    st.InformationStateTensor(p, absl::MakeSpan(info));
+    Fold(d, TensorHash(info.data(), static_cast<int>(info.size())));
+  }
+  for (int p = 0; p < 2; ++p) {
+    st.ObservationTensor(p, absl::MakeSpan(obs));
+    Fold(d, TensorHash(obs.data(), static_cast<int>(obs.size())));
+  }
+}
+
+int ref_replay_digest(const uint8_t* actions, int n_actions, uint64_t* digest_out) {
+  auto g = TheGame();
+  std::vector<float> info(g->InformationStateTensorSize()), obs(g->ObservationTensorSize());
+  auto st = g->NewInitialState();
+  uint64_t d = 0;
+  int reports = 0;
+  for (int i = 0; i < n_actions; ++i) {
+    try {
+      if (st->IsTerminal()) throw RefError("ApplyAction on terminal state");
+      st->ApplyAction(actions[i]);
+    } catch (const RefError& e) {
+      g_last_error = e.what();
+      return -(i + 1);
+    }
+    if (!st->IsChanceNode()) {
+      FoldState(*st, d, info, obs);
+      ++reports;
+    }
+  }
+  *digest_out = d;
+  return reports;
+}
+
+// Batched over trajectories; digests[t], reports[t] (negative = rejected). Returns #rejected.
+int ref_replay_digest_batch(const uint8_t* actions, const int64_t* offsets, int n_traj, uint64_t* digests,
+                            int32_t* reports, int threads) {
+  TheGame();
+  std::atomic<int> next{0}, bad{0};
+  auto work = [&] {
+    while (true) {
+      int t0 = next.fetch_add(256);
+      if (t0 >= n_traj) break;
+      for (int t = t0; t < std::min(n_traj, t0 + 256); ++t) {
+        reports[t] = ref_replay_digest(actions + offsets[t], static_cast<int>(offsets[t + 1] - offsets[t]), &digests[t]);
+        if (reports[t] < 0) bad.fetch_add(1);
+      }
+    }
+  };
+  std::vector<std::thread> th;
+  for (int i = 0; i < std::max(1, threads); ++i) th.emplace_back(work);
+  for (auto& x : th) x.join();
+  return bad.load();
+}
+
 // CPU baseline: the reference's own rollout benchmark protocol (examples/benchmark_game.cc:32-140):
 // uniform-random legal actions, SampleAction on ChanceOutcomes(), one Game-independent State and one
 // std::mt19937 per thread. mode 0: step + LegalActions only; 1: + InformationStateTensor(current

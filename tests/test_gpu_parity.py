@@ -529,6 +529,60 @@ def test_philox_stream_matches_specification():
         env.step(torch.as_tensor(acts, device=env.device))
 
 
+def test_device_trajectories_reproduced_from_philox_and_oracle(oracle):
+    """Exact, not statistical: given (seed, global env id, step counter) the device's action choices, chance
+    draws and auto-reset deals are those of the documented stream -- Philox4x32-10 words mapped with
+    floor(u * n / 2^32) -- so NumPy Philox + the CPU oracle reproduce every trajectory move for move."""
+    n, seed, offset = 160, 0xDEADBEEF12345678, 77
+    env = CoupVectorEnv(n, seed=seed, global_env_offset=offset, auto_reset=True)
+
+    def words(step, purpose):
+        genv = offset + np.arange(n, dtype=np.uint64)
+        key = np.stack([genv & np.uint64(0xFFFFFFFF), ((genv >> np.uint64(32)) ^ np.uint64(seed & 0xFFFFFFFF)) & np.uint64(0xFFFFFFFF)], -1).astype(np.uint32)
+        ctr = np.zeros((n, 4), np.uint32)
+        ctr[:, 0], ctr[:, 1], ctr[:, 2], ctr[:, 3] = step & 0xFFFFFFFF, step >> 32, purpose, seed >> 32
+        return _philox4x32_10(ctr, key)
+
+    def draw_card(s, u):
+        deck = [s.deck[i] for i in range(5)]
+        r = (int(u) * sum(deck)) >> 32
+        c = 0
+        while r >= deck[c]:
+            r -= deck[c]
+            c += 1
+        return c
+
+    def deal(s, us):
+        k = 0
+        while oracle.current_player(s) == -1:
+            assert oracle.apply(s, draw_card(s, us[k])) == 0
+            k += 1
+
+    states = []
+    w = words(0, 1)                                   # the reset at creation used step counter 0
+    for e in range(n):
+        s = oracle.new_state()
+        deal(s, w[e])
+        states.append(s)
+    for t in range(45):
+        step = env.step_counter
+        env.rollout(1)
+        w0, w1 = words(step, 0), words(step, 1)
+        for e in range(n):
+            s = states[e]
+            la = oracle.legal_actions(s)
+            assert oracle.apply(s, la[(int(w0[e, 0]) * len(la)) >> 32]) == 0
+            deal(s, w0[e, 1:])
+            if oracle.is_terminal(s):
+                s = states[e] = oracle.new_state()
+                deal(s, w1[e])
+        got = env.trajectories()
+        for e in range(n):
+            s = states[e]
+            assert list(got[e][0]) == [s.history_action[i] for i in range(s.history_len)], (t, e)
+    assert env.stats()["episodes"] > n
+
+
 @pytest.mark.parametrize("n", [1, 31, 33, 255, 257])
 def test_ragged_sizes(oracle, n):
     env = CoupVectorEnv(n, seed=n, auto_reset=True, plain_store_encoder=(n % 2 == 0))
