@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline sample budget")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra-contracts", action="store_true")
+    ap.add_argument("--no-selfplay", action="store_true")
     ap.add_argument("--e2e-slabs", type=int, default=4, help="sub-slabs (handles/streams) of the host-buffer leg")
     ap.add_argument("--encoder", default="staged", choices=["staged", "plain"],
                     help="info-state encoder: shared-memory staging + bulk (TMA) stores, or per-lane vector stores")
@@ -303,6 +304,28 @@ def main():
     assert st2[_lib.STAT_DECISION_STEPS] == Ke * ns * S_ * world and st2[_lib.STAT_ILLEGAL] == 0
     e2e_value = st2[_lib.STAT_DECISION_STEPS] / float(e2e_s.item())
 
+    # ---- BASELINE configs[3]: self-play data generation, MLP policy on the info-state tensor, 2^18 envs ----
+    selfplay = None
+    if not args.no_selfplay:
+        from open_spiel_coup_b200.selfplay import MLPPolicy, SelfPlayDataGen
+        for sl in slabs:
+            sl[0].close()
+        del slabs, out
+        torch.cuda.empty_cache()
+        torch.manual_seed(args.seed)
+        n_sp = 1 << 18
+        gen = SelfPlayDataGen(num_envs=n_sp, policy=MLPPolicy(), seed=args.seed, device=local,
+                              global_env_offset=rank * n_sp, reservoir_capacity=0)
+        gen.env.rollout(100)
+        gen.run(5)
+        k_sp = max(10, min(K, 60))
+        ms_sp = timed(lambda k: gen.run(k), k_sp)
+        selfplay = {"steps_per_s": k_sp * n_sp * world / (ms_sp * 1e-3), "envs_per_gpu": n_sp, "ms_per_step": ms_sp / k_sp,
+                    "policy": "MLP 2492-1024-1024-18 (bf16, torch), masked softmax sampling fused on device (k_sample_policy)",
+                    "note": "per step: encode bf16 info-state of the player to move, policy forward, masked sampling, env step"}
+        del gen
+        torch.cuda.empty_cache()
+
     clocks = sampler.stop() if rank == 0 else None
 
     cpu = None
@@ -340,6 +363,7 @@ def main():
             "gpu_launches": K,
             "clocks": clocks,
             "contracts": extra,
+            "selfplay": selfplay,
             "episodes": stats[_lib.STAT_EPISODES], "moves_per_episode": stats[_lib.STAT_EPISODE_MOVES] / max(1, stats[_lib.STAT_EPISODES]),
             "moves_per_s": value * (stats[_lib.STAT_DECISION_STEPS] + stats[_lib.STAT_CHANCE_MOVES]) / max(1, stats[_lib.STAT_DECISION_STEPS]),
         }

@@ -142,6 +142,13 @@ int coup_vec_step(coup_vec_env* env, const uint8_t* d_actions, const uint8_t* d_
  * writes uint8[num_envs] to d_actions_out (terminal envs get 0xFF). */
 int coup_vec_sample_uniform(coup_vec_env* env, uint8_t* d_actions_out, void* stream);
 
+/* Masked policy sampling, the acting rule of the reference's agents (python/algorithms/nfsp.py:154-167:
+ * softmax, zero the illegal actions, renormalise, sample): d_logits is dtype[num_envs][18] (COUP_DTYPE_F32 or
+ * COUP_DTYPE_BF16) on the device; writes the sampled action ids to d_actions_out (uint8[num_envs], 0xFF for
+ * terminal envs) and, if d_probs_out is not NULL, the renormalised probabilities float[num_envs][18]. */
+int coup_vec_sample_policy(coup_vec_env* env, const void* d_logits, int dtype, float* d_probs_out,
+                           uint8_t* d_actions_out, void* stream);
+
 /* Fused random rollout: n_steps x (sample uniform legal action, step, resolve chance, [auto-reset],
  * encode). encode_player: COUP_PLAYER_* or -1 for no tensor. d_tensor_out: dtype[rows][2492] where
  * rows = num_envs (x2 for COUP_PLAYER_BOTH); it is overwritten at every step (the consumer reads it

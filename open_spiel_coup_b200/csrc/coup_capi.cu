@@ -203,6 +203,21 @@ int coup_vec_sample_uniform(coup_vec_env* env, uint8_t* d_actions_out, void* str
   return launch_status("k_sample_uniform");
 }
 
+int coup_vec_sample_policy(coup_vec_env* env, const void* d_logits, int dtype, float* d_probs_out,
+                           uint8_t* d_actions_out, void* stream) {
+  if (!env || !d_logits || !d_actions_out || (dtype != COUP_DTYPE_F32 && dtype != COUP_DTYPE_BF16))
+    return fail(COUP_ERR_INVALID_ARG, "coup_vec_sample_policy: bad arguments (logits must be f32 or bf16)");
+  DeviceGuard guard(env->opts.device);
+  const unsigned grid = blocks_for(env->A.n);
+  if (dtype == COUP_DTYPE_F32)
+    k_sample_policy<float><<<grid, kBlockThreads, 0, S(stream)>>>(env->A, static_cast<const float*>(d_logits), d_probs_out,
+                                                                    d_actions_out, env->step_counter);
+  else
+    k_sample_policy<__nv_bfloat16><<<grid, kBlockThreads, 0, S(stream)>>>(
+        env->A, static_cast<const __nv_bfloat16*>(d_logits), d_probs_out, d_actions_out, env->step_counter);
+  return launch_status("k_sample_policy");
+}
+
 int coup_vec_rollout(coup_vec_env* env, int n_steps, int encode_player, int dtype, void* d_tensor_out, void* stream) {
   if (!env || n_steps < 0) return fail(COUP_ERR_INVALID_ARG, "coup_vec_rollout: bad arguments");
   if (encode_player >= 0 && (!valid_player_sel(encode_player) || !valid_dtype(dtype) || !d_tensor_out))

@@ -220,6 +220,59 @@ k_sample_uniform(EnvArrays A, uint8_t* __restrict__ actions_out, uint64_t step) 
   actions_out[e] = static_cast<uint8_t>(a);
 }
 
+// ---- masked policy sampling: the acting rule of the reference's agents (python/algorithms/nfsp.py:154-167)
+// fused on the device: probs = softmax(logits); illegal -> 0; renormalise; action ~ probs. One thread per
+// env; the draw is the x word of the step's Philox block (the slot coup_vec_sample_uniform uses).
+template <typename T> __device__ __forceinline__ float logit_to_float(T v);
+template <> __device__ __forceinline__ float logit_to_float<float>(float v) { return v; }
+template <> __device__ __forceinline__ float logit_to_float<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename T>
+__global__ void __launch_bounds__(kBlockThreads)
+k_sample_policy(EnvArrays A, const T* __restrict__ logits, float* __restrict__ probs_out,
+                uint8_t* __restrict__ actions_out, uint64_t step) {
+  const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= A.n) return;
+  const uint32_t legal = A.legal[e];
+  const T* row = logits + static_cast<size_t>(e) * kNumActions;
+  float p[kNumActions];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int a = 0; a < kNumActions; ++a) {
+    p[a] = logit_to_float<T>(row[a]);
+    if ((legal >> a) & 1u) mx = fmaxf(mx, p[a]);
+  }
+  // softmax over all actions followed by masking and renormalising == softmax over the legal ones;
+  // subtracting the legal maximum keeps it finite.
+  float sum = 0.f;
+#pragma unroll
+  for (int a = 0; a < kNumActions; ++a) {
+    p[a] = ((legal >> a) & 1u) ? expf(p[a] - mx) : 0.f;
+    sum += p[a];
+  }
+  uint32_t action = 0xFFu;
+  if (legal != 0) {
+    const float inv = 1.f / sum;
+    const uint4 rnd = env_random(A.seed, A.global_env_offset + e, step, 0);
+    const float u = static_cast<float>(rnd.x >> 8) * (1.0f / 16777216.0f);  // 24-bit uniform in [0,1)
+    float cdf = 0.f;
+    action = 31u - __clz(legal);  // falls back to the last legal action if rounding leaves u >= cdf
+    bool found = false;
+#pragma unroll
+    for (int a = 0; a < kNumActions; ++a) {
+      p[a] *= inv;
+      cdf += p[a];
+      if (!found && ((legal >> a) & 1u) && u < cdf) { action = a; found = true; }
+    }
+  }
+  if (probs_out != nullptr) {
+    float* o = probs_out + static_cast<size_t>(e) * kNumActions;
+#pragma unroll
+    for (int a = 0; a < kNumActions; ++a) o[a] = legal ? p[a] : 0.f;
+  }
+  actions_out[e] = static_cast<uint8_t>(action);
+}
+
 // ---- dense legal mask: uint8[n][18] (State::LegalActionsMask, spiel.cc:371-377) ----------------------
 __global__ void __launch_bounds__(kBlockThreads)
 k_legal_actions_mask(const uint32_t* __restrict__ legal, uint8_t* __restrict__ out, uint32_t n) {

@@ -122,6 +122,17 @@ class CoupVectorEnv:
         check(self._lib.coup_vec_sample_uniform(self._h, self._ptr(out), _stream_ptr(self.device)))
         return out
 
+    def sample_policy(self, logits, probs_out=None, actions_out=None):
+        """Masked softmax sampling (nfsp.py:154-167) from logits [num_envs, 18] (float32 or bfloat16)."""
+        logits = logits.contiguous()
+        if tuple(logits.shape) != (self.num_envs, NUM_DISTINCT_ACTIONS):
+            raise ValueError(f"logits must be [{self.num_envs}, {NUM_DISTINCT_ACTIONS}]")
+        if actions_out is None:
+            actions_out = torch.empty(self.num_envs, dtype=torch.uint8, device=self.device)
+        check(self._lib.coup_vec_sample_policy(self._h, self._ptr(logits), _TORCH_TO_DTYPE[logits.dtype],
+                                               self._ptr(probs_out), self._ptr(actions_out), _stream_ptr(self.device)))
+        return actions_out
+
     def rollout(self, n_steps, encode_player=None, out=None, dtype=torch.float32):
         """n_steps fused (uniform-random action, step, chance, [auto-reset], encode) kernels."""
         if encode_player is None:
