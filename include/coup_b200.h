@@ -138,6 +138,18 @@ int coup_vec_reset(coup_vec_env* env, const uint8_t* d_reset_mask, const uint8_t
 int coup_vec_step(coup_vec_env* env, const uint8_t* d_actions, const uint8_t* d_forced_chance,
                   void* stream);
 
+/* ---- the OpenSpiel State surface with EXPLICIT chance nodes (one move at a time), used by the single-state
+ * Game/State mirror (open_spiel_coup_b200/spiel.py). Envs driven this way can sit at chance nodes; then
+ * coup_vec_current_player() is COUP_CHANCE_PLAYER_ID, the legal mask holds the card ids still in the deck
+ * (coup.cc:828-836) and bit 27 of the step word is set. Do not mix with coup_vec_step/rollout on one handle.
+ *   coup_vec_new_initial_state: CoupState ctor (coup.cc:393-428) WITHOUT dealing; d_mask as in coup_vec_reset.
+ *   coup_vec_apply_move: State::ApplyAction (spiel.cc:322-332): d_moves uint8[num_envs], a card id at a
+ *     chance node / an action id at a decision node, 0xFF = leave the env untouched.
+ *   coup_vec_copy_env: State::Clone (coup.cc:1058-1060) from slot src to slot dst. */
+int coup_vec_new_initial_state(coup_vec_env* env, const uint8_t* d_mask, void* stream);
+int coup_vec_apply_move(coup_vec_env* env, const uint8_t* d_moves, void* stream);
+int coup_vec_copy_env(coup_vec_env* env, uint32_t src, uint32_t dst, void* stream);
+
 /* Uniform-random legal action per env (the policy of benchmark_game.cc:96-99), Philox-driven:
  * writes uint8[num_envs] to d_actions_out (terminal envs get 0xFF). */
 int coup_vec_sample_uniform(coup_vec_env* env, uint8_t* d_actions_out, void* stream);

@@ -194,6 +194,27 @@ int coup_vec_step(coup_vec_env* env, const uint8_t* d_actions, const uint8_t* d_
   return launch_status("k_step");
 }
 
+int coup_vec_new_initial_state(coup_vec_env* env, const uint8_t* d_mask, void* stream) {
+  if (!env) return fail(COUP_ERR_INVALID_ARG, "null handle");
+  DeviceGuard guard(env->opts.device);
+  k_single_move<<<blocks_for(env->A.n), kBlockThreads, 0, S(stream)>>>(env->A, d_mask, 0);
+  return launch_status("k_single_move(new_initial_state)");
+}
+
+int coup_vec_apply_move(coup_vec_env* env, const uint8_t* d_moves, void* stream) {
+  if (!env || !d_moves) return fail(COUP_ERR_INVALID_ARG, "coup_vec_apply_move: null argument");
+  DeviceGuard guard(env->opts.device);
+  k_single_move<<<blocks_for(env->A.n), kBlockThreads, 0, S(stream)>>>(env->A, d_moves, 1);
+  return launch_status("k_single_move(apply_move)");
+}
+
+int coup_vec_copy_env(coup_vec_env* env, uint32_t src, uint32_t dst, void* stream) {
+  if (!env || src >= env->A.n || dst >= env->A.n) return fail(COUP_ERR_INVALID_ARG, "coup_vec_copy_env: bad index");
+  DeviceGuard guard(env->opts.device);
+  k_copy_env<<<1, 32, 0, S(stream)>>>(env->A, src, dst);
+  return launch_status("k_copy_env");
+}
+
 int coup_vec_sample_uniform(coup_vec_env* env, uint8_t* d_actions_out, void* stream) {
   if (!env || !d_actions_out) return fail(COUP_ERR_INVALID_ARG, "coup_vec_sample_uniform: null argument");
   DeviceGuard guard(env->opts.device);

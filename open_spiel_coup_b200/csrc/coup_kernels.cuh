@@ -206,6 +206,77 @@ k_step(EnvArrays A, const uint8_t* __restrict__ actions, const uint8_t* __restri
   st.flush(A.stats);
 }
 
+// ---- single moves with explicit chance nodes (the OpenSpiel State surface: State::ApplyAction at any
+// node, spiel.cc:322-332, without the rl_environment-style chance resolution of k_step) ----------------
+__device__ __forceinline__ void write_outputs_any_node(const EnvArrays& A, uint32_t e, const Env& s) {
+  StepResult r = {};
+  const bool term = is_terminal(s);
+  const bool chance = !term && g_chance(s.g);
+  r.legal = term ? 0u : chance ? legal_mask_chance(s) : legal_mask_decision(s);           // coup.cc:824-938
+  r.cur_player = term ? COUP_TERMINAL_PLAYER_ID : chance ? COUP_CHANCE_PLAYER_ID : static_cast<int>(g_mover(s.g));
+  r.done = term;
+  r.reward0 = c_reward0(s.c);
+  r.return0 = returns_p0(s);
+  write_outputs(A, e, r);
+  if (chance) A.step_word[e] |= 1u << 27;
+}
+
+// mode 0: CoupState ctor only (env left at its first chance node); mode 1: apply one move per env
+// (0xFF = leave untouched). An illegal move sets the sticky error bit and changes nothing else.
+__global__ void __launch_bounds__(kBlockThreads)
+k_single_move(EnvArrays A, const uint8_t* __restrict__ moves_or_mask, int mode) {
+  __shared__ uint32_t s_stats[COUP_STATS_LEN];
+  BlockStats st;
+  st.init(s_stats);
+  const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  bool illegal = false;
+  if (e < A.n) {
+    uint32_t* hist_row = A.history + static_cast<size_t>(e) * kHistoryWords;
+    if (mode == 0) {
+      if (moves_or_mask == nullptr || moves_or_mask[e] != 0) {
+        const Env s = initial_state();
+        store_env(A.state + e, s);
+        write_outputs_any_node(A, e, s);
+      }
+    } else {
+      const uint32_t mv = moves_or_mask[e];
+      if (mv != 0xFFu) {
+        Env s = load_env(A.state + e);
+        const bool term = is_terminal(s);
+        const bool chance = !term && g_chance(s.g);
+        const uint32_t legal = term ? 0u : chance ? legal_mask_chance(s) : legal_mask_decision(s);
+        if (mv < 18u && ((legal >> mv) & 1u)) {
+          HistoryWriter hw(hist_row);
+          if (chance) apply_chance(s, mv, hw); else apply_player_action(s, mv, hw);
+          hw.flush();
+        } else {
+          s.g |= kBitError;
+          illegal = true;
+        }
+        store_env(A.state + e, s);
+        write_outputs_any_node(A, e, s);
+      }
+    }
+  }
+  st.count(COUP_STAT_ILLEGAL, illegal);
+  st.flush(A.stats);
+}
+
+// Copies env `src` onto env `dst` (State::Clone, coup.cc:1058-1060): state, history and outputs.
+__global__ void k_copy_env(EnvArrays A, uint32_t src, uint32_t dst) {
+  const int t = threadIdx.x;
+  if (t < kHistoryWords) A.history[static_cast<size_t>(dst) * kHistoryWords + t] = A.history[static_cast<size_t>(src) * kHistoryWords + t];
+  if (t == 0) {
+    A.state[dst] = A.state[src];
+    A.legal[dst] = A.legal[src];
+    A.cur_player[dst] = A.cur_player[src];
+    A.done[dst] = A.done[src];
+    A.rewards[2 * dst] = A.rewards[2 * src]; A.rewards[2 * dst + 1] = A.rewards[2 * src + 1];
+    A.returns[2 * dst] = A.returns[2 * src]; A.returns[2 * dst + 1] = A.returns[2 * src + 1];
+    A.step_word[dst] = A.step_word[src];
+  }
+}
+
 // ---- uniform-random legal action (same draw the fused rollout would use at this step counter) ------
 __global__ void __launch_bounds__(kBlockThreads)
 k_sample_uniform(EnvArrays A, uint8_t* __restrict__ actions_out, uint64_t step) {
