@@ -194,6 +194,13 @@ int coup_vec_legal_actions_mask(coup_vec_env* env, uint8_t* d_out, void* stream)
  * overwritten (the reference's ContiguousAllocator zero-fills first, observer.h:175-177). */
 int coup_vec_information_state_tensor(coup_vec_env* env, int player, int dtype, void* d_out, void* stream);
 int coup_vec_observation_tensor(coup_vec_env* env, int player, int dtype, void* d_out, void* stream);
+/* Same tensors with a padded row stride (in elements, a multiple of 4, >= 2492): elements
+ * [2492, row_stride) of every row are written as zeros. row_stride 2496 keeps the consumer's first GEMM on
+ * its aligned (fast) path: K = 2492 is not a multiple of 8 and costs a bf16 cuBLAS GEMM 5.6x on B200. */
+int coup_vec_information_state_tensor_strided(coup_vec_env* env, int player, int dtype, void* d_out,
+                                              uint32_t row_stride, void* stream);
+int coup_vec_rollout_strided(coup_vec_env* env, int n_steps, int encode_player, int dtype, void* d_tensor_out,
+                             uint32_t row_stride, void* stream);
 
 /* ---- host-buffer convenience path (what a host-driven caller such as rl_environment would use):
  * copies uint8[num_envs] actions from (pinned) host memory, steps, optionally encodes the current

@@ -38,7 +38,8 @@ EXPORTED_SYMBOLS = [
     "coup_vec_reset", "coup_vec_step", "coup_vec_new_initial_state", "coup_vec_apply_move", "coup_vec_copy_env", "coup_vec_sample_uniform", "coup_vec_sample_policy", "coup_vec_rollout",
     "coup_vec_legal_mask", "coup_vec_current_player", "coup_vec_done", "coup_vec_rewards",
     "coup_vec_returns", "coup_vec_step_word", "coup_vec_state", "coup_vec_history", "coup_vec_legal_actions_mask",
-    "coup_vec_information_state_tensor", "coup_vec_observation_tensor", "coup_vec_step_host", "coup_vec_step_host_packed",
+    "coup_vec_information_state_tensor", "coup_vec_observation_tensor",
+    "coup_vec_information_state_tensor_strided", "coup_vec_rollout_strided", "coup_vec_step_host", "coup_vec_step_host_packed",
     "coup_host_sample_uniform", "coup_vec_stats", "coup_vec_stats_device", "coup_vec_clear_stats", "coup_vec_check_errors",
     "coup_tensor_row_hash", "coup_vec_step_counter", "coup_vec_set_step_counter",
 ]
@@ -94,6 +95,8 @@ def load():
         getattr(lib, name).restype = vp
     lib.coup_vec_legal_actions_mask.argtypes = [vp, vp, vp]
     lib.coup_vec_information_state_tensor.argtypes = [vp, C.c_int, C.c_int, vp, vp]
+    lib.coup_vec_information_state_tensor_strided.argtypes = [vp, C.c_int, C.c_int, vp, C.c_uint32, vp]
+    lib.coup_vec_rollout_strided.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.c_uint32, vp]
     lib.coup_vec_observation_tensor.argtypes = [vp, C.c_int, C.c_int, vp, vp]
     lib.coup_vec_step_host.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int, vp, vp]
     lib.coup_vec_step_host_packed.argtypes = [vp, vp, vp, C.c_int, vp, vp]

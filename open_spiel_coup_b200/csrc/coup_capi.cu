@@ -68,37 +68,42 @@ int launch_status(const char* what) {
 bool valid_player_sel(int p) { return p >= COUP_PLAYER_0 && p <= COUP_PLAYER_BOTH; }
 bool valid_dtype(int d) { return d == COUP_DTYPE_F32 || d == COUP_DTYPE_U8 || d == COUP_DTYPE_BF16; }
 
-bool use_staged_encoder(const coup_vec_env* env) { return (env->opts.flags & COUP_FLAG_PLAIN_STORE_ENCODER) == 0; }
+// The staged (bulk-store) encoder needs row groups that are multiples of 16 bytes: contiguous rows
+// (stride 2492) or the GEMM-friendly padded stride 2496. Other strides use the plain-store encoder.
+bool use_staged_encoder(const coup_vec_env* env, uint32_t stride) {
+  return (env->opts.flags & COUP_FLAG_PLAIN_STORE_ENCODER) == 0 && (stride == COUP_INFO_STATE_SIZE || stride == 2496u);
+}
+bool valid_stride(uint32_t stride) { return stride >= COUP_INFO_STATE_SIZE && stride % 4u == 0 && stride <= 4096u; }
 
 template <typename T>
-int rollout_typed(coup_vec_env* env, int n_steps, int encode_player, void* d_out, cudaStream_t st) {
+int rollout_typed(coup_vec_env* env, int n_steps, int encode_player, void* d_out, uint32_t stride, cudaStream_t st) {
   const unsigned grid = blocks_for(env->A.n);
-  const bool staged = encode_player >= 0 && use_staged_encoder(env);
+  const bool staged = encode_player >= 0 && use_staged_encoder(env, stride);
   if (staged) {
     cudaError_t err = cudaFuncSetAttribute(k_rollout_tma<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmemBytes);
     if (err != cudaSuccess) return fail(COUP_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(err));
   }
   for (int i = 0; i < n_steps; ++i) {
     if (staged)
-      k_rollout_tma<T><<<grid, kTmaBlockThreads, kTmaSmemBytes, st>>>(env->A, env->step_counter, encode_player, static_cast<T*>(d_out));
+      k_rollout_tma<T><<<grid, kTmaBlockThreads, kTmaSmemBytes, st>>>(env->A, env->step_counter, encode_player, static_cast<T*>(d_out), stride);
     else if (encode_player >= 0)
-      k_rollout<T, true><<<grid, kBlockThreads, 0, st>>>(env->A, env->step_counter, encode_player, static_cast<T*>(d_out));
+      k_rollout<T, true><<<grid, kBlockThreads, 0, st>>>(env->A, env->step_counter, encode_player, static_cast<T*>(d_out), stride);
     else
-      k_rollout<T, false><<<grid, kBlockThreads, 0, st>>>(env->A, env->step_counter, 0, static_cast<T*>(nullptr));
+      k_rollout<T, false><<<grid, kBlockThreads, 0, st>>>(env->A, env->step_counter, 0, static_cast<T*>(nullptr), stride);
     env->step_counter++;
   }
   return launch_status("k_rollout");
 }
 
 template <typename T>
-int encode_info_typed(coup_vec_env* env, int player, void* d_out, cudaStream_t st) {
+int encode_info_typed(coup_vec_env* env, int player, void* d_out, uint32_t stride, cudaStream_t st) {
   const unsigned grid = (env->A.n + 32 * kWarpsPerBlock - 1) / (32 * kWarpsPerBlock);
-  if (use_staged_encoder(env)) {
+  if (use_staged_encoder(env, stride)) {
     cudaError_t err = cudaFuncSetAttribute(k_encode_info_tma<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmemBytes);
     if (err != cudaSuccess) return fail(COUP_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(err));
-    k_encode_info_tma<T><<<grid, kTmaBlockThreads, kTmaSmemBytes, st>>>(env->A.state, env->A.history, env->A.n, player, static_cast<T*>(d_out));
+    k_encode_info_tma<T><<<grid, kTmaBlockThreads, kTmaSmemBytes, st>>>(env->A.state, env->A.history, env->A.n, player, static_cast<T*>(d_out), stride);
   } else {
-    k_encode_info<T><<<grid, kBlockThreads, 0, st>>>(env->A.state, env->A.history, env->A.n, player, static_cast<T*>(d_out));
+    k_encode_info<T><<<grid, kBlockThreads, 0, st>>>(env->A.state, env->A.history, env->A.n, player, static_cast<T*>(d_out), stride);
   }
   return launch_status("k_encode_info");
 }
@@ -239,17 +244,22 @@ int coup_vec_sample_policy(coup_vec_env* env, const void* d_logits, int dtype, f
   return launch_status("k_sample_policy");
 }
 
-int coup_vec_rollout(coup_vec_env* env, int n_steps, int encode_player, int dtype, void* d_tensor_out, void* stream) {
+int coup_vec_rollout_strided(coup_vec_env* env, int n_steps, int encode_player, int dtype, void* d_tensor_out,
+                             uint32_t row_stride, void* stream) {
   if (!env || n_steps < 0) return fail(COUP_ERR_INVALID_ARG, "coup_vec_rollout: bad arguments");
-  if (encode_player >= 0 && (!valid_player_sel(encode_player) || !valid_dtype(dtype) || !d_tensor_out))
+  if (encode_player >= 0 && (!valid_player_sel(encode_player) || !valid_dtype(dtype) || !d_tensor_out || !valid_stride(row_stride)))
     return fail(COUP_ERR_INVALID_ARG, "coup_vec_rollout: bad encode arguments");
   DeviceGuard guard(env->opts.device);
-  if (encode_player < 0) return rollout_typed<float>(env, n_steps, -1, nullptr, S(stream));
+  if (encode_player < 0) return rollout_typed<float>(env, n_steps, -1, nullptr, COUP_INFO_STATE_SIZE, S(stream));
   switch (dtype) {
-    case COUP_DTYPE_F32: return rollout_typed<float>(env, n_steps, encode_player, d_tensor_out, S(stream));
-    case COUP_DTYPE_U8: return rollout_typed<uint8_t>(env, n_steps, encode_player, d_tensor_out, S(stream));
-    default: return rollout_typed<__nv_bfloat16>(env, n_steps, encode_player, d_tensor_out, S(stream));
+    case COUP_DTYPE_F32: return rollout_typed<float>(env, n_steps, encode_player, d_tensor_out, row_stride, S(stream));
+    case COUP_DTYPE_U8: return rollout_typed<uint8_t>(env, n_steps, encode_player, d_tensor_out, row_stride, S(stream));
+    default: return rollout_typed<__nv_bfloat16>(env, n_steps, encode_player, d_tensor_out, row_stride, S(stream));
   }
+}
+
+int coup_vec_rollout(coup_vec_env* env, int n_steps, int encode_player, int dtype, void* d_tensor_out, void* stream) {
+  return coup_vec_rollout_strided(env, n_steps, encode_player, dtype, d_tensor_out, COUP_INFO_STATE_SIZE, stream);
 }
 
 const uint32_t* coup_vec_legal_mask(const coup_vec_env* env) { return env ? env->A.legal : nullptr; }
@@ -269,15 +279,20 @@ int coup_vec_legal_actions_mask(coup_vec_env* env, uint8_t* d_out, void* stream)
   return launch_status("k_legal_actions_mask");
 }
 
-int coup_vec_information_state_tensor(coup_vec_env* env, int player, int dtype, void* d_out, void* stream) {
-  if (!env || !d_out || !valid_player_sel(player) || !valid_dtype(dtype))
+int coup_vec_information_state_tensor_strided(coup_vec_env* env, int player, int dtype, void* d_out,
+                                              uint32_t row_stride, void* stream) {
+  if (!env || !d_out || !valid_player_sel(player) || !valid_dtype(dtype) || !valid_stride(row_stride))
     return fail(COUP_ERR_INVALID_ARG, "coup_vec_information_state_tensor: bad arguments");
   DeviceGuard guard(env->opts.device);
   switch (dtype) {
-    case COUP_DTYPE_F32: return encode_info_typed<float>(env, player, d_out, S(stream));
-    case COUP_DTYPE_U8: return encode_info_typed<uint8_t>(env, player, d_out, S(stream));
-    default: return encode_info_typed<__nv_bfloat16>(env, player, d_out, S(stream));
+    case COUP_DTYPE_F32: return encode_info_typed<float>(env, player, d_out, row_stride, S(stream));
+    case COUP_DTYPE_U8: return encode_info_typed<uint8_t>(env, player, d_out, row_stride, S(stream));
+    default: return encode_info_typed<__nv_bfloat16>(env, player, d_out, row_stride, S(stream));
   }
+}
+
+int coup_vec_information_state_tensor(coup_vec_env* env, int player, int dtype, void* d_out, void* stream) {
+  return coup_vec_information_state_tensor_strided(env, player, dtype, d_out, COUP_INFO_STATE_SIZE, stream);
 }
 
 int coup_vec_observation_tensor(coup_vec_env* env, int player, int dtype, void* d_out, void* stream) {

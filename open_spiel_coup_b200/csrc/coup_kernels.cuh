@@ -145,7 +145,7 @@ __device__ __forceinline__ void write_outputs(const EnvArrays& A, uint32_t e, co
   A.done[e] = r.done ? 1 : 0;
   reinterpret_cast<char2*>(A.rewards)[e] = make_char2(static_cast<signed char>(r.reward0), static_cast<signed char>(-r.reward0));
   reinterpret_cast<char2*>(A.returns)[e] = make_char2(static_cast<signed char>(r.return0), static_cast<signed char>(-r.return0));
-  A.step_word[e] = r.legal | (r.cur_player == 1 ? 1u << 18 : 0u) | (r.cur_player < 0 ? 1u << 19 : 0u) |
+  A.step_word[e] = r.legal | (r.cur_player == 1 ? 1u << 18 : 0u) | (r.cur_player == COUP_TERMINAL_PLAYER_ID ? 1u << 19 : 0u) |
                    (r.done ? 1u << 20 : 0u) | (static_cast<uint32_t>(r.reward0 + 2) << 21) |
                    (static_cast<uint32_t>(r.return0 + 2) << 24);
 }
@@ -417,7 +417,7 @@ __device__ __forceinline__ uint32_t info_value(const uint32_t* rec, uint64_t mas
 // out_row0. Rows are 623 units of four elements; within a row lane l handles units l, l+32, ...
 template <typename T>
 __device__ __forceinline__ void warp_encode_info(const uint32_t* recs, int nrec, bool both,
-                                                 typename Unit4<T>::type* out_units, int lane) {
+                                                 typename Unit4<T>::type* out_units, int lane, int row_units) {
   using U = typename Unit4<T>::type;
   const int nrows = both ? 2 * nrec : nrec;
   for (int r = 0; r < nrows; ++r) {
@@ -429,7 +429,7 @@ __device__ __forceinline__ void warp_encode_info(const uint32_t* recs, int nrec,
     const int len = static_cast<int>(meta & 255u);
     // units [0, nz_end) can hold non-zeros: the 62-float head plus `len` history rows of 18
     const int nz_end = min(kUnitsPerInfoRow, (62 + 18 * len + 3) >> 2);
-    U* row = out_units + static_cast<size_t>(r) * kUnitsPerInfoRow;
+    U* row = out_units + static_cast<size_t>(r) * row_units;  // row_units >= 623: padded row stride
     int q = lane;
     for (; q < nz_end; q += 32) {
       const uint32_t p0 = 4u * q;
@@ -445,14 +445,14 @@ __device__ __forceinline__ void warp_encode_info(const uint32_t* recs, int nrec,
     }
     const U zero = Unit4<T>::make(0, 0, 0, 0);
 #pragma unroll 4
-    for (; q < kUnitsPerInfoRow; q += 32) row[q] = zero;
+    for (; q < row_units; q += 32) row[q] = zero;
   }
 }
 
 template <typename T>
 __global__ void __launch_bounds__(kBlockThreads)
 k_encode_info(const uint4* __restrict__ state, const uint32_t* __restrict__ history, uint32_t n,
-              int player_sel, T* __restrict__ out) {
+              int player_sel, T* __restrict__ out, uint32_t stride) {
   __shared__ uint32_t s_rec[kWarpsPerBlock][32 * kRecWords];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t e0 = (blockIdx.x * kWarpsPerBlock + warp) * 32u;
@@ -466,8 +466,9 @@ k_encode_info(const uint4* __restrict__ state, const uint32_t* __restrict__ hist
   const int nrec = static_cast<int>(min(32u, n - e0));
   const bool both = player_sel == COUP_PLAYER_BOTH;
   using U = typename Unit4<T>::type;
-  U* out_units = reinterpret_cast<U*>(out) + static_cast<size_t>(e0) * (both ? 2 : 1) * kUnitsPerInfoRow;
-  warp_encode_info<T>(s_rec[warp], nrec, both, out_units, lane);
+  const int row_units = static_cast<int>(stride / 4);
+  U* out_units = reinterpret_cast<U*>(out) + static_cast<size_t>(e0) * (both ? 2 : 1) * row_units;
+  warp_encode_info<T>(s_rec[warp], nrec, both, out_units, lane, row_units);
 }
 
 // ---- info-state encoder, staged variant: rows are composed in shared memory and written with bulk
@@ -476,7 +477,7 @@ k_encode_info(const uint4* __restrict__ state, const uint32_t* __restrict__ hist
 // hands the buffer to the TMA engine (cp.async.bulk shared -> global, 1 instruction, SASS UBLKCP), waits
 // for the engine to have READ the buffer, and un-pokes the same positions. 9 968 B = one f32 row = two
 // bf16 rows = four u8 rows, always a multiple of 16 B and 16-B aligned in the output.
-constexpr int kStageBytes = kInfoStateSize * 4;                  // 9968
+constexpr int kStageBytes = 2496 * 4;   // 9984: room for the padded row stride 2496 (2492 -> 9968 used)
 constexpr int kTmaWarpsPerBlock = 8;
 constexpr int kTmaBlockThreads = kTmaWarpsPerBlock * 32;
 constexpr int kTmaSmemPerWarp = kStageBytes + 32 * kRecWords * 4;  // staging buffer + 32 records
@@ -520,26 +521,27 @@ __device__ __forceinline__ void poke_row(T* row, const uint32_t* rec, int view, 
 // Full warp (32 records): nrows = 32 or 64 rows, in groups of G = 4/sizeof(T) rows per bulk store.
 template <typename T>
 __device__ __forceinline__ void warp_encode_info_tma(const uint32_t* recs, bool both, T* stage,
-                                                     unsigned char* out_bytes, int lane) {
+                                                     unsigned char* out_bytes, int lane, int stride) {
   constexpr int G = 4 / static_cast<int>(sizeof(T));
+  const uint32_t group_bytes = static_cast<uint32_t>(G * stride) * sizeof(T);  // 9968 (stride 2492) or 9984 (2496)
   const int ngroups = (both ? 64 : 32) / G;
   for (int g = 0; g < ngroups; ++g) {
 #pragma unroll
     for (int k = 0; k < G; ++k) {
       const int r = g * G + k;
-      poke_row<T>(stage + k * kInfoStateSize, recs + (both ? (r >> 1) : r) * kRecWords, both ? (r & 1) : 0, true, lane);
+      poke_row<T>(stage + k * stride, recs + (both ? (r >> 1) : r) * kRecWords, both ? (r & 1) : 0, true, lane);
     }
     tma_store_fence();   // generic-proxy writes -> visible to the async proxy
     __syncwarp();
     if (lane == 0) {
-      tma_bulk_store(out_bytes + static_cast<size_t>(g) * kStageBytes, stage, kStageBytes);
+      tma_bulk_store(out_bytes + static_cast<size_t>(g) * group_bytes, stage, group_bytes);
       tma_wait_read_all();  // the engine has read the buffer (the global write itself is still in flight)
     }
     __syncwarp();
 #pragma unroll
     for (int k = 0; k < G; ++k) {
       const int r = g * G + k;
-      poke_row<T>(stage + k * kInfoStateSize, recs + (both ? (r >> 1) : r) * kRecWords, both ? (r & 1) : 0, false, lane);
+      poke_row<T>(stage + k * stride, recs + (both ? (r >> 1) : r) * kRecWords, both ? (r & 1) : 0, false, lane);
     }
   }
 }
@@ -563,7 +565,7 @@ __device__ __forceinline__ void zero_stage(unsigned char* stage, int lane) {
 template <typename T>
 __global__ void __launch_bounds__(kTmaBlockThreads, 2)
 k_encode_info_tma(const uint4* __restrict__ state, const uint32_t* __restrict__ history, uint32_t n,
-                  int player_sel, T* __restrict__ out) {
+                  int player_sel, T* __restrict__ out, uint32_t stride) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   TmaSmem sm(smem_raw, warp);
@@ -581,11 +583,12 @@ k_encode_info_tma(const uint4* __restrict__ state, const uint32_t* __restrict__ 
   const size_t row0 = static_cast<size_t>(e0) * (both ? 2 : 1);
   if (full) {
     warp_encode_info_tma<T>(sm.recs, both, reinterpret_cast<T*>(sm.stage),
-                            reinterpret_cast<unsigned char*>(out) + row0 * kInfoStateSize * sizeof(T), lane);
+                            reinterpret_cast<unsigned char*>(out) + row0 * stride * sizeof(T), lane, static_cast<int>(stride));
     if (lane == 0) tma_wait_all();
   } else {  // ragged last warp: plain vector stores
     using U = typename Unit4<T>::type;
-    warp_encode_info<T>(sm.recs, static_cast<int>(n - e0), both, reinterpret_cast<U*>(out) + row0 * kUnitsPerInfoRow, lane);
+    warp_encode_info<T>(sm.recs, static_cast<int>(n - e0), both, reinterpret_cast<U*>(out) + row0 * (stride / 4), lane,
+                        static_cast<int>(stride / 4));
   }
 }
 
@@ -644,7 +647,7 @@ k_encode_obs(const uint4* __restrict__ state, uint32_t n, int player_sel, T* __r
 // ---- fused random rollout step: sample -> step -> chance -> [auto-reset] -> outputs -> encode -------
 template <typename T, bool kEncode>
 __global__ void __launch_bounds__(kBlockThreads)
-k_rollout(EnvArrays A, uint64_t step, int player_sel, T* __restrict__ out) {
+k_rollout(EnvArrays A, uint64_t step, int player_sel, T* __restrict__ out, uint32_t stride) {
   __shared__ uint32_t s_stats[COUP_STATS_LEN];
   __shared__ uint32_t s_rec[kEncode ? kWarpsPerBlock : 1][kEncode ? 32 * kRecWords : 1];
   BlockStats st;
@@ -668,8 +671,9 @@ k_rollout(EnvArrays A, uint64_t step, int player_sel, T* __restrict__ out) {
     const int nrec = static_cast<int>(min(32u, A.n - e0));
     const bool both = player_sel == COUP_PLAYER_BOTH;
     using U = typename Unit4<T>::type;
-    U* out_units = reinterpret_cast<U*>(out) + static_cast<size_t>(e0) * (both ? 2 : 1) * kUnitsPerInfoRow;
-    warp_encode_info<T>(s_rec[warp], nrec, both, out_units, lane);
+    const int row_units = static_cast<int>(stride / 4);
+    U* out_units = reinterpret_cast<U*>(out) + static_cast<size_t>(e0) * (both ? 2 : 1) * row_units;
+    warp_encode_info<T>(s_rec[warp], nrec, both, out_units, lane, row_units);
   }
   st.flush(A.stats);
 }
@@ -677,7 +681,7 @@ k_rollout(EnvArrays A, uint64_t step, int player_sel, T* __restrict__ out) {
 // Same fused step, with the staged (shared memory + bulk store) encoder.
 template <typename T>
 __global__ void __launch_bounds__(kTmaBlockThreads, 2)
-k_rollout_tma(EnvArrays A, uint64_t step, int player_sel, T* __restrict__ out) {
+k_rollout_tma(EnvArrays A, uint64_t step, int player_sel, T* __restrict__ out, uint32_t stride) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   TmaSmem sm(smem_raw, warp);
@@ -704,11 +708,12 @@ k_rollout_tma(EnvArrays A, uint64_t step, int player_sel, T* __restrict__ out) {
     const size_t row0 = static_cast<size_t>(e0) * (both ? 2 : 1);
     if (full) {
       warp_encode_info_tma<T>(sm.recs, both, reinterpret_cast<T*>(sm.stage),
-                              reinterpret_cast<unsigned char*>(out) + row0 * kInfoStateSize * sizeof(T), lane);
+                              reinterpret_cast<unsigned char*>(out) + row0 * stride * sizeof(T), lane, static_cast<int>(stride));
       if (lane == 0) tma_wait_all();
     } else {
       using U = typename Unit4<T>::type;
-      warp_encode_info<T>(sm.recs, static_cast<int>(A.n - e0), both, reinterpret_cast<U*>(out) + row0 * kUnitsPerInfoRow, lane);
+      warp_encode_info<T>(sm.recs, static_cast<int>(A.n - e0), both, reinterpret_cast<U*>(out) + row0 * (stride / 4), lane,
+                          static_cast<int>(stride / 4));
     }
   }
   st.flush(A.stats);

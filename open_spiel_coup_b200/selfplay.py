@@ -13,6 +13,11 @@ import torch
 from torch import nn
 
 from ._lib import INFO_STATE_SIZE, NUM_DISTINCT_ACTIONS, PLAYER_CURRENT
+
+# Row stride of the policy input: 2492 padded to a multiple of 32 elements. K = 2492 is not a multiple of 8, which
+# takes a bf16 cuBLAS GEMM off its fast path (5.2 ms vs 0.93 ms for [2^18, K] x [K, 1024] on B200); the encoder
+# writes zeros into the four pad columns (coup_vec_information_state_tensor_strided).
+PADDED_INFO_STATE_SIZE = 2496
 from .vector_env import CoupVectorEnv
 
 
@@ -21,9 +26,13 @@ class MLPPolicy(nn.Module):
     (`open_spiel/python/pytorch/dqn.py:36-107`) at the thesis sizes 2492 -> 1024 -> 1024 -> 18
     (`coup_experiments/scripts/flags/thesis_runs/nfsp-final1.cfg:2`)."""
 
-    def __init__(self, input_size=INFO_STATE_SIZE, hidden_sizes=(1024, 1024), output_size=NUM_DISTINCT_ACTIONS):
+    def __init__(self, input_size=INFO_STATE_SIZE, hidden_sizes=(1024, 1024), output_size=NUM_DISTINCT_ACTIONS,
+                 padded_input_size=None):
         super().__init__()
-        layers, prev = [], input_size
+        self.input_size = input_size
+        # weights of the pad columns only ever see zeros: they do not change the function or its gradients
+        self.padded_input_size = padded_input_size or input_size
+        layers, prev = [], self.padded_input_size
         for h in hidden_sizes:
             layers += [nn.Linear(prev, h), nn.ReLU()]
             prev = h
@@ -100,8 +109,11 @@ class SelfPlayDataGen:
         self.env = CoupVectorEnv(num_envs, seed=seed, device=device, global_env_offset=global_env_offset,
                                  auto_reset=True)
         dev = self.env.device
-        self.policy = (policy if policy is not None else MLPPolicy()).to(device=dev, dtype=tensor_dtype).eval()
-        self.info_state = torch.empty((num_envs, INFO_STATE_SIZE), dtype=tensor_dtype, device=dev)
+        if policy is None:
+            policy = MLPPolicy(padded_input_size=PADDED_INFO_STATE_SIZE)
+        self.policy = policy.to(device=dev, dtype=tensor_dtype).eval()
+        width = getattr(policy, "padded_input_size", INFO_STATE_SIZE)
+        self.info_state = torch.zeros((num_envs, width), dtype=tensor_dtype, device=dev)
         self.action_probs = torch.empty((num_envs, NUM_DISTINCT_ACTIONS), dtype=torch.float32, device=dev)
         self.actions = torch.empty(num_envs, dtype=torch.uint8, device=dev)
         self.acting_player = torch.empty(num_envs, dtype=torch.int8, device=dev)
@@ -118,7 +130,7 @@ class SelfPlayDataGen:
         self.legal_before.copy_(env.legal_mask)
         env.sample_policy(logits, probs_out=self.action_probs, actions_out=self.actions)
         if self.reservoir is not None:
-            self.reservoir.add(self.info_state, self.action_probs, self.legal_before)
+            self.reservoir.add(self.info_state[:, :INFO_STATE_SIZE], self.action_probs, self.legal_before)
         env.step(self.actions)
         self.steps += 1
         # After the call: env.rewards / env.returns / env.done describe the transition just made

@@ -100,6 +100,13 @@ class CoupVectorEnv:
     def _ptr(t):
         return None if t is None else C.c_void_p(t.data_ptr())
 
+    @staticmethod
+    def _row_stride(out):
+        """Row stride in elements of a [rows, >=2492] output (2496 = padded, GEMM-aligned rows)."""
+        if out.dim() != 2 or out.stride(1) != 1 or out.shape[1] < INFO_STATE_SIZE:
+            raise ValueError("info-state output must be [rows, >=2492] with unit inner stride")
+        return int(out.stride(0))
+
     def _rows(self, player):
         return self.num_envs * (2 if player == PLAYER_BOTH else 1)
 
@@ -140,8 +147,8 @@ class CoupVectorEnv:
             return None
         if out is None:
             out = torch.empty((self._rows(encode_player), INFO_STATE_SIZE), dtype=dtype, device=self.device)
-        check(self._lib.coup_vec_rollout(self._h, n_steps, encode_player, _TORCH_TO_DTYPE[out.dtype],
-                                         self._ptr(out), _stream_ptr(self.device)))
+        check(self._lib.coup_vec_rollout_strided(self._h, n_steps, encode_player, _TORCH_TO_DTYPE[out.dtype],
+                                                 self._ptr(out), self._row_stride(out), _stream_ptr(self.device)))
         return out
 
     def step_host(self, h_actions, h_legal_mask=None, h_current_player=None, h_done=None, h_rewards=None,
@@ -168,8 +175,9 @@ class CoupVectorEnv:
         """CoupState::InformationStateTensor (coup.cc:1044-1049) for every env; [rows, 2492]."""
         if out is None:
             out = torch.empty((self._rows(player), INFO_STATE_SIZE), dtype=dtype, device=self.device)
-        check(self._lib.coup_vec_information_state_tensor(self._h, player, _TORCH_TO_DTYPE[out.dtype],
-                                                          self._ptr(out), _stream_ptr(self.device)))
+        check(self._lib.coup_vec_information_state_tensor_strided(self._h, player, _TORCH_TO_DTYPE[out.dtype],
+                                                                  self._ptr(out), self._row_stride(out),
+                                                                  _stream_ptr(self.device)))
         return out
 
     def observation_tensor(self, player=PLAYER_CURRENT, out=None, dtype=torch.float32):

@@ -370,6 +370,34 @@ def test_dtypes_agree(oracle, plain):
     assert torch.equal(a.float(), env.information_state_tensor(_lib.PLAYER_CURRENT))
 
 
+@pytest.mark.parametrize("plain", [False, True], ids=["staged-tma", "plain-stores"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.uint8])
+@pytest.mark.parametrize("width", [2496, 2560])
+def test_padded_row_stride(plain, dtype, width):
+    """Rows padded to a GEMM-friendly stride: same values, zero pad columns (2496 takes the staged path,
+    2560 the plain-store path)."""
+    n = 1000 + 13
+    env = CoupVectorEnv(n, seed=8, auto_reset=True, plain_store_encoder=plain)
+    env.rollout(19)
+    for sel in (_lib.PLAYER_CURRENT, _lib.PLAYER_BOTH):
+        rows = n * (2 if sel == _lib.PLAYER_BOTH else 1)
+        dense = env.information_state_tensor(sel, dtype=dtype)
+        padded = torch.full((rows, width), 7, dtype=dtype, device=env.device)
+        env.information_state_tensor(sel, out=padded)
+        assert torch.equal(padded[:, :INFO], dense) and (padded[:, INFO:] == 0).all()
+    e2 = CoupVectorEnv(n, seed=8, auto_reset=True, plain_store_encoder=plain)
+    e2.rollout(19)
+    padded = torch.full((n, width), 7, dtype=dtype, device=env.device)
+    e2.rollout(1, _lib.PLAYER_CURRENT, out=padded)
+    env.rollout(1)
+    assert torch.equal(padded[:, :INFO], env.information_state_tensor(_lib.PLAYER_CURRENT, dtype=dtype))
+    assert (padded[:, INFO:] == 0).all()
+    with pytest.raises(ValueError):
+        env.information_state_tensor(_lib.PLAYER_0, out=torch.empty((n, 2400), dtype=dtype, device=env.device))
+    with pytest.raises(_lib.CoupError):
+        env.information_state_tensor(_lib.PLAYER_0, out=torch.empty((n, 2494), dtype=dtype, device=env.device))
+
+
 def test_legal_actions_mask_dense():
     env = CoupVectorEnv(3000, seed=2, auto_reset=True)
     env.rollout(17)

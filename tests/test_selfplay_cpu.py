@@ -27,6 +27,8 @@ def test_mlp_policy_shape_follows_thesis_flagfile():
     sizes = [(m.in_features, m.out_features) for m in net.net if isinstance(m, torch.nn.Linear)]
     assert sizes == [(2492, 1024), (1024, 1024), (1024, 18)]
     assert net(torch.zeros(3, 2492)).shape == (3, 18)
+    padded = MLPPolicy(padded_input_size=2496)          # GEMM-aligned input rows; pad columns are always zero
+    assert padded.net[0].in_features == 2496 and padded(torch.zeros(3, 2496)).shape == (3, 18)
 
 
 def test_reservoir_fills_then_samples_uniformly():
