@@ -314,14 +314,14 @@ def main():
         torch.cuda.empty_cache()
         torch.manual_seed(args.seed)
         n_sp = 1 << 18
-        gen = SelfPlayDataGen(num_envs=n_sp, policy=MLPPolicy(), seed=args.seed, device=local,
+        gen = SelfPlayDataGen(num_envs=n_sp, policy=None, seed=args.seed, device=local,
                               global_env_offset=rank * n_sp, reservoir_capacity=0)
         gen.env.rollout(100)
         gen.run(5)
         k_sp = max(10, min(K, 60))
         ms_sp = timed(lambda k: gen.run(k), k_sp)
         selfplay = {"steps_per_s": k_sp * n_sp * world / (ms_sp * 1e-3), "envs_per_gpu": n_sp, "ms_per_step": ms_sp / k_sp,
-                    "policy": "MLP 2492-1024-1024-18 (bf16, torch), masked softmax sampling fused on device (k_sample_policy)",
+                    "policy": "MLP 2492(+4 zero pad)-1024-1024-18 (bf16, torch), masked softmax sampling fused on device (k_sample_policy)",
                     "note": "per step: encode bf16 info-state of the player to move, policy forward, masked sampling, env step"}
         del gen
         torch.cuda.empty_cache()
