@@ -32,6 +32,14 @@ struct Env {
   uint32_t c;     // counters + reward
 };
 
+// Player words are always picked with selects, never with a run-time array index, so that the state stays
+// in registers (a dynamically indexed p[] would be demoted to local memory).
+__device__ __forceinline__ uint32_t get_p(const Env& s, uint32_t i) { return i ? s.p[1] : s.p[0]; }
+__device__ __forceinline__ void set_p(Env& s, uint32_t i, uint32_t v) {
+  s.p[0] = i ? s.p[0] : v;
+  s.p[1] = i ? v : s.p[1];
+}
+
 // player word
 __device__ __forceinline__ uint32_t pw_hand(uint32_t w) { return w & 0xFFFFu; }
 __device__ __forceinline__ uint32_t pw_coins(uint32_t w) { return (w >> 16) & 31u; }
@@ -117,7 +125,7 @@ __device__ __forceinline__ uint32_t lose_card_mask(uint32_t hand) {
 // neither terminal nor a chance node.
 __device__ __forceinline__ uint32_t legal_mask_decision(const Env& s) {
   const uint32_t m = g_mover(s.g);
-  const uint32_t cp = s.p[m], op = s.p[m ^ 1u];
+  const uint32_t cp = get_p(s, m), op = get_p(s, m ^ 1u);
   if (g_turn_begin(s.g)) {                                              // 841-854
     const uint32_t coins = pw_coins(cp);
     if (coins >= 10) return 1u << kCoup;
@@ -202,29 +210,29 @@ __device__ __forceinline__ void queue_deals(Env& s, uint32_t player, uint32_t n)
   s.g = (s.g & ~((7u << 24) | kBitQInitial | kBitQPlayer)) | (qn << 24) | (player << 28) | kBitChance;
 }
 
-// ChallengeFailReplaceCard, 468-486, for player `who` (the reference's opp_player_).
-__device__ __forceinline__ void replace_card(Env& s, uint32_t who, uint32_t card) {
-  uint32_t h = pw_hand(s.p[who]);
+// ChallengeFailReplaceCard, 468-486, for player `who` (the reference's opp_player_) whose word is `w`.
+__device__ __forceinline__ void replace_card(Env& s, uint32_t& w, uint32_t who, uint32_t card) {
+  uint32_t h = pw_hand(w);
   uint32_t slot = hand_find(h, card << 1);
   s.g += 1u << (4 * card);  // deck_[card] += 1
-  s.p[who] = pw_set_hand(s.p[who], hand_remove(h, slot));
+  w = pw_set_hand(w, hand_remove(h, slot));
   queue_deals(s, who, 1);
 }
 
-// Turn every face-down card among slots 0 and 1 of `who` face up (660-669 / 733-742); returns the
+// Turn every face-down card among slots 0 and 1 of a player face up (660-669 / 733-742); returns the
 // number flipped. No re-sort: the reference does not sort here, and the order cannot change.
-__device__ __forceinline__ int flip_two(Env& s, uint32_t who) {
-  uint32_t h = pw_hand(s.p[who]);
+__device__ __forceinline__ int flip_two(uint32_t& w) {
+  uint32_t h = pw_hand(w);
   uint32_t down = ~h & 0x11u;
-  s.p[who] = pw_set_hand(s.p[who], h | down);
+  w = pw_set_hand(w, h | down);
   return __popc(down);
 }
 
-// (cp steals from op) 599-601 / 685-687 / 758-760
-__device__ __forceinline__ void steal(Env& s, uint32_t to, uint32_t from) {
-  int k = pw_coins(s.p[from]) > 1 ? 2 : 1;
-  s.p[to] = pw_add_coins(s.p[to], k);
-  s.p[from] = pw_add_coins(s.p[from], -k);
+// (`to` steals from `from`) 599-601 / 685-687 / 758-760
+__device__ __forceinline__ void steal(uint32_t& to, uint32_t& from) {
+  int k = pw_coins(from) > 1 ? 2 : 1;
+  to = pw_add_coins(to, k);
+  from = pw_add_coins(from, -k);
 }
 
 // One PLAYER move: State::ApplyAction (spiel.cc:322-332) + the non-chance branch of
@@ -234,13 +242,14 @@ __device__ __forceinline__ void apply_player_action(Env& s, uint32_t a, HistoryW
   const uint32_t m = g_mover(s.g), o = m ^ 1u;
   hist.append(c_moves(s.c), a);
   int rew_m = 0;  // reward of the mover; the other player's is the negation
-  const uint32_t prev_last = pw_last(s.p[m]);
+  uint32_t cp = get_p(s, m), op = get_p(s, o);  // mover / other player words, written back at the end
+  const uint32_t prev_last = pw_last(cp);
   // Every branch of the reference sets cp.last_action = action before anything else, except the
   // "complete the action" else-branches that only run through the recursion.
-  s.p[m] = pw_set_last(s.p[m], a);
+  cp = pw_set_last(cp, a);
   switch (a) {
     case kIncome:                                                      // 531-534
-      s.p[m] = pw_add_coins(s.p[m], 1);
+      cp = pw_add_coins(cp, 1);
       next_turn(s);
       break;
     case kForeignAid: case kTax: case kExchange: case kSteal:          // declared: 536-541 etc.
@@ -248,25 +257,25 @@ __device__ __forceinline__ void apply_player_action(Env& s, uint32_t a, HistoryW
       next_move(s);
       break;
     case kCoup:                                                        // 548-553
-      s.p[m] = pw_add_coins(s.p[m], -7);
+      cp = pw_add_coins(cp, -7);
       next_move(s);
       break;
     case kAssassinate:                                                 // 567-573
-      s.p[m] = pw_add_coins(s.p[m], -3);
+      cp = pw_add_coins(cp, -3);
       next_move(s);
       break;
     case kLoseCard1: case kLoseCard2: {                                // 605-616
       const uint32_t k = a - kLoseCard1;
-      uint32_t h = pw_hand(s.p[m]);
+      uint32_t h = pw_hand(cp);
       const uint32_t key = hand_slot(h, k);
       h = hand_insert(hand_remove(h, k), key | 1u);  // FaceUp, then SortCards
-      s.p[m] = pw_set_lost(pw_set_hand(s.p[m], h), 0);
+      cp = pw_set_lost(pw_set_hand(cp, h), 0);
       rew_m = -1;
       next_turn(s);
       break;
     }
     case kPass: {                                                      // 618-629
-      const uint32_t n = pw_last(s.p[o]);
+      const uint32_t n = pw_last(op);
       if (n == kBlock) {
         next_turn(s);
       } else if (n == kExchange) {
@@ -275,79 +284,79 @@ __device__ __forceinline__ void apply_player_action(Env& s, uint32_t a, HistoryW
         queue_deals(s, o, 2);
       } else {
         // NextPlayerMove then the completing else-branch, which ends in NextPlayerTurn.
-        if (n == kForeignAid) s.p[o] = pw_add_coins(s.p[o], 2);        // 544
-        else if (n == kTax) s.p[o] = pw_add_coins(s.p[o], 3);          // 563
-        else steal(s, o, m);                                           // 599-601 (n == kSteal)
+        if (n == kForeignAid) op = pw_add_coins(op, 2);        // 544
+        else if (n == kTax) op = pw_add_coins(op, 3);          // 563
+        else steal(op, cp);                                           // 599-601 (n == kSteal)
         next_turn(s);
       }
       break;
     }
     case kChallenge: {                                                 // 635-771
-      const uint32_t ol = pw_last(s.p[o]);
-      const uint32_t oh = pw_hand(s.p[o]);
+      const uint32_t ol = pw_last(op);
+      const uint32_t oh = pw_hand(op);
       if (ol == kBlock) {
         if (prev_last == kForeignAid) {                                // 637-649
           if (hand_find(oh, kDuke << 1) < 4) {
-            s.p[m] = pw_set_lost(s.p[m], 1);
-            replace_card(s, o, kDuke);
+            cp = pw_set_lost(cp, 1);
+            replace_card(s, op, o, kDuke);
           } else {
-            s.p[o] = pw_set_lost(s.p[o], 1);
-            s.p[m] = pw_add_coins(s.p[m], 2);
+            op = pw_set_lost(op, 1);
+            cp = pw_add_coins(cp, 2);
             next_move(s);
           }
         } else if (prev_last == kAssassinate) {                        // 650-670
           if (hand_find(oh, kContessa << 1) < 4) {
-            s.p[m] = pw_set_lost(s.p[m], 1);
-            replace_card(s, o, kContessa);
+            cp = pw_set_lost(cp, 1);
+            replace_card(s, op, o, kContessa);
           } else {
-            rew_m = flip_two(s, o);
+            rew_m = flip_two(op);
           }
         } else {                                                       // 671-690 (prev == kSteal)
           if (hand_find(oh, kCaptain << 1) < 4) {
-            s.p[m] = pw_set_lost(s.p[m], 1);
-            replace_card(s, o, kCaptain);
+            cp = pw_set_lost(cp, 1);
+            replace_card(s, op, o, kCaptain);
           } else if (hand_find(oh, kAmbassador << 1) < 4) {
-            s.p[m] = pw_set_lost(s.p[m], 1);
-            replace_card(s, o, kAmbassador);
+            cp = pw_set_lost(cp, 1);
+            replace_card(s, op, o, kAmbassador);
           } else {
-            s.p[o] = pw_set_lost(s.p[o], 1);
-            steal(s, m, o);
+            op = pw_set_lost(op, 1);
+            steal(cp, op);
             next_move(s);
           }
         }
       } else if (ol == kTax) {                                         // 694-706
         if (hand_find(oh, kDuke << 1) < 4) {
-          s.p[m] = pw_set_lost(s.p[m], 1);
-          replace_card(s, o, kDuke);
-          s.p[o] = pw_add_coins(s.p[o], 3);
+          cp = pw_set_lost(cp, 1);
+          replace_card(s, op, o, kDuke);
+          op = pw_add_coins(op, 3);
         } else {
-          s.p[o] = pw_set_lost(s.p[o], 1);
+          op = pw_set_lost(op, 1);
           next_move(s);
         }
       } else if (ol == kExchange) {                                    // 708-725
         if (hand_find(oh, kAmbassador << 1) < 4) {
-          s.p[m] = pw_set_lost(s.p[m], 1);
-          replace_card(s, o, kAmbassador);
+          cp = pw_set_lost(cp, 1);
+          replace_card(s, op, o, kAmbassador);
           next_move(s);
           queue_deals(s, o, 2);  // the recursive Exchange (718): queue is now [o, o, o]
         } else {
-          s.p[o] = pw_set_lost(s.p[o], 1);
+          op = pw_set_lost(op, 1);
           next_move(s);
         }
       } else if (ol == kAssassinate) {                                 // 727-749
         if (hand_find(oh, kAssassin << 1) < 4) {
-          rew_m = -flip_two(s, m);
+          rew_m = -flip_two(cp);
         } else {
-          s.p[o] = pw_add_coins(pw_set_lost(s.p[o], 1), 3);
+          op = pw_add_coins(pw_set_lost(op, 1), 3);
           next_move(s);
         }
       } else {                                                         // 751-767 (ol == kSteal)
         if (hand_find(oh, kCaptain << 1) < 4) {
-          s.p[m] = pw_set_lost(s.p[m], 1);
-          replace_card(s, o, kCaptain);
-          steal(s, o, m);
+          cp = pw_set_lost(cp, 1);
+          replace_card(s, op, o, kCaptain);
+          steal(op, cp);
         } else {
-          s.p[o] = pw_set_lost(s.p[o], 1);
+          op = pw_set_lost(op, 1);
           next_move(s);
         }
       }
@@ -358,16 +367,18 @@ __device__ __forceinline__ void apply_player_action(Env& s, uint32_t a, HistoryW
       const uint32_t k = a - kExchangeReturn12;
       const uint32_t i = (0x940u >> (2 * k)) & 3u;    // 0,0,0,1,1,2
       const uint32_t j = (0xFB9u >> (2 * k)) & 3u;    // 1,2,3,2,3,3
-      uint32_t h = pw_hand(s.p[m]);
+      uint32_t h = pw_hand(cp);
       h = hand_remove(hand_remove(h, j), i);
-      s.p[m] = pw_set_hand(s.p[m], h);
+      cp = pw_set_hand(cp, h);
       // REFERENCE QUIRK (789-795): the deck count that grows is indexed by the hand SLOT, not by the
       // value of the card that was returned. Reproduced for bit-exact replay.
       s.g += (1u << (4 * j)) + (1u << (4 * i));
-      if (pw_lost(s.p[o])) next_move(s); else next_turn(s);
+      if (pw_lost(op)) next_move(s); else next_turn(s);
       break;
     }
   }
+  set_p(s, m, cp);
+  set_p(s, o, op);
   // cur_rewards_ (527, 614-615, 662-668, 735-741): zero-sum, stored from player 0's point of view.
   s.c = c_set_reward0(s.c, m == 0 ? rew_m : -rew_m) + 1u;  // ++move_number_
 }
@@ -378,7 +389,8 @@ __device__ __forceinline__ void apply_chance(Env& s, uint32_t card, HistoryWrite
   const uint32_t target = (s.g & kBitQInitial) ? (qn & 1u) : ((s.g >> 28) & 1u);  // queue 0,1,0,1
   hist.append(c_moves(s.c), 18u + 5u * target + card);
   s.g -= 1u << (4 * card);                                             // deck_[card] -= 1
-  s.p[target] = pw_set_hand(s.p[target], hand_insert(pw_hand(s.p[target]), card << 1));
+  const uint32_t tw = get_p(s, target);
+  set_p(s, target, pw_set_hand(tw, hand_insert(pw_hand(tw), card << 1)));
   s.g -= 1u << 24;                                                     // pop
   if (qn == 1) s.g &= ~(kBitChance | kBitQInitial);                    // 520
   s.c += 1u;                                                           // ++move_number_

@@ -103,7 +103,11 @@ __device__ __forceinline__ StepResult step_env(Env& s, uint32_t* hist_row, uint3
   r.stepped = false; r.illegal = false; r.n_legal_before = 0; r.chance_moves = 0;
   r.finished = false; r.truncated = false; r.final_moves = 0;
   const uint64_t genv = A.global_env_offset + e;
+  const bool auto_reset = (A.flags & COUP_FLAG_AUTO_RESET) != 0;
   bool term = is_terminal(s);
+  r.done = term;
+  r.reward0 = c_reward0(s.c);
+  r.return0 = returns_p0(s);
   if (!term) {
     const uint32_t legal = legal_mask_decision(s);
     const uint4 rnd = env_random(A.seed, genv, step, 0);
@@ -112,27 +116,60 @@ __device__ __forceinline__ StepResult step_env(Env& s, uint32_t* hist_row, uint3
     if (a < 18u && ((legal >> a) & 1u)) {
       HistoryWriter hw(hist_row);
       apply_player_action(s, a, hw);
-      r.chance_moves = resolve_chance(s, rnd, 1, forced, hw);
-      hw.flush();
       r.stepped = true;
+      // Chance words of this step: y/z/w of the step block, or -- when the action ended the episode and the env
+      // re-deals in place -- the four words of the reset block. One shared deal loop serves both.
+      uint4 cw = make_uint4(rnd.y, rnd.z, rnd.w, 0u);
       term = is_terminal(s);
       if (term) {
         r.finished = true;
         r.final_moves = c_moves(s.c);
         r.truncated = r.final_moves > kMaxGameLength;
+        r.done = true;
+        r.reward0 = c_reward0(s.c);
+        r.return0 = returns_p0(s);
+        if (auto_reset) {
+          hw.flush();
+          hw = HistoryWriter(hist_row);
+          s = initial_state();
+          cw = env_random(A.seed, genv, step, 1);
+          forced = nullptr;
+          term = false;
+        }
+      }
+      // Deals never change who is alive, so inside the loop only the move cap (coup.cc:990) can end the game.
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (!g_chance(s.g) || c_moves(s.c) > kMaxGameLength) break;
+        uint32_t card = sample_card(s, k == 0 ? cw.x : k == 1 ? cw.y : k == 2 ? cw.z : cw.w);
+        if (forced != nullptr) {
+          const uint32_t f = forced[k];
+          if (f < 5u && g_deck(s.g, f) != 0) card = f;
+        }
+        apply_chance(s, card, hw);
+        r.chance_moves++;
+      }
+      hw.flush();
+      if (!r.finished) {
+        term = is_terminal(s);
+        r.done = term;
+        r.reward0 = c_reward0(s.c);
+        r.return0 = returns_p0(s);
+        if (term) {  // only reachable through the move cap in the middle of a deal sequence: rare slow path
+          r.finished = true;
+          r.final_moves = c_moves(s.c);
+          r.truncated = true;
+          if (auto_reset) {
+            const uint4 rr = env_random(A.seed, genv, step, 1);
+            r.chance_moves += deal_new_episode(s, hist_row, rr, nullptr);
+            term = false;
+          }
+        }
       }
     } else {
       s.g |= kBitError;  // sticky; the reference would SpielFatalError / raise (rl_environment.py:270-280)
       r.illegal = true;
     }
-  }
-  r.done = term;
-  r.reward0 = c_reward0(s.c);
-  r.return0 = returns_p0(s);
-  if (r.finished && (A.flags & COUP_FLAG_AUTO_RESET)) {
-    const uint4 rr = env_random(A.seed, genv, step, 1);
-    r.chance_moves += deal_new_episode(s, hist_row, rr, nullptr);
-    term = false;
   }
   r.legal = term ? 0u : legal_mask_decision(s);
   r.cur_player = term ? COUP_TERMINAL_PLAYER_ID : static_cast<int>(g_mover(s.g));
@@ -150,15 +187,36 @@ __device__ __forceinline__ void write_outputs(const EnvArrays& A, uint32_t e, co
                    (static_cast<uint32_t>(r.return0 + 2) << 24);
 }
 
+// All counters of one warp-step in four warp reductions: small fields are packed side by side (a count
+// over 32 lanes fits 6 bits), summed with REDUX, and lanes 0..18 each add one counter to shared memory.
 __device__ __forceinline__ void account(BlockStats& st, const StepResult& r, bool active) {
-  st.count(COUP_STAT_DECISION_STEPS, active && r.stepped);
-  st.sum(COUP_STAT_CHANCE_MOVES, active ? r.chance_moves : 0u);
-  st.count(COUP_STAT_EPISODES, active && r.finished);
-  st.count(COUP_STAT_TRUNCATED, active && r.truncated);
-  st.sum(COUP_STAT_EPISODE_MOVES, active ? r.final_moves : 0u);
-  st.count(COUP_STAT_ILLEGAL, active && r.illegal);
-  st.hist(COUP_STAT_RETURN_HIST, 5, static_cast<uint32_t>(r.return0 + 2), active && r.finished);
-  st.hist(COUP_STAT_LEGAL_HIST, 8, min(r.n_legal_before, 7u), active && r.stepped);
+  const uint32_t nl = min(r.n_legal_before, 7u);
+  const bool stepped = active && r.stepped, finished = active && r.finished;
+  // A: stepped | finished<<6 | truncated<<12 | illegal<<18 | chance moves<<24 (<= 7 per lane)
+  uint32_t a = !active ? 0u : (r.stepped ? 1u : 0u) | (r.finished ? 1u << 6 : 0u) | (r.truncated ? 1u << 12 : 0u) |
+                                  (r.illegal ? 1u << 18 : 0u) | (r.chance_moves << 24);
+  // B: Returns()[0] histogram of finished episodes, 5 bins x 6 bits
+  uint32_t b = finished ? 1u << (6 * (r.return0 + 2)) : 0u;
+  // C: sum of final move numbers (12 bits, <= 32 x 91) | legal-count bins 0..2 ; D: legal-count bins 3..7
+  uint32_t c = (finished ? r.final_moves : 0u) | ((stepped && nl < 3u) ? 1u << (12u + 6u * nl) : 0u);
+  uint32_t d = (stepped && nl >= 3u) ? 1u << (6u * (nl - 3u)) : 0u;
+  a = __reduce_add_sync(0xffffffffu, a);
+  b = __reduce_add_sync(0xffffffffu, b);
+  c = __reduce_add_sync(0xffffffffu, c);
+  d = __reduce_add_sync(0xffffffffu, d);
+  const int lane = threadIdx.x & 31;
+  uint32_t val = 0;
+  int idx = 0;
+  if (lane == 0) { val = a & 63u; idx = COUP_STAT_DECISION_STEPS; }
+  else if (lane == 1) { val = (a >> 6) & 63u; idx = COUP_STAT_EPISODES; }
+  else if (lane == 2) { val = (a >> 12) & 63u; idx = COUP_STAT_TRUNCATED; }
+  else if (lane == 3) { val = (a >> 18) & 63u; idx = COUP_STAT_ILLEGAL; }
+  else if (lane == 4) { val = a >> 24; idx = COUP_STAT_CHANCE_MOVES; }
+  else if (lane == 5) { val = c & 4095u; idx = COUP_STAT_EPISODE_MOVES; }
+  else if (lane < 11) { val = (b >> (6 * (lane - 6))) & 63u; idx = COUP_STAT_RETURN_HIST + lane - 6; }
+  else if (lane < 14) { val = (c >> (12 + 6 * (lane - 11))) & 63u; idx = COUP_STAT_LEGAL_HIST + lane - 11; }
+  else if (lane < 19) { val = (d >> (6 * (lane - 14))) & 63u; idx = COUP_STAT_LEGAL_HIST + 3 + lane - 14; }
+  if (val) atomicAdd(&st.sm[idx], val);
 }
 
 // ---- reset -------------------------------------------------------------------------------------
