@@ -39,6 +39,12 @@ BYTES_PER_STEP = {"d32": 42 + 9968 + 11, "bf16": 42 + 4984 + 11, "d8": 42 + 2492
 CONTRACT_DTYPE = {"d32": "f32", "bf16": "bf16", "d8": "u8", "env": "u32"}
 
 
+def workload_text(contract):
+    return ("2-player Coup uniform-random rollouts, 2^20 envs per GPU, legal mask + dense info-state tensor "
+            "(2492 x %s, player to move) per decision step, auto-reset, Philox4x32-10 chance (BASELINE.json configs[1])"
+            % CONTRACT_DTYPE[contract])
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -166,8 +172,11 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": min(args.warmup, 3), "ms_per_step": 1e3 * secs / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "2-player Coup uniform-random rollouts on host cores, info-state tensor of the player to move per decision step",
-                   "threads": threads},
+        "config": {"workload": workload_text("d32"), "envs_per_gpu": args.envs, "contract": "d32",
+                   "bytes_per_step": BYTES_PER_STEP["d32"],
+                   "reference_arm": "the reference's CoupState on %d host threads: uniform-random legal actions, SampleAction on "
+                                    "ChanceOutcomes, LegalActions + InformationStateTensor(current player) at every decision node "
+                                    "(examples/benchmark_game.cc protocol); each step = a bounded sample of %d episodes" % (threads, eps_per_step)},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -344,8 +353,7 @@ def main():
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": CONTRACT_DTYPE[contract], "data": "synthetic",
             "config": {
-                "workload": "2-player Coup uniform-random rollouts, 2^20 envs per GPU, legal mask + dense info-state tensor "
-                            "(2492 x %s, player to move) per decision step, auto-reset, Philox4x32-10 chance (BASELINE.json configs[1])" % CONTRACT_DTYPE[contract],
+                "workload": workload_text(contract),
                 "envs_per_gpu": n, "contract": contract, "bytes_per_step": BYTES_PER_STEP[contract], "encoder": args.encoder,
                 "parallelism": f"env-slab x{world} (no data-path collective; NCCL all-reduce of the stats vector only)",
                 "l2": "per-step working set (%.2f GB written + 80 MB state/history) >> 126 MB L2, no flush needed" % (bytes_per_launch / 1e9)

@@ -201,6 +201,11 @@ int coup_vec_information_state_tensor_strided(coup_vec_env* env, int player, int
                                               uint32_t row_stride, void* stream);
 int coup_vec_rollout_strided(coup_vec_env* env, int n_steps, int encode_player, int dtype, void* d_tensor_out,
                              uint32_t row_stride, void* stream);
+/* Info-state tensors of a SUBSET of envs: output row i (rows 2i, 2i+1 for COUP_PLAYER_BOTH) describes env
+ * d_env_ids[i] (uint32[count] on the device). Used to fetch, e.g., both players' terminal observations of the
+ * envs that just finished (what every agent is stepped with at episode end, coup_experiments/scripts/nfsp.py:141-143). */
+int coup_vec_information_state_tensor_gather(coup_vec_env* env, const uint32_t* d_env_ids, uint32_t count, int player,
+                                             int dtype, void* d_out, uint32_t row_stride, void* stream);
 
 /* ---- host-buffer convenience path (what a host-driven caller such as rl_environment would use):
  * copies uint8[num_envs] actions from (pinned) host memory, steps, optionally encodes the current

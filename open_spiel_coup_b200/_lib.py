@@ -39,7 +39,7 @@ EXPORTED_SYMBOLS = [
     "coup_vec_legal_mask", "coup_vec_current_player", "coup_vec_done", "coup_vec_rewards",
     "coup_vec_returns", "coup_vec_step_word", "coup_vec_state", "coup_vec_history", "coup_vec_legal_actions_mask",
     "coup_vec_information_state_tensor", "coup_vec_observation_tensor",
-    "coup_vec_information_state_tensor_strided", "coup_vec_rollout_strided", "coup_vec_step_host", "coup_vec_step_host_packed",
+    "coup_vec_information_state_tensor_strided", "coup_vec_rollout_strided", "coup_vec_information_state_tensor_gather", "coup_vec_step_host", "coup_vec_step_host_packed",
     "coup_host_sample_uniform", "coup_vec_stats", "coup_vec_stats_device", "coup_vec_clear_stats", "coup_vec_check_errors",
     "coup_tensor_row_hash", "coup_vec_step_counter", "coup_vec_set_step_counter",
 ]
@@ -96,6 +96,7 @@ def load():
     lib.coup_vec_legal_actions_mask.argtypes = [vp, vp, vp]
     lib.coup_vec_information_state_tensor.argtypes = [vp, C.c_int, C.c_int, vp, vp]
     lib.coup_vec_information_state_tensor_strided.argtypes = [vp, C.c_int, C.c_int, vp, C.c_uint32, vp]
+    lib.coup_vec_information_state_tensor_gather.argtypes = [vp, vp, C.c_uint32, C.c_int, C.c_int, vp, C.c_uint32, vp]
     lib.coup_vec_rollout_strided.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.c_uint32, vp]
     lib.coup_vec_observation_tensor.argtypes = [vp, C.c_int, C.c_int, vp, vp]
     lib.coup_vec_step_host.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int, vp, vp]

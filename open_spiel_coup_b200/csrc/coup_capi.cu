@@ -96,14 +96,17 @@ int rollout_typed(coup_vec_env* env, int n_steps, int encode_player, void* d_out
 }
 
 template <typename T>
-int encode_info_typed(coup_vec_env* env, int player, void* d_out, uint32_t stride, cudaStream_t st) {
-  const unsigned grid = (env->A.n + 32 * kWarpsPerBlock - 1) / (32 * kWarpsPerBlock);
+int encode_info_typed(coup_vec_env* env, int player, void* d_out, uint32_t stride, const uint32_t* d_ids, uint32_t count,
+                      cudaStream_t st) {
+  const uint32_t n = d_ids ? count : env->A.n;  // rows to produce (before the x2 of COUP_PLAYER_BOTH)
+  if (n == 0) return COUP_OK;
+  const unsigned grid = (n + 32 * kWarpsPerBlock - 1) / (32 * kWarpsPerBlock);
   if (use_staged_encoder(env, stride)) {
     cudaError_t err = cudaFuncSetAttribute(k_encode_info_tma<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmemBytes);
     if (err != cudaSuccess) return fail(COUP_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(err));
-    k_encode_info_tma<T><<<grid, kTmaBlockThreads, kTmaSmemBytes, st>>>(env->A.state, env->A.history, env->A.n, player, static_cast<T*>(d_out), stride);
+    k_encode_info_tma<T><<<grid, kTmaBlockThreads, kTmaSmemBytes, st>>>(env->A.state, env->A.history, n, player, static_cast<T*>(d_out), stride, d_ids);
   } else {
-    k_encode_info<T><<<grid, kBlockThreads, 0, st>>>(env->A.state, env->A.history, env->A.n, player, static_cast<T*>(d_out), stride);
+    k_encode_info<T><<<grid, kBlockThreads, 0, st>>>(env->A.state, env->A.history, n, player, static_cast<T*>(d_out), stride, d_ids);
   }
   return launch_status("k_encode_info");
 }
@@ -279,15 +282,31 @@ int coup_vec_legal_actions_mask(coup_vec_env* env, uint8_t* d_out, void* stream)
   return launch_status("k_legal_actions_mask");
 }
 
+int coup_vec_information_state_tensor_gather(coup_vec_env* env, const uint32_t* d_env_ids, uint32_t count, int player,
+                                             int dtype, void* d_out, uint32_t row_stride, void* stream) {
+  if (!env || !d_out || !valid_player_sel(player) || !valid_dtype(dtype) || !valid_stride(row_stride) ||
+      (count > 0 && !d_env_ids))
+    return fail(COUP_ERR_INVALID_ARG, "coup_vec_information_state_tensor_gather: bad arguments");
+  DeviceGuard guard(env->opts.device);
+  // a NULL id list with count == 0 is an empty gather, not "all envs"
+  static const uint32_t kNoIds = 0;
+  const uint32_t* ids = d_env_ids ? d_env_ids : &kNoIds;
+  switch (dtype) {
+    case COUP_DTYPE_F32: return encode_info_typed<float>(env, player, d_out, row_stride, ids, count, S(stream));
+    case COUP_DTYPE_U8: return encode_info_typed<uint8_t>(env, player, d_out, row_stride, ids, count, S(stream));
+    default: return encode_info_typed<__nv_bfloat16>(env, player, d_out, row_stride, ids, count, S(stream));
+  }
+}
+
 int coup_vec_information_state_tensor_strided(coup_vec_env* env, int player, int dtype, void* d_out,
                                               uint32_t row_stride, void* stream) {
   if (!env || !d_out || !valid_player_sel(player) || !valid_dtype(dtype) || !valid_stride(row_stride))
     return fail(COUP_ERR_INVALID_ARG, "coup_vec_information_state_tensor: bad arguments");
   DeviceGuard guard(env->opts.device);
   switch (dtype) {
-    case COUP_DTYPE_F32: return encode_info_typed<float>(env, player, d_out, row_stride, S(stream));
-    case COUP_DTYPE_U8: return encode_info_typed<uint8_t>(env, player, d_out, row_stride, S(stream));
-    default: return encode_info_typed<__nv_bfloat16>(env, player, d_out, row_stride, S(stream));
+    case COUP_DTYPE_F32: return encode_info_typed<float>(env, player, d_out, row_stride, nullptr, 0, S(stream));
+    case COUP_DTYPE_U8: return encode_info_typed<uint8_t>(env, player, d_out, row_stride, nullptr, 0, S(stream));
+    default: return encode_info_typed<__nv_bfloat16>(env, player, d_out, row_stride, nullptr, 0, S(stream));
   }
 }
 

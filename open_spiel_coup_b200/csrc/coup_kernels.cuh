@@ -510,15 +510,16 @@ __device__ __forceinline__ void warp_encode_info(const uint32_t* recs, int nrec,
 template <typename T>
 __global__ void __launch_bounds__(kBlockThreads)
 k_encode_info(const uint4* __restrict__ state, const uint32_t* __restrict__ history, uint32_t n,
-              int player_sel, T* __restrict__ out, uint32_t stride) {
+              int player_sel, T* __restrict__ out, uint32_t stride, const uint32_t* __restrict__ ids) {
   __shared__ uint32_t s_rec[kWarpsPerBlock][32 * kRecWords];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t e0 = (blockIdx.x * kWarpsPerBlock + warp) * 32u;
   if (e0 >= n) return;
   const uint32_t e = e0 + lane;
   if (e < n) {
-    const Env s = load_env(state + e);
-    fill_record(&s_rec[warp][lane * kRecWords], s, history + static_cast<size_t>(e) * kHistoryWords, player_sel);
+    const uint32_t src = ids ? ids[e] : e;  // gather: output row e describes env ids[e]
+    const Env s = load_env(state + src);
+    fill_record(&s_rec[warp][lane * kRecWords], s, history + static_cast<size_t>(src) * kHistoryWords, player_sel);
   }
   __syncwarp();
   const int nrec = static_cast<int>(min(32u, n - e0));
@@ -623,7 +624,7 @@ __device__ __forceinline__ void zero_stage(unsigned char* stage, int lane) {
 template <typename T>
 __global__ void __launch_bounds__(kTmaBlockThreads, 2)
 k_encode_info_tma(const uint4* __restrict__ state, const uint32_t* __restrict__ history, uint32_t n,
-                  int player_sel, T* __restrict__ out, uint32_t stride) {
+                  int player_sel, T* __restrict__ out, uint32_t stride, const uint32_t* __restrict__ ids) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   TmaSmem sm(smem_raw, warp);
@@ -633,8 +634,9 @@ k_encode_info_tma(const uint4* __restrict__ state, const uint32_t* __restrict__ 
   const bool full = e0 + 32u <= n;
   if (full) zero_stage(sm.stage, lane);
   if (e < n) {
-    const Env s = load_env(state + e);
-    fill_record(sm.recs + lane * kRecWords, s, history + static_cast<size_t>(e) * kHistoryWords, player_sel);
+    const uint32_t src = ids ? ids[e] : e;
+    const Env s = load_env(state + src);
+    fill_record(sm.recs + lane * kRecWords, s, history + static_cast<size_t>(src) * kHistoryWords, player_sel);
   }
   __syncwarp();
   const bool both = player_sel == COUP_PLAYER_BOTH;

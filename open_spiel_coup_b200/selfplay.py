@@ -140,3 +140,161 @@ class SelfPlayDataGen:
     def run(self, n_steps):
         for _ in range(n_steps):
             self.step()
+
+
+class UniformRandomPolicy:
+    """The `random` exploitee / baseline bot of the reference's evaluation scripts
+    (`coup_experiments/algorithms/rl_response.py:60`): uniform over the legal actions."""
+
+
+@torch.no_grad()
+def evaluate_policies(policies, num_episodes, num_envs=1 << 16, seed=1234, device=0, tensor_dtype=torch.bfloat16):
+    """Batched agent-vs-agent evaluation (`coup_experiments/scripts/agent_cmp.py`, and the inner loop of
+    `rl_response.eval_against_fixed_bots`, rl_response.py:65-91): `policies[p]` acts whenever player p is
+    to move; exactly `num_episodes` complete games are played (batches without auto-reset, so the sample of
+    episodes is unbiased). Returns the mean episode reward of each seat and the number of decision steps."""
+    totals = torch.zeros(2, dtype=torch.float64)
+    played = steps = 0
+    batch_seed = seed
+    while played < num_episodes:
+        n = min(num_envs, num_episodes - played)
+        env = CoupVectorEnv(n, seed=batch_seed, device=device, auto_reset=False)
+        dev = env.device
+        nets = [None if isinstance(p, UniformRandomPolicy) else p.to(device=dev, dtype=tensor_dtype).eval() for p in policies]
+        width = max([getattr(p, "padded_input_size", INFO_STATE_SIZE) for p in nets if p is not None], default=INFO_STATE_SIZE)
+        info = torch.zeros((n, width), dtype=tensor_dtype, device=dev) if any(p is not None for p in nets) else None
+        for _ in range(100):                      # a game has at most 91 moves
+            if bool(env.done.all()):
+                break
+            if info is not None:
+                env.information_state_tensor(PLAYER_CURRENT, out=info)
+            acts = []
+            for p in nets:
+                if p is None:
+                    acts.append(env.sample_uniform())
+                else:
+                    acts.append(env.sample_policy(p(info[:, :getattr(p, "padded_input_size", INFO_STATE_SIZE)])))
+            a = torch.where(env.current_player == 1, acts[1], acts[0])
+            a = torch.where(env.done.bool(), torch.zeros_like(a), a)
+            env.step(a)
+        assert bool(env.done.all())
+        totals += env.returns.double().sum(0).cpu()   # sum of per-step rewards == Returns() (coup.cc:1016-1032)
+        steps += env.stats()["decision_steps"]
+        played += n
+        batch_seed += 1
+        env.close()
+    return (totals / played).tolist(), steps
+
+
+def eval_against_fixed_bots(trained_policies, fixed_policies, num_episodes, **kw):
+    """`rl_response.eval_against_fixed_bots` (rl_response.py:65-91): for each seat, the trained policy of that
+    seat against the fixed policy in the other seat; returns the mean episode reward of the trained seat."""
+    out = []
+    for seat in range(2):
+        cur = list(fixed_policies)
+        cur[seat] = trained_policies[seat]
+        mean, _ = evaluate_policies(cur, num_episodes, **kw)
+        out.append(mean[seat])
+    return out
+
+
+class ReplayBuffer:
+    """Circular replay buffer of DQN transitions on the device
+    (`open_spiel/python/algorithms/dqn.py:30-32`: `Transition(info_state, action, reward, next_info_state,
+    is_final_step, legal_actions_mask)`; `ReplayBuffer`, dqn.py:35-80). Info states are stored as uint8
+    (values are 0, 1 and coin counts, exact)."""
+
+    def __init__(self, capacity, device):
+        self.capacity, self.device = int(capacity), device
+        self.info_state = torch.zeros((self.capacity, INFO_STATE_SIZE), dtype=torch.uint8, device=device)
+        self.next_info_state = torch.zeros((self.capacity, INFO_STATE_SIZE), dtype=torch.uint8, device=device)
+        self.action = torch.zeros(self.capacity, dtype=torch.uint8, device=device)
+        self.reward = torch.zeros(self.capacity, dtype=torch.int8, device=device)
+        self.is_final_step = torch.zeros(self.capacity, dtype=torch.uint8, device=device)
+        self.legal_actions_mask = torch.zeros(self.capacity, dtype=torch.int32, device=device)   # of the NEXT state
+        self.total = 0
+
+    @property
+    def size(self):
+        return min(self.capacity, self.total)
+
+    def add(self, info_state, action, reward, next_info_state, is_final_step, legal_mask_bits):
+        k = int(action.numel())
+        if k == 0:
+            return
+        pos = (self.total + torch.arange(k, device=self.device)) % self.capacity
+        self.info_state[pos] = info_state
+        self.action[pos] = action
+        self.reward[pos] = reward.to(torch.int8)
+        self.next_info_state[pos] = next_info_state
+        self.is_final_step[pos] = is_final_step.to(torch.uint8) if torch.is_tensor(is_final_step) else int(is_final_step)
+        self.legal_actions_mask[pos] = legal_mask_bits.to(torch.int32) if torch.is_tensor(legal_mask_bits) else int(legal_mask_bits)
+        self.total += k
+
+
+class ReplayRecorder:
+    """Self-play with the reference agents' transition bookkeeping, batched: every env plays both seats with
+    the same acting policy, and for each (env, seat) the recorder keeps the seat's previous decision exactly as
+    `DQN.step` keeps `_prev_timestep` / `_prev_action` (dqn.py:175-222): a transition is emitted when that
+    seat acts again (reward = `Rewards()[seat]` at that moment, next state = its info state then), and, when
+    the episode ends, for BOTH seats with the terminal info state, `is_final_step = 1` and an empty legal
+    mask -- every agent is stepped with the final time step (`coup_experiments/scripts/nfsp.py:141-143`).
+    Rewards that fall between a seat's own turns are dropped, as in the reference."""
+
+    def __init__(self, num_envs, policy=None, seed=1234, device=0, tensor_dtype=torch.bfloat16, replay_capacity=1 << 20,
+                 on_episode_end=None):
+        self.env = CoupVectorEnv(num_envs, seed=seed, device=device, auto_reset=False)
+        dev = self.env.device
+        self.policy = None
+        if not isinstance(policy, UniformRandomPolicy):
+            policy = policy if policy is not None else MLPPolicy(padded_input_size=PADDED_INFO_STATE_SIZE)
+            self.policy = policy.to(device=dev, dtype=tensor_dtype).eval()
+            width = getattr(policy, "padded_input_size", INFO_STATE_SIZE)
+            self.policy_input = torch.zeros((num_envs, width), dtype=tensor_dtype, device=dev)
+        self.info_u8 = torch.empty((num_envs, INFO_STATE_SIZE), dtype=torch.uint8, device=dev)
+        self.pend_info = torch.zeros((num_envs, 2, INFO_STATE_SIZE), dtype=torch.uint8, device=dev)
+        self.pend_action = torch.zeros((num_envs, 2), dtype=torch.uint8, device=dev)
+        self.pend_valid = torch.zeros((num_envs, 2), dtype=torch.bool, device=dev)
+        self.replay = ReplayBuffer(replay_capacity, dev)
+        self.on_episode_end = on_episode_end
+        self._idx = torch.arange(num_envs, device=dev)
+
+    @torch.no_grad()
+    def step(self):
+        env, idx = self.env, self._idx
+        seat = env.current_player.long()                  # every env is at a decision node here
+        env.information_state_tensor(PLAYER_CURRENT, out=self.info_u8)
+        if self.policy is None:
+            actions = env.sample_uniform()
+        else:
+            env.information_state_tensor(PLAYER_CURRENT, out=self.policy_input)
+            actions = env.sample_policy(self.policy(self.policy_input))
+        # the acting seat's previous decision becomes a transition (dqn.py:223-246)
+        had = self.pend_valid[idx, seat]
+        rows = idx[had]
+        s = seat[rows]
+        self.replay.add(self.pend_info[rows, s], self.pend_action[rows, s], env.rewards[rows, s], self.info_u8[rows],
+                        torch.zeros_like(rows), env.legal_mask[rows])
+        self.pend_info[idx, seat] = self.info_u8
+        self.pend_action[idx, seat] = actions
+        self.pend_valid[idx, seat] = True
+        env.step(actions)
+        done = env.done.bool()
+        ids = idx[done]
+        if ids.numel():
+            final = env.information_state_tensor_gather(ids, _lib_player_both(), dtype=torch.uint8).view(-1, 2, INFO_STATE_SIZE)
+            for p in (0, 1):
+                sel = self.pend_valid[ids, p]
+                rows = ids[sel]
+                self.replay.add(self.pend_info[rows, p], self.pend_action[rows, p], env.rewards[rows, p], final[sel, p],
+                                torch.ones_like(rows), torch.zeros_like(rows))
+            if self.on_episode_end is not None:
+                self.on_episode_end(self, ids)
+            self.pend_valid[ids] = False
+            env.reset(envs_to_reset=done)
+        return actions
+
+
+def _lib_player_both():
+    from ._lib import PLAYER_BOTH
+    return PLAYER_BOTH

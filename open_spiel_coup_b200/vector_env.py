@@ -180,6 +180,20 @@ class CoupVectorEnv:
                                                                   _stream_ptr(self.device)))
         return out
 
+    def information_state_tensor_gather(self, env_ids, player=PLAYER_CURRENT, out=None, dtype=torch.float32):
+        """Info-state rows of the envs listed in `env_ids` (int32/int64 device tensor) only."""
+        ids = env_ids.to(device=self.device, dtype=torch.int32).contiguous()
+        count = int(ids.numel())
+        rows = count * (2 if player == PLAYER_BOTH else 1)
+        if out is None:
+            out = torch.empty((rows, INFO_STATE_SIZE), dtype=dtype, device=self.device)
+        if out.shape[0] < rows:
+            raise ValueError("output has too few rows")
+        check(self._lib.coup_vec_information_state_tensor_gather(
+            self._h, self._ptr(ids) if count else None, count, player, _TORCH_TO_DTYPE[out.dtype], self._ptr(out),
+            self._row_stride(out), _stream_ptr(self.device)))
+        return out[:rows]
+
     def observation_tensor(self, player=PLAYER_CURRENT, out=None, dtype=torch.float32):
         """CoupState::ObservationTensor (coup.cc:1051-1056) for every env; [rows, 98]."""
         if out is None:

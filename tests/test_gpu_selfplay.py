@@ -72,3 +72,82 @@ def test_selfplay_datagen_runs_and_records():
     # stored probabilities vanish outside the stored legal mask
     bits = ((mask.view(-1, 1) >> torch.arange(18, device="cuda", dtype=torch.int32)) & 1).bool()
     assert (probs[~bits] == 0).all()
+
+
+def test_batched_evaluation_random_vs_random():
+    """agent_cmp / eval_against_fixed_bots batched on the device. Uniform-random vs uniform-random must
+    reproduce the reference's workload statistics (P0 returns -2/-1/+1/+2 =
+    30.4/20.5/20.0/29.1 % => mean -0.031) and be exactly zero-sum."""
+    from open_spiel_coup_b200.selfplay import UniformRandomPolicy, eval_against_fixed_bots, evaluate_policies
+    n = 300_000
+    mean, steps = evaluate_policies([UniformRandomPolicy(), UniformRandomPolicy()], n, num_envs=1 << 17, seed=5)
+    assert mean[0] == -mean[1]
+    assert abs(mean[0] - (-0.031)) < 0.02
+    assert abs(steps / n - 15.03) < 0.08
+    # an MLP policy in seat 0 against the random bot: runs, legal, zero-sum
+    torch.manual_seed(1)
+    seat = eval_against_fixed_bots([MLPPolicy(padded_input_size=2496), MLPPolicy(padded_input_size=2496)],
+                                   [UniformRandomPolicy(), UniformRandomPolicy()], 20_000, num_envs=1 << 14, seed=6)
+    assert len(seat) == 2 and all(-2 <= x <= 2 for x in seat)
+
+
+def test_replay_recorder_matches_reference_bookkeeping(oracle):
+    """Every transition the batched recorder emits is compared with a sequential re-enactment of the reference
+    loop (nfsp.py:134-144 driving DQN.step/add_transition, dqn.py:175-246) over the same games, with time steps
+    produced by the CPU oracle."""
+    from open_spiel_coup_b200.selfplay import ReplayRecorder, UniformRandomPolicy
+    from open_spiel_coup_b200.vector_env import decode_history
+    n, steps = 96, 70
+    games = [[] for _ in range(n)]        # finished games per env: full action lists
+
+    def on_end(rec, ids):
+        hist = rec.env.history[ids].cpu().numpy().view(np.uint32)
+        lens = rec.env.move_numbers()[ids].cpu().numpy()
+        for e, (acts, _) in zip(ids.cpu().tolist(), decode_history(hist, lens)):
+            games[e].append(list(acts))
+
+    rec = ReplayRecorder(n, policy=UniformRandomPolicy(), seed=31, replay_capacity=1 << 15, on_episode_end=on_end)
+    for _ in range(steps):
+        rec.step()
+    # unfinished games: their pending decisions have emitted only the "acted again" transitions
+    open_hist = rec.env.trajectories()
+    expected = []
+
+    def time_step(s):
+        return {"info": [oracle.info_state(s, p).astype(np.uint8) for p in (0, 1)], "legal": oracle.legal_mask(s),
+                "rewards": oracle.rewards(s), "cur": oracle.current_player(s), "last": oracle.is_terminal(s)}
+
+    def play(actions, finished):
+        s = oracle.new_state()
+        prev = [None, None]
+        i = 0
+        while True:
+            while oracle.current_player(s) == -1:                       # rl_environment resolves chance nodes
+                oracle.apply(s, actions[i]); i += 1
+            ts = time_step(s)
+            if ts["last"]:
+                for p in (0, 1):                                        # every agent sees the final time step
+                    if prev[p] is not None:
+                        expected.append((prev[p][0][p].tobytes(), prev[p][1], ts["rewards"][p], ts["info"][p].tobytes(), 1, 0))
+                return
+            p = ts["cur"]
+            if i >= len(actions):
+                return                                                  # game still running on the device
+            if prev[p] is not None:
+                expected.append((prev[p][0][p].tobytes(), prev[p][1], ts["rewards"][p], ts["info"][p].tobytes(), 0, ts["legal"]))
+            a = actions[i]; i += 1
+            prev[p] = (ts["info"], a)
+            oracle.apply(s, a)
+
+    for e in range(n):
+        for g in games[e]:
+            play(g, True)
+        play(list(open_hist[e][0]), False)
+    rb = rec.replay
+    assert rb.total == len(expected) and rb.total < rb.capacity
+    got = sorted(zip([bytes(x) for x in rb.info_state[:rb.total].cpu().numpy()], rb.action[:rb.total].cpu().tolist(),
+                     [float(x) for x in rb.reward[:rb.total].cpu().tolist()],
+                     [bytes(x) for x in rb.next_info_state[:rb.total].cpu().numpy()],
+                     rb.is_final_step[:rb.total].cpu().tolist(), rb.legal_actions_mask[:rb.total].cpu().tolist()))
+    assert got == sorted(expected)
+    assert sum(len(g) for g in games) > 0 and rb.is_final_step[:rb.total].sum() > 0
