@@ -150,6 +150,19 @@ int coup_vec_new_initial_state(coup_vec_env* env, const uint8_t* d_mask, void* s
 int coup_vec_apply_move(coup_vec_env* env, const uint8_t* d_moves, void* stream);
 int coup_vec_copy_env(coup_vec_env* env, uint32_t src, uint32_t dst, void* stream);
 
+/* Single-env accessors with HOST buffers, following rust_open_spiel.h one to one (GameNewInitialState :41,
+ * StateApplyAction :62, StateClone :49, StateInformationStateTensor / StateObservationTensor :73-76: tensors
+ * are written into a caller-provided buffer of explicit length). `slot` indexes an env of the handle; these
+ * calls synchronise. coup_env_apply_action returns COUP_ERR_ILLEGAL_ACTION and changes nothing when the move is
+ * not in LegalActions() (card ids at chance nodes). coup_env_read copies the packed state (uint32[4]), the
+ * history (uint32[16]) and the step word of one env; any pointer may be NULL. */
+int coup_env_new_initial_state(coup_vec_env* env, uint32_t slot);
+int coup_env_apply_action(coup_vec_env* env, uint32_t slot, int action);
+int coup_env_clone(coup_vec_env* env, uint32_t src, uint32_t dst);
+int coup_env_read(coup_vec_env* env, uint32_t slot, uint32_t* h_state4, uint32_t* h_history16, uint32_t* h_step_word);
+int coup_env_information_state_tensor(coup_vec_env* env, uint32_t slot, int player, float* h_buf, int length);
+int coup_env_observation_tensor(coup_vec_env* env, uint32_t slot, int player, float* h_buf, int length);
+
 /* Uniform-random legal action per env (the policy of benchmark_game.cc:96-99), Philox-driven:
  * writes uint8[num_envs] to d_actions_out (terminal envs get 0xFF). */
 int coup_vec_sample_uniform(coup_vec_env* env, uint8_t* d_actions_out, void* stream);

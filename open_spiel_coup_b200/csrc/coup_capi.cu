@@ -22,6 +22,9 @@ struct coup_vec_env {
   coup_vec_opts opts;
   EnvArrays A;
   uint8_t* d_actions;   // staging for coup_vec_step_host
+  uint32_t* d_scratch;  // [4]: id / illegal flag of the single-env host accessors
+  float* d_row;         // [2 * 2496]: one env's info-state rows
+  float* d_obs_all;     // [n][2][98], allocated on first use
   cudaEvent_t host_outputs_ready;
   uint64_t step_counter;
 };
@@ -137,6 +140,9 @@ int coup_vec_create(const coup_vec_opts* opts, coup_vec_env** out) {
   env->step_counter = 0;
   env->host_outputs_ready = nullptr;
   env->d_actions = nullptr;
+  env->d_scratch = nullptr;
+  env->d_row = nullptr;
+  env->d_obs_all = nullptr;
   const size_t n = opts->num_envs;
   EnvArrays& A = env->A;
   std::memset(&A, 0, sizeof(A));
@@ -156,6 +162,8 @@ int coup_vec_create(const coup_vec_opts* opts, coup_vec_env** out) {
   alloc(reinterpret_cast<void**>(&A.step_word), n * sizeof(uint32_t));
   alloc(reinterpret_cast<void**>(&A.stats), COUP_STATS_LEN * sizeof(unsigned long long));
   alloc(reinterpret_cast<void**>(&env->d_actions), n);
+  alloc(reinterpret_cast<void**>(&env->d_scratch), 4 * sizeof(uint32_t));
+  alloc(reinterpret_cast<void**>(&env->d_row), 2 * 2496 * sizeof(float));
   if (err == cudaSuccess) err = cudaEventCreateWithFlags(&env->host_outputs_ready, cudaEventDisableTiming);
   if (err == cudaSuccess) err = cudaMemset(A.stats, 0, COUP_STATS_LEN * sizeof(unsigned long long));
   if (err == cudaSuccess) err = cudaMemset(A.history, 0, n * kHistoryWords * sizeof(uint32_t));
@@ -178,7 +186,7 @@ int coup_vec_destroy(coup_vec_env* env) {
   cudaFree(env->A.state); cudaFree(env->A.history); cudaFree(env->A.legal); cudaFree(env->A.cur_player);
   cudaFree(env->A.done); cudaFree(env->A.rewards); cudaFree(env->A.returns); cudaFree(env->A.stats);
   cudaFree(env->A.step_word);
-  cudaFree(env->d_actions);
+  cudaFree(env->d_actions); cudaFree(env->d_scratch); cudaFree(env->d_row); cudaFree(env->d_obs_all);
   if (env->host_outputs_ready) cudaEventDestroy(env->host_outputs_ready);
   delete env;
   return COUP_OK;
@@ -221,6 +229,68 @@ int coup_vec_copy_env(coup_vec_env* env, uint32_t src, uint32_t dst, void* strea
   DeviceGuard guard(env->opts.device);
   k_copy_env<<<1, 32, 0, S(stream)>>>(env->A, src, dst);
   return launch_status("k_copy_env");
+}
+
+// ---- single-env accessors with HOST buffers, in the style of rust_open_spiel.h ------------------------
+static int one_move(coup_vec_env* env, uint32_t slot, uint32_t mv, int mode) {
+  if (!env || slot >= env->A.n) return fail(COUP_ERR_INVALID_ARG, "coup_env_*: bad handle or slot");
+  DeviceGuard guard(env->opts.device);
+  k_single_move_one<<<1, 32>>>(env->A, slot, mv, mode, env->d_scratch + 1);
+  uint32_t illegal = 0;
+  if (mode == 1) CUDA_TRY(cudaMemcpy(&illegal, env->d_scratch + 1, sizeof(illegal), cudaMemcpyDeviceToHost));
+  else CUDA_TRY(cudaDeviceSynchronize());
+  int rc = launch_status("k_single_move_one");
+  if (rc != COUP_OK) return rc;
+  return illegal ? fail(COUP_ERR_ILLEGAL_ACTION, "illegal action " + std::to_string(mv)) : COUP_OK;
+}
+
+int coup_env_new_initial_state(coup_vec_env* env, uint32_t slot) { return one_move(env, slot, 0, 0); }
+
+int coup_env_apply_action(coup_vec_env* env, uint32_t slot, int action) {
+  if (action < 0 || action > 255) return fail(COUP_ERR_ILLEGAL_ACTION, "illegal action " + std::to_string(action));
+  return one_move(env, slot, static_cast<uint32_t>(action), 1);
+}
+
+int coup_env_clone(coup_vec_env* env, uint32_t src, uint32_t dst) {
+  int rc = coup_vec_copy_env(env, src, dst, nullptr);
+  if (rc != COUP_OK) return rc;
+  DeviceGuard guard(env->opts.device);
+  CUDA_TRY(cudaDeviceSynchronize());
+  return COUP_OK;
+}
+
+int coup_env_read(coup_vec_env* env, uint32_t slot, uint32_t* h_state4, uint32_t* h_history16, uint32_t* h_step_word) {
+  if (!env || slot >= env->A.n) return fail(COUP_ERR_INVALID_ARG, "coup_env_read: bad handle or slot");
+  DeviceGuard guard(env->opts.device);
+  if (h_state4) CUDA_TRY(cudaMemcpy(h_state4, env->A.state + slot, 16, cudaMemcpyDeviceToHost));
+  if (h_history16) CUDA_TRY(cudaMemcpy(h_history16, env->A.history + static_cast<size_t>(slot) * kHistoryWords, 64, cudaMemcpyDeviceToHost));
+  if (h_step_word) CUDA_TRY(cudaMemcpy(h_step_word, env->A.step_word + slot, 4, cudaMemcpyDeviceToHost));
+  return COUP_OK;
+}
+
+int coup_env_information_state_tensor(coup_vec_env* env, uint32_t slot, int player, float* h_buf, int length) {
+  if (!env || slot >= env->A.n || !h_buf || (player != 0 && player != 1) || length != COUP_INFO_STATE_SIZE)
+    return fail(COUP_ERR_INVALID_ARG, "coup_env_information_state_tensor: bad arguments");
+  DeviceGuard guard(env->opts.device);
+  CUDA_TRY(cudaMemcpy(env->d_scratch, &slot, sizeof(slot), cudaMemcpyHostToDevice));
+  int rc = coup_vec_information_state_tensor_gather(env, env->d_scratch, 1, player, COUP_DTYPE_F32, env->d_row,
+                                                    COUP_INFO_STATE_SIZE, nullptr);
+  if (rc != COUP_OK) return rc;
+  CUDA_TRY(cudaMemcpy(h_buf, env->d_row, COUP_INFO_STATE_SIZE * sizeof(float), cudaMemcpyDeviceToHost));
+  return COUP_OK;
+}
+
+int coup_env_observation_tensor(coup_vec_env* env, uint32_t slot, int player, float* h_buf, int length) {
+  if (!env || slot >= env->A.n || !h_buf || (player != 0 && player != 1) || length != COUP_OBSERVATION_SIZE)
+    return fail(COUP_ERR_INVALID_ARG, "coup_env_observation_tensor: bad arguments");
+  DeviceGuard guard(env->opts.device);
+  if (!env->d_obs_all)
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&env->d_obs_all), static_cast<size_t>(env->A.n) * 2 * COUP_OBSERVATION_SIZE * sizeof(float)));
+  int rc = coup_vec_observation_tensor(env, COUP_PLAYER_BOTH, COUP_DTYPE_F32, env->d_obs_all, nullptr);
+  if (rc != COUP_OK) return rc;
+  CUDA_TRY(cudaMemcpy(h_buf, env->d_obs_all + (static_cast<size_t>(slot) * 2 + player) * COUP_OBSERVATION_SIZE,
+                      COUP_OBSERVATION_SIZE * sizeof(float), cudaMemcpyDeviceToHost));
+  return COUP_OK;
 }
 
 int coup_vec_sample_uniform(coup_vec_env* env, uint8_t* d_actions_out, void* stream) {

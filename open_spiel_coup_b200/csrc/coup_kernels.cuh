@@ -320,6 +320,32 @@ k_single_move(EnvArrays A, const uint8_t* __restrict__ moves_or_mask, int mode) 
   st.flush(A.stats);
 }
 
+// One move on ONE env (mode as in k_single_move); *illegal_out is set to 1 when the move was rejected.
+__global__ void k_single_move_one(EnvArrays A, uint32_t slot, uint32_t mv, int mode, uint32_t* illegal_out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  uint32_t* hist_row = A.history + static_cast<size_t>(slot) * kHistoryWords;
+  Env s;
+  if (mode == 0) {
+    s = initial_state();
+  } else {
+    s = load_env(A.state + slot);
+    const bool term = is_terminal(s);
+    const bool chance = !term && g_chance(s.g);
+    const uint32_t legal = term ? 0u : chance ? legal_mask_chance(s) : legal_mask_decision(s);
+    if (mv < 18u && ((legal >> mv) & 1u)) {
+      HistoryWriter hw(hist_row);
+      if (chance) apply_chance(s, mv, hw); else apply_player_action(s, mv, hw);
+      hw.flush();
+      *illegal_out = 0;
+    } else {
+      *illegal_out = 1;  // nothing changes: the caller raises, as ApplyAction would (spiel_utils.cc:119-137)
+      return;
+    }
+  }
+  store_env(A.state + slot, s);
+  write_outputs_any_node(A, slot, s);
+}
+
 // Copies env `src` onto env `dst` (State::Clone, coup.cc:1058-1060): state, history and outputs.
 __global__ void k_copy_env(EnvArrays A, uint32_t src, uint32_t dst) {
   const int t = threadIdx.x;
