@@ -58,6 +58,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra-contracts", action="store_true")
     ap.add_argument("--no-selfplay", action="store_true")
+    ap.add_argument("--no-host-tensor", action="store_true")
     ap.add_argument("--e2e-slabs", type=int, default=4, help="sub-slabs (handles/streams) of the host-buffer leg")
     ap.add_argument("--encoder", default="staged", choices=["staged", "plain"],
                     help="info-state encoder: shared-memory staging + bulk (TMA) stores, or per-lane vector stores")
@@ -313,6 +314,35 @@ def main():
     assert st2[_lib.STAT_DECISION_STEPS] == Ke * ns * S_ * world and st2[_lib.STAT_ILLEGAL] == 0
     e2e_value = st2[_lib.STAT_DECISION_STEPS] / float(e2e_s.item())
 
+    # Secondary end-to-end number for a HOST-side consumer: additionally copy the whole (uint8, exact) info-state
+    # tensor to pinned host memory every step. This is PCIe-bound by construction (2492 B per step over ~55 GB/s).
+    e2e_host_tensor = None
+    if not args.no_host_tensor and rank == 0 and out is not None:
+        try:
+            h_tensor = torch.empty((n, 2492), dtype=torch.uint8).pin_memory()
+            d_u8 = [torch.empty((ns, 2492), dtype=torch.uint8, device=dev) for _ in slabs]
+
+            def host_tensor_steps(k):
+                for _ in range(k):
+                    for i, (ev, h_act, h_words, t_out, stream, offset) in enumerate(slabs):
+                        lib.coup_host_sample_uniform(C.c_void_p(h_words.data_ptr()), ns, args.seed, offset, ev.step_counter,
+                                                     C.c_void_p(h_act.data_ptr()), threads)
+                        ev.step_host_packed(h_act, h_words, tensor_out=d_u8[i], stream=stream)
+                        with torch.cuda.stream(stream):
+                            h_tensor[i * ns:(i + 1) * ns].copy_(d_u8[i], non_blocking=True)
+                    torch.cuda.synchronize()
+
+            host_tensor_steps(1)
+            t0 = time.perf_counter()
+            host_tensor_steps(3)
+            dt = time.perf_counter() - t0
+            e2e_host_tensor = {"value": 3 * ns * S_ / dt, "unit": UNIT, "dtype": "u8", "d2h_bytes_per_step": (2492 + 4) * ns * S_,
+                               "d2h_gb_per_s": 3 * (2492 + 4) * ns * S_ / dt / 1e9, "steps": 3,
+                               "note": "same loop, plus the full uint8 info-state tensor copied to pinned host memory every step (rank 0 only)"}
+            del h_tensor, d_u8
+        except Exception as exc:       # pinned allocation can fail on small hosts; the primary e2e number stands
+            e2e_host_tensor = {"unavailable": str(exc)[:200]}
+
     # ---- BASELINE configs[3]: self-play data generation, MLP policy on the info-state tensor, 2^18 envs ----
     selfplay = None
     if not args.no_selfplay:
@@ -368,6 +398,7 @@ def main():
                             "one uint32 step word per env (legal mask, current player, done, reward, return) to pinned host memory out, "
                             "every step; the host policy (coup_host_sample_uniform) picks the next actions from those words; the "
                             "info-state tensor is encoded every step and left in HBM for the on-device consumer" % S_},
+            "e2e_tensor_to_host": e2e_host_tensor,
             "gpu_launches": K,
             "clocks": clocks,
             "contracts": extra,

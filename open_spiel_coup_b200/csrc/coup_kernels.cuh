@@ -603,6 +603,17 @@ __device__ __forceinline__ void poke_row(T* row, const uint32_t* rec, int view, 
   }
 }
 
+// Erases a row again: every non-zero lives in the first 62 + 18*len elements, so instead of recomputing the
+// poked positions the warp zero-fills that prefix with four-element stores (2 store instructions for len ~ 10).
+template <typename T>
+__device__ __forceinline__ void clear_row(T* row, const uint32_t* rec, int lane) {
+  using U = typename Unit4<T>::type;
+  const int units = min(kUnitsPerInfoRow, static_cast<int>((62u + 18u * (rec[20] & 255u) + 3u) >> 2));
+  const U zero = Unit4<T>::make(0, 0, 0, 0);
+  U* r4 = reinterpret_cast<U*>(row);
+  for (int q = lane; q < units; q += 32) r4[q] = zero;
+}
+
 // Full warp (32 records): nrows = 32 or 64 rows, in groups of G = 4/sizeof(T) rows per bulk store.
 template <typename T>
 __device__ __forceinline__ void warp_encode_info_tma(const uint32_t* recs, bool both, T* stage,
@@ -626,7 +637,7 @@ __device__ __forceinline__ void warp_encode_info_tma(const uint32_t* recs, bool 
 #pragma unroll
     for (int k = 0; k < G; ++k) {
       const int r = g * G + k;
-      poke_row<T>(stage + k * stride, recs + (both ? (r >> 1) : r) * kRecWords, both ? (r & 1) : 0, false, lane);
+      clear_row<T>(stage + k * stride, recs + (both ? (r >> 1) : r) * kRecWords, lane);
     }
   }
 }

@@ -398,6 +398,35 @@ def test_padded_row_stride(plain, dtype, width):
         env.information_state_tensor(_lib.PLAYER_0, out=torch.empty((n, 2494), dtype=dtype, device=env.device))
 
 
+@pytest.mark.parametrize("plain", [False, True], ids=["staged-tma", "plain-stores"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.uint8])
+@pytest.mark.parametrize("n", [1, 3, 32, 35, 257, 1023])
+def test_encoders_stay_inside_their_output(plain, dtype, n):
+    """compute-sanitizer is closed on this pool, so out-of-bounds writes are hunted with guard bands: the
+    output sits between two canary regions that must survive every encoder variant, for ragged sizes that
+    exercise the partial-warp and partial-group (bulk store) paths."""
+    env = CoupVectorEnv(n, seed=n, auto_reset=True, plain_store_encoder=plain)
+    env.rollout(9)
+    canary = 113 if dtype == torch.uint8 else 113.0
+    guard = 4096
+    for sel, rows, width, fn in (
+            (_lib.PLAYER_CURRENT, n, INFO, env.information_state_tensor), (_lib.PLAYER_BOTH, 2 * n, INFO, env.information_state_tensor),
+            (_lib.PLAYER_BOTH, 2 * n, 2496, env.information_state_tensor), (_lib.PLAYER_BOTH, 2 * n, OBS, env.observation_tensor)):
+        flat = torch.full((guard + rows * width + guard,), canary, dtype=dtype, device=env.device)
+        out = flat[guard: guard + rows * width].view(rows, width)
+        if out.data_ptr() % 16:       # the C ABI requires 16-byte aligned tensors; shift the window if needed
+            continue
+        fn(sel, out=out)
+        torch.cuda.synchronize()
+        assert (flat[:guard] == canary).all() and (flat[guard + rows * width:] == canary).all()
+        assert (out != canary).all()
+    flat = torch.full((guard + n * INFO + guard,), canary, dtype=dtype, device=env.device)
+    out = flat[guard: guard + n * INFO].view(n, INFO)
+    if out.data_ptr() % 16 == 0:
+        env.rollout(1, _lib.PLAYER_CURRENT, out=out)
+        assert (flat[:guard] == canary).all() and (flat[guard + n * INFO:] == canary).all() and (out != canary).all()
+
+
 def test_legal_actions_mask_dense():
     env = CoupVectorEnv(3000, seed=2, auto_reset=True)
     env.rollout(17)
