@@ -253,6 +253,13 @@ int coup_vec_check_errors(coup_vec_env* env, void* stream); /* COUP_OK or COUP_E
 int coup_tensor_row_hash(const void* d_tensor, int dtype, uint32_t rows, uint32_t row_len,
                          uint64_t* d_hash_out, void* stream);
 
+/* Checkpoint / resume of a whole slab (the reference checkpoints a game as its action history,
+ * State::Serialize spiel.cc:297-311; here a snapshot is the raw packed state + history + outputs + statistics +
+ * the Philox step counter, so a restored handle continues bit-identically). Host buffers. */
+size_t coup_vec_snapshot_size(const coup_vec_env* env);
+int coup_vec_snapshot(coup_vec_env* env, void* h_buf, size_t bytes, void* stream);
+int coup_vec_restore(coup_vec_env* env, const void* h_buf, size_t bytes, void* stream);
+
 /* Global step counter that keys the Philox streams (snapshot = state + history + this counter). */
 uint64_t coup_vec_step_counter(const coup_vec_env* env);
 int coup_vec_set_step_counter(coup_vec_env* env, uint64_t value);

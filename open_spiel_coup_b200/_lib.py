@@ -43,7 +43,7 @@ EXPORTED_SYMBOLS = [
     "coup_vec_information_state_tensor", "coup_vec_observation_tensor",
     "coup_vec_information_state_tensor_strided", "coup_vec_rollout_strided", "coup_vec_information_state_tensor_gather", "coup_vec_step_host", "coup_vec_step_host_packed",
     "coup_host_sample_uniform", "coup_vec_stats", "coup_vec_stats_device", "coup_vec_clear_stats", "coup_vec_check_errors",
-    "coup_tensor_row_hash", "coup_vec_step_counter", "coup_vec_set_step_counter",
+    "coup_tensor_row_hash", "coup_vec_snapshot_size", "coup_vec_snapshot", "coup_vec_restore", "coup_vec_step_counter", "coup_vec_set_step_counter",
 ]
 
 
@@ -114,6 +114,10 @@ def load():
     lib.coup_vec_clear_stats.argtypes = [vp, vp]
     lib.coup_vec_check_errors.argtypes = [vp, vp]
     lib.coup_tensor_row_hash.argtypes = [vp, C.c_int, C.c_uint32, C.c_uint32, vp, vp]
+    lib.coup_vec_snapshot_size.argtypes = [vp]
+    lib.coup_vec_snapshot_size.restype = C.c_size_t
+    lib.coup_vec_snapshot.argtypes = [vp, vp, C.c_size_t, vp]
+    lib.coup_vec_restore.argtypes = [vp, vp, C.c_size_t, vp]
     lib.coup_vec_step_counter.argtypes = [vp]
     lib.coup_vec_step_counter.restype = C.c_uint64
     lib.coup_vec_set_step_counter.argtypes = [vp, C.c_uint64]

@@ -8,6 +8,7 @@
 #include <new>
 #include <algorithm>
 #include <string>
+#include <vector>
 
 #include "coup_kernels.cuh"
 
@@ -494,6 +495,61 @@ int coup_tensor_row_hash(const void* d_tensor, int dtype, uint32_t rows, uint32_
       break;
   }
   return launch_status("k_row_hash");
+}
+
+// ---- snapshot / restore: raw copy of the packed slab + outputs + statistics + the Philox step counter ----------
+namespace {
+struct SnapshotHeader {
+  uint64_t magic, num_envs, seed, global_env_offset, step_counter, flags;
+};
+constexpr uint64_t kSnapshotMagic = 0x31304e53424f4355ull;  // "UCOBSN01"
+struct Part { void* ptr; size_t bytes; };
+std::vector<Part> snapshot_parts(coup_vec_env* env) {
+  const size_t n = env->A.n;
+  return {{env->A.state, n * 16}, {env->A.history, n * kHistoryWords * 4}, {env->A.legal, n * 4}, {env->A.cur_player, n},
+          {env->A.done, n}, {env->A.rewards, n * 2}, {env->A.returns, n * 2}, {env->A.step_word, n * 4},
+          {env->A.stats, COUP_STATS_LEN * 8}};
+}
+}  // namespace
+
+size_t coup_vec_snapshot_size(const coup_vec_env* env) {
+  if (!env) return 0;
+  size_t total = sizeof(SnapshotHeader);
+  for (const Part& p : snapshot_parts(const_cast<coup_vec_env*>(env))) total += p.bytes;
+  return total;
+}
+
+int coup_vec_snapshot(coup_vec_env* env, void* h_buf, size_t bytes, void* stream) {
+  if (!env || !h_buf || bytes < coup_vec_snapshot_size(env)) return fail(COUP_ERR_INVALID_ARG, "coup_vec_snapshot: buffer too small");
+  DeviceGuard guard(env->opts.device);
+  SnapshotHeader hdr{kSnapshotMagic, env->A.n, env->A.seed, env->A.global_env_offset, env->step_counter, env->A.flags};
+  std::memcpy(h_buf, &hdr, sizeof(hdr));
+  char* dst = static_cast<char*>(h_buf) + sizeof(hdr);
+  for (const Part& p : snapshot_parts(env)) {
+    CUDA_TRY(cudaMemcpyAsync(dst, p.ptr, p.bytes, cudaMemcpyDeviceToHost, S(stream)));
+    dst += p.bytes;
+  }
+  CUDA_TRY(cudaStreamSynchronize(S(stream)));
+  return COUP_OK;
+}
+
+int coup_vec_restore(coup_vec_env* env, const void* h_buf, size_t bytes, void* stream) {
+  if (!env || !h_buf || bytes < coup_vec_snapshot_size(env)) return fail(COUP_ERR_INVALID_ARG, "coup_vec_restore: buffer too small");
+  SnapshotHeader hdr;
+  std::memcpy(&hdr, h_buf, sizeof(hdr));
+  if (hdr.magic != kSnapshotMagic || hdr.num_envs != env->A.n)
+    return fail(COUP_ERR_INVALID_ARG, "coup_vec_restore: not a snapshot of a handle with this many envs");
+  DeviceGuard guard(env->opts.device);
+  const char* src = static_cast<const char*>(h_buf) + sizeof(hdr);
+  for (const Part& p : snapshot_parts(env)) {
+    CUDA_TRY(cudaMemcpyAsync(p.ptr, src, p.bytes, cudaMemcpyHostToDevice, S(stream)));
+    src += p.bytes;
+  }
+  CUDA_TRY(cudaStreamSynchronize(S(stream)));
+  env->A.seed = env->opts.seed = hdr.seed;
+  env->A.global_env_offset = env->opts.global_env_offset = hdr.global_env_offset;
+  env->step_counter = hdr.step_counter;
+  return COUP_OK;
 }
 
 uint64_t coup_vec_step_counter(const coup_vec_env* env) { return env ? env->step_counter : 0; }

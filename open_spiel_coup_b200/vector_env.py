@@ -237,6 +237,23 @@ class CoupVectorEnv:
     def step_counter(self, v):
         check(self._lib.coup_vec_set_step_counter(self._h, int(v)))
 
+    # ---- checkpoint / resume ------------------------------------------------------------------------
+    def snapshot(self):
+        """Whole-slab checkpoint as a numpy byte array (state, history, outputs, stats, Philox counter)."""
+        size = int(self._lib.coup_vec_snapshot_size(self._h))
+        buf = np.empty(size, np.uint8)
+        check(self._lib.coup_vec_snapshot(self._h, C.c_void_p(buf.ctypes.data), size, _stream_ptr(self.device)))
+        return buf
+
+    def restore(self, buf):
+        buf = np.ascontiguousarray(buf, np.uint8)
+        check(self._lib.coup_vec_restore(self._h, C.c_void_p(buf.ctypes.data), buf.size, _stream_ptr(self.device)))
+
+    def serialized_states(self):
+        """Every env's current state in the reference's wire format (State::Serialize, spiel.cc:297-311:
+        one action id per line), loadable with Game::DeserializeState / pyspiel.deserialize_game_and_state."""
+        return ["\n".join(str(int(a)) for a in acts) + "\n" for acts, _ in self.trajectories()]
+
     # ---- trajectory export (host side, for replay through the oracle) -----------------------------
     def move_numbers(self):
         return (self.state[:, 3] & 127).to(torch.int64)

@@ -348,6 +348,8 @@ class Reference:
         L.ref_trace.argtypes = [vp, C.c_int, vp]
         L.ref_trace_batch.argtypes = [vp, vp, C.c_int, vp, C.c_int]
         L.ref_replay_digest_batch.argtypes = [vp, vp, C.c_int, vp, vp, C.c_int]
+        L.ref_deserialize_state.argtypes = [C.c_char_p]
+        L.ref_deserialize_state.restype = vp
         L.ref_state_from_actions.argtypes = [vp, C.c_int]
         L.ref_state_from_actions.restype = vp
         L.ref_bench.argtypes = [C.c_int, C.c_int, C.c_long, C.c_uint32, vp]
@@ -380,6 +382,12 @@ class Reference:
         h = self.lib.ref_state_from_actions(a.ctypes.data, len(a))
         if not h:
             raise ValueError("reference rejected action list: " + self.last_error())
+        return h
+
+    def deserialize_state(self, text):
+        h = self.lib.ref_deserialize_state(text.encode())
+        if not h:
+            raise ValueError("reference rejected serialized state: " + self.last_error())
         return h
 
     def apply(self, h, a):

@@ -218,6 +218,19 @@ int ref_history(const void* h, long* actions, int* players, int cap) {
   return n;
 }
 
+// Game::DeserializeState (spiel.cc:393-432): the reference parses a serialized state. nullptr on error.
+void* ref_deserialize_state(const char* text) {
+  try {
+    return TheGame()->DeserializeState(text).release();
+  } catch (const RefError& e) {
+    g_last_error = e.what();
+    return nullptr;
+  } catch (const std::exception& e) {
+    g_last_error = e.what();
+    return nullptr;
+  }
+}
+
 // CoupState convenience accessors (coup.h:139-143).
 int ref_get_cards(const void* h, int player, int* values, int* states) {
   auto* cs = static_cast<const open_spiel::coup::CoupState*>(S(h));

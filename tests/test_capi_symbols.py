@@ -68,3 +68,26 @@ def test_product_never_touches_oracle():
                 code = "\n".join(ln for ln in text.split("\n") if not ln.strip().startswith(("//", "#", "*", "/*")))
                 assert "coup_oracle" not in code and "libcoup_ref" not in code and "from oracle" not in code \
                     and "import oracle" not in code, f"{f} references the oracle"
+
+
+def test_cpp_wrapper_compiles_links_and_refuses_without_device(lib):
+    """include/coup_b200.hpp (RAII layer over the C ABI) builds against the library with the host compiler."""
+    src = r'''
+#include "coup_b200.hpp"
+#include <cstdio>
+int main() {
+  if (coup_device_count() == 0) {
+    try { coup_b200::VectorEnv env(64); } catch (const coup_b200::Error& e) { return e.code == COUP_ERR_NO_DEVICE ? 0 : 2; }
+    return 3;
+  }
+  coup_b200::VectorEnv env(64, 1, 0, 0, true);
+  env.Rollout(10);
+  auto st = env.Stats();
+  return st[COUP_STAT_DECISION_STEPS] == 640 && st[COUP_STAT_ILLEGAL] == 0 ? 0 : 4;
+}
+'''
+    exe = "/tmp/coup_b200_hpp_test"
+    pkg = os.path.join(ROOT, "open_spiel_coup_b200")
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-I", os.path.join(ROOT, "include"), "-x", "c++", "-", "-o", exe,
+                    "-L", pkg, "-lcoup_b200", f"-Wl,-rpath,{pkg}"], input=src.encode(), check=True)
+    assert subprocess.run([exe]).returncode == 0

@@ -672,3 +672,34 @@ def test_full_size_properties():
     total = deck["deck"].sum(1) + deck["num_cards"].sum(1)
     assert (total == 15).all()                                                           # cards are conserved
     assert (deck["coins"] <= 12).all()
+
+
+def test_snapshot_restore_resumes_bit_identically(oracle):
+    n = 5000
+    env = CoupVectorEnv(n, seed=17, auto_reset=True)
+    env.rollout(20)
+    snap = env.snapshot()
+    counter = env.step_counter
+    out_a = torch.empty((n, INFO), dtype=torch.float32, device=env.device)
+    env.rollout(25, _lib.PLAYER_CURRENT, out=out_a)
+    state_a, hist_a, stats_a, word_a = env.state.clone(), env.history.clone(), env.stats(), env.step_word.clone()
+    # restore into the same handle ...
+    env.restore(snap)
+    assert env.step_counter == counter
+    out_b = torch.empty_like(out_a)
+    env.rollout(25, _lib.PLAYER_CURRENT, out=out_b)
+    assert torch.equal(env.state, state_a) and torch.equal(env.history, hist_a) and torch.equal(out_a, out_b)
+    assert env.stats() == stats_a and torch.equal(env.step_word, word_a)
+    # ... and into a fresh handle created with other parameters (seed / offset come from the snapshot)
+    other = CoupVectorEnv(n, seed=999, auto_reset=True, global_env_offset=123)
+    other.restore(snap)
+    other.rollout(25, _lib.PLAYER_CURRENT, out=out_b)
+    assert torch.equal(other.state, state_a) and torch.equal(out_a, out_b) and other.stats() == stats_a
+    with pytest.raises(_lib.CoupError):
+        CoupVectorEnv(n + 1, seed=1).restore(snap)
+    # the wire format of the current states replays through the oracle to the same states
+    texts = env.serialized_states()
+    for e in range(0, n, 250):
+        acts = [int(x) for x in texts[e].split("\n") if x]
+        s = oracle.state_from_actions(acts)
+        assert oracle.legal_mask(s) == int(env.legal_mask[e]) & 0xFFFFFFFF

@@ -67,3 +67,19 @@ def test_action_to_string_matches_reference(reference):
         assert reference.action_to_string(0, a) == ACTION_NAMES[a]
     for c in range(5):
         assert reference.action_to_string(-1, c) == "Chance drawn card:" + CARD_NAMES[c]
+
+
+def test_wire_format_loads_in_the_reference(reference, ref_trajectories):
+    """SURVEY.md section 8(f)-3: trajectories are exported as the reference's own serialisation (State::Serialize,
+    spiel.cc:297-311: one action id per line), so the reference's Game::DeserializeState loads them."""
+    actions, offsets, _ = ref_trajectories
+    for t in range(0, 400, 7):
+        acts = actions[offsets[t]:offsets[t + 1]]
+        for upto in (len(acts), len(acts) // 2, 4, 0):
+            text = "\n".join(str(int(a)) for a in acts[:upto]) + "\n"   # CoupVectorEnv.serialized_states() / CoupState.serialize()
+            h = reference.deserialize_state(text)
+            g = reference.state_from_actions(acts[:upto])
+            assert reference.serialize(h) == text
+            assert reference.to_string(h) == reference.to_string(g)
+            reference.free(h)
+            reference.free(g)
