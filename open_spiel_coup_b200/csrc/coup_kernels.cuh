@@ -614,42 +614,49 @@ __device__ __forceinline__ void clear_row(T* row, const uint32_t* rec, int lane)
   for (int q = lane; q < units; q += 32) r4[q] = zero;
 }
 
-// Full warp (32 records): nrows = 32 or 64 rows, in groups of G = 4/sizeof(T) rows per bulk store.
+// Full block (8 warps x 32 records): the block's rows form one contiguous span of the output, written in groups
+// of G = 4/sizeof(T) rows per bulk store. Groups are dealt to the warps ROUND-ROBIN (warp w takes groups w, w+8,
+// ...), so at any moment the eight warps of a block are writing eight ADJACENT groups: that keeps the DRAM write
+// stream sequential over ~80 KB windows and is worth ~5 % of HBM write bandwidth over each warp streaming its own
+// 32 rows (scripts/store_bw_probe.cu: 7.26 vs 6.93 TB/s for pure bulk stores of this shape).
 template <typename T>
-__device__ __forceinline__ void warp_encode_info_tma(const uint32_t* recs, bool both, T* stage,
-                                                     unsigned char* out_bytes, int lane, int stride) {
+__device__ __forceinline__ void block_encode_info_tma(const uint32_t* block_recs, bool both, T* stage,
+                                                      unsigned char* out_block_bytes, int warp, int lane, int stride) {
   constexpr int G = 4 / static_cast<int>(sizeof(T));
   const uint32_t group_bytes = static_cast<uint32_t>(G * stride) * sizeof(T);  // 9968 (stride 2492) or 9984 (2496)
-  const int ngroups = (both ? 64 : 32) / G;
-  for (int g = 0; g < ngroups; ++g) {
+  const int ngroups = (both ? 2 : 1) * kTmaWarpsPerBlock * 32 / G;
+  for (int g = warp; g < ngroups; g += kTmaWarpsPerBlock) {
 #pragma unroll
     for (int k = 0; k < G; ++k) {
       const int r = g * G + k;
-      poke_row<T>(stage + k * stride, recs + (both ? (r >> 1) : r) * kRecWords, both ? (r & 1) : 0, true, lane);
+      poke_row<T>(stage + k * stride, block_recs + (both ? (r >> 1) : r) * kRecWords, both ? (r & 1) : 0, true, lane);
     }
     tma_store_fence();   // generic-proxy writes -> visible to the async proxy
     __syncwarp();
     if (lane == 0) {
-      tma_bulk_store(out_bytes + static_cast<size_t>(g) * group_bytes, stage, group_bytes);
+      tma_bulk_store(out_block_bytes + static_cast<size_t>(g) * group_bytes, stage, group_bytes);
       tma_wait_read_all();  // the engine has read the buffer (the global write itself is still in flight)
     }
     __syncwarp();
 #pragma unroll
     for (int k = 0; k < G; ++k) {
       const int r = g * G + k;
-      clear_row<T>(stage + k * stride, recs + (both ? (r >> 1) : r) * kRecWords, lane);
+      clear_row<T>(stage + k * stride, block_recs + (both ? (r >> 1) : r) * kRecWords, lane);
     }
   }
+  if (lane == 0) tma_wait_all();
 }
 
-// Carves the dynamic shared memory of a staged kernel: per warp [stage 9968 B][32 records], then stats.
+// Carves the dynamic shared memory of a staged kernel: [8 stage buffers of 9984 B][8 x 32 records][stats].
 struct TmaSmem {
-  unsigned char* stage;
-  uint32_t* recs;
+  unsigned char* stage;   // this warp's staging buffer
+  uint32_t* block_recs;   // records of the whole block, indexed by env-in-block
+  uint32_t* recs;         // this warp's 32 records
   uint32_t* stats;
   __device__ __forceinline__ TmaSmem(unsigned char* base, int warp) {
     stage = base + static_cast<size_t>(warp) * kStageBytes;
-    recs = reinterpret_cast<uint32_t*>(base + static_cast<size_t>(kTmaWarpsPerBlock) * kStageBytes) + warp * 32 * kRecWords;
+    block_recs = reinterpret_cast<uint32_t*>(base + static_cast<size_t>(kTmaWarpsPerBlock) * kStageBytes);
+    recs = block_recs + warp * 32 * kRecWords;
     stats = reinterpret_cast<uint32_t*>(base + static_cast<size_t>(kTmaWarpsPerBlock) * kTmaSmemPerWarp);
   }
 };
@@ -665,26 +672,27 @@ k_encode_info_tma(const uint4* __restrict__ state, const uint32_t* __restrict__ 
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   TmaSmem sm(smem_raw, warp);
-  const uint32_t e0 = (blockIdx.x * kTmaWarpsPerBlock + warp) * 32u;
-  if (e0 >= n) return;
+  const uint32_t b0 = blockIdx.x * (kTmaWarpsPerBlock * 32u);
+  const uint32_t e0 = b0 + warp * 32u;
   const uint32_t e = e0 + lane;
-  const bool full = e0 + 32u <= n;
-  if (full) zero_stage(sm.stage, lane);
+  const bool block_full = b0 + kTmaWarpsPerBlock * 32u <= n;  // uniform over the block
+  const bool both = player_sel == COUP_PLAYER_BOTH;
+  if (block_full) zero_stage(sm.stage, lane);
   if (e < n) {
     const uint32_t src = ids ? ids[e] : e;
     const Env s = load_env(state + src);
     fill_record(sm.recs + lane * kRecWords, s, history + static_cast<size_t>(src) * kHistoryWords, player_sel);
   }
-  __syncwarp();
-  const bool both = player_sel == COUP_PLAYER_BOTH;
-  const size_t row0 = static_cast<size_t>(e0) * (both ? 2 : 1);
-  if (full) {
-    warp_encode_info_tma<T>(sm.recs, both, reinterpret_cast<T*>(sm.stage),
-                            reinterpret_cast<unsigned char*>(out) + row0 * stride * sizeof(T), lane, static_cast<int>(stride));
-    if (lane == 0) tma_wait_all();
-  } else {  // ragged last warp: plain vector stores
+  if (block_full) {
+    __syncthreads();
+    block_encode_info_tma<T>(sm.block_recs, both, reinterpret_cast<T*>(sm.stage),
+                             reinterpret_cast<unsigned char*>(out) + static_cast<size_t>(b0) * (both ? 2 : 1) * stride * sizeof(T),
+                             warp, lane, static_cast<int>(stride));
+  } else if (e0 < n) {  // ragged last block: per-warp plain vector stores
+    __syncwarp();
     using U = typename Unit4<T>::type;
-    warp_encode_info<T>(sm.recs, static_cast<int>(n - e0), both, reinterpret_cast<U*>(out) + row0 * (stride / 4), lane,
+    const size_t row0 = static_cast<size_t>(e0) * (both ? 2 : 1);
+    warp_encode_info<T>(sm.recs, static_cast<int>(min(32u, n - e0)), both, reinterpret_cast<U*>(out) + row0 * (stride / 4), lane,
                         static_cast<int>(stride / 4));
   }
 }
@@ -784,11 +792,13 @@ k_rollout_tma(EnvArrays A, uint64_t step, int player_sel, T* __restrict__ out, u
   TmaSmem sm(smem_raw, warp);
   BlockStats st;
   st.init(sm.stats);
-  const uint32_t e0 = (blockIdx.x * kTmaWarpsPerBlock + warp) * 32u;
+  const uint32_t b0 = blockIdx.x * (kTmaWarpsPerBlock * 32u);
+  const uint32_t e0 = b0 + warp * 32u;
   const uint32_t e = e0 + lane;
   const bool active = e < A.n;
-  const bool full = e0 + 32u <= A.n;
-  if (full) zero_stage(sm.stage, lane);
+  const bool block_full = b0 + kTmaWarpsPerBlock * 32u <= A.n;  // uniform over the block
+  const bool both = player_sel == COUP_PLAYER_BOTH;
+  if (block_full) zero_stage(sm.stage, lane);
   StepResult r = {};
   if (active) {
     Env s = load_env(A.state + e);
@@ -799,19 +809,17 @@ k_rollout_tma(EnvArrays A, uint64_t step, int player_sel, T* __restrict__ out, u
     fill_record(sm.recs + lane * kRecWords, s, hist_row, player_sel);
   }
   account(st, r, active);
-  if (e0 < A.n) {
+  if (block_full) {
+    __syncthreads();   // every warp's records are in shared memory
+    block_encode_info_tma<T>(sm.block_recs, both, reinterpret_cast<T*>(sm.stage),
+                             reinterpret_cast<unsigned char*>(out) + static_cast<size_t>(b0) * (both ? 2 : 1) * stride * sizeof(T),
+                             warp, lane, static_cast<int>(stride));
+  } else if (e0 < A.n) {
     __syncwarp();
-    const bool both = player_sel == COUP_PLAYER_BOTH;
+    using U = typename Unit4<T>::type;
     const size_t row0 = static_cast<size_t>(e0) * (both ? 2 : 1);
-    if (full) {
-      warp_encode_info_tma<T>(sm.recs, both, reinterpret_cast<T*>(sm.stage),
-                              reinterpret_cast<unsigned char*>(out) + row0 * stride * sizeof(T), lane, static_cast<int>(stride));
-      if (lane == 0) tma_wait_all();
-    } else {
-      using U = typename Unit4<T>::type;
-      warp_encode_info<T>(sm.recs, static_cast<int>(A.n - e0), both, reinterpret_cast<U*>(out) + row0 * (stride / 4), lane,
-                          static_cast<int>(stride / 4));
-    }
+    warp_encode_info<T>(sm.recs, static_cast<int>(min(32u, A.n - e0)), both, reinterpret_cast<U*>(out) + row0 * (stride / 4), lane,
+                        static_cast<int>(stride / 4));
   }
   st.flush(A.stats);
 }
