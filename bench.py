@@ -48,7 +48,7 @@ def workload_text(contract):
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs", type=int, default=1 << 20, help="envs per GPU")
@@ -143,8 +143,20 @@ def cpu_reference_run(mode, threads, seconds, seed=1234):
               f"LegalActions + InformationStateTensor(current player) at every decision node "
               f"(open_spiel/examples/benchmark_game.cc protocol), one State + std::mt19937 per thread, -O3 -DNDEBUG"
               + ("" if kind == "reference" else "; C restatement of the reference (oracle/_ref not built)"))
-    return {"value": res["decisions_per_s"], "unit": UNIT, "cores": threads, "kind": kind, "sample": sample,
-            "moves_per_s": res["moves_per_s"], "episodes_per_s": res["episodes_per_s"]}, res
+    out = {"value": res["decisions_per_s"], "unit": UNIT, "cores": threads, "kind": kind, "sample": sample,
+           "moves_per_s": res["moves_per_s"], "episodes_per_s": res["episodes_per_s"]}
+    # The other protocols of SURVEY.md section 8(d) / BASELINE.md section 3, on short samples (decision steps/s):
+    # mode 0 = step + LegalActions only, mode 2 = info-state of BOTH players (rl_environment semantics), and
+    # BASELINE.json configs[0]: 10^4 episodes on ONE thread with the benchmark_game.cc protocol.
+    extra = {}
+    for name, m, th, eps in (("step_and_legal_actions_only", 0, threads, int(probe["episodes_per_s"] * 6)),
+                             ("info_state_both_players", 2, threads, int(probe["episodes_per_s"] * 1.5)),
+                             ("config0_single_thread_10k_episodes", 1, 1, 10000)):
+        r = impl.bench(m, th, max(eps, 1000 * th), seed + 7)
+        extra[name] = {"steps_per_s": r["decisions_per_s"], "moves_per_s": r["moves_per_s"], "threads": th,
+                       "episodes": r["episodes"], "seconds": round(r["seconds"], 2)}
+    out["other_protocols"] = extra
+    return out, res
 
 
 def run_reference_arm(args):

@@ -245,7 +245,7 @@ k_reset(EnvArrays A, const uint8_t* __restrict__ mask, const uint8_t* __restrict
 }
 
 // ---- step with caller-provided actions --------------------------------------------------------------
-__global__ void __launch_bounds__(kBlockThreads)
+__global__ void __launch_bounds__(kBlockThreads, 5)
 k_step(EnvArrays A, const uint8_t* __restrict__ actions, const uint8_t* __restrict__ forced, uint64_t step) {
   __shared__ uint32_t s_stats[COUP_STATS_LEN];
   BlockStats st;
@@ -751,7 +751,7 @@ k_encode_obs(const uint4* __restrict__ state, uint32_t n, int player_sel, T* __r
 
 // ---- fused random rollout step: sample -> step -> chance -> [auto-reset] -> outputs -> encode -------
 template <typename T, bool kEncode>
-__global__ void __launch_bounds__(kBlockThreads)
+__global__ void __launch_bounds__(kBlockThreads, kEncode ? 4 : 5)   // rules only: cap registers for 5 blocks/SM
 k_rollout(EnvArrays A, uint64_t step, int player_sel, T* __restrict__ out, uint32_t stride) {
   __shared__ uint32_t s_stats[COUP_STATS_LEN];
   __shared__ uint32_t s_rec[kEncode ? kWarpsPerBlock : 1][kEncode ? 32 * kRecWords : 1];
