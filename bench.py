@@ -60,6 +60,8 @@ def parse_args():
     ap.add_argument("--no-selfplay", action="store_true")
     ap.add_argument("--no-host-tensor", action="store_true")
     ap.add_argument("--e2e-slabs", type=int, default=4, help="sub-slabs (handles/streams) of the host-buffer leg")
+    ap.add_argument("--fused", default="ws", choices=["ws", "cta"],
+                    help="fused rollout kernel: persistent warp-specialised (rules warps + encoder warps), or one CTA per 256 envs")
     ap.add_argument("--encoder", default="staged", choices=["staged", "plain"],
                     help="info-state encoder: shared-memory staging + bulk (TMA) stores, or per-lane vector stores")
     return ap.parse_args()
@@ -223,7 +225,7 @@ def main():
     contract = args.contract
     torch_dtype = {"d32": torch.float32, "bf16": torch.bfloat16, "d8": torch.uint8, "env": None}[contract]
     env = CoupVectorEnv(n, seed=args.seed, device=local, global_env_offset=slab_offset, auto_reset=True,
-                        plain_store_encoder=(args.encoder == "plain"))
+                        plain_store_encoder=(args.encoder == "plain"), warp_specialised=(args.fused == "ws"))
     out = None if torch_dtype is None else torch.empty((n, 2492), dtype=torch_dtype, device=dev)
     sel = None if out is None else _lib.PLAYER_CURRENT
 
@@ -387,7 +389,7 @@ def main():
         peak, peak_src = measured_peak()
         bytes_per_launch = BYTES_PER_STEP[contract] * n
         achieved = bytes_per_launch / per_launch_s / 1e9
-        kname = "k_rollout_tma<%s>" if args.encoder == "staged" else "k_rollout<%s,true>"
+        kname = ("k_rollout_ws<%s>" if args.fused == "ws" else "k_rollout_tma<%s>") if args.encoder == "staged" else "k_rollout<%s,true>"
         kernel = {"d32": kname % "float", "bf16": kname % "__nv_bfloat16", "d8": kname % "uint8_t",
                   "env": "k_rollout<float,false>"}[contract]
         line = {
@@ -396,7 +398,7 @@ def main():
             "dtype": CONTRACT_DTYPE[contract], "data": "synthetic",
             "config": {
                 "workload": workload_text(contract),
-                "envs_per_gpu": n, "contract": contract, "bytes_per_step": BYTES_PER_STEP[contract], "encoder": args.encoder,
+                "envs_per_gpu": n, "contract": contract, "bytes_per_step": BYTES_PER_STEP[contract], "encoder": args.encoder, "fused_kernel": args.fused,
                 "parallelism": f"env-slab x{world} (no data-path collective; NCCL all-reduce of the stats vector only)",
                 "l2": "per-step working set (%.2f GB written + 80 MB state/history) >> 126 MB L2, no flush needed" % (bytes_per_launch / 1e9)
                       if contract != "env" else "state+history 80 MiB/GPU is L2-resident by design (env-only contract)",

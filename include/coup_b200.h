@@ -76,6 +76,8 @@ enum {
                                     then describe the first decision of the new episode */
   , COUP_FLAG_PLAIN_STORE_ENCODER = 1u << 1 /* info-state rows written with per-lane vector stores instead
                                     of the default shared-memory staging + bulk (TMA) stores; same bytes */
+  , COUP_FLAG_NO_WARP_SPECIALISATION = 1u << 2 /* fused rollout: one CTA per 256 envs instead of the default
+                                    persistent kernel whose rules warps and encoder warps overlap; same bytes */
 };
 
 typedef struct coup_vec_opts {

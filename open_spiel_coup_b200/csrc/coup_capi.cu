@@ -83,17 +83,33 @@ template <typename T>
 int rollout_typed(coup_vec_env* env, int n_steps, int encode_player, void* d_out, uint32_t stride, cudaStream_t st) {
   const unsigned grid = blocks_for(env->A.n);
   const bool staged = encode_player >= 0 && use_staged_encoder(env, stride);
+  const bool specialised = staged && (env->opts.flags & COUP_FLAG_NO_WARP_SPECIALISATION) == 0 && env->A.n >= kWsBatch;
+  int sms = 0;
   if (staged) {
     cudaError_t err = cudaFuncSetAttribute(k_rollout_tma<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmemBytes);
+    if (err == cudaSuccess && specialised) {
+      err = cudaFuncSetAttribute(k_rollout_ws<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWsSmemBytes);
+      if (err == cudaSuccess) err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, env->opts.device);
+    }
     if (err != cudaSuccess) return fail(COUP_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(err));
   }
+  const uint32_t n_batches = env->A.n / kWsBatch, tail_base = n_batches * kWsBatch;
   for (int i = 0; i < n_steps; ++i) {
-    if (staged)
-      k_rollout_tma<T><<<grid, kTmaBlockThreads, kTmaSmemBytes, st>>>(env->A, env->step_counter, encode_player, static_cast<T*>(d_out), stride);
-    else if (encode_player >= 0)
+    if (specialised) {
+      // persistent, warp-specialised: one CTA per SM over the full 256-env batches, then the ragged tail (if any)
+      cudaMemsetAsync(env->d_scratch + 2, 0, sizeof(uint32_t), st);   // the dynamic batch counter
+      k_rollout_ws<T><<<std::min<unsigned>(sms, n_batches), kWsThreads, kWsSmemBytes, st>>>(
+          env->A, env->step_counter, encode_player, static_cast<T*>(d_out), stride, n_batches, env->d_scratch + 2);
+      if (tail_base < env->A.n)
+        k_rollout_tma<T><<<1, kTmaBlockThreads, kTmaSmemBytes, st>>>(env->A, env->step_counter, encode_player,
+                                                                      static_cast<T*>(d_out), stride, tail_base);
+    } else if (staged) {
+      k_rollout_tma<T><<<grid, kTmaBlockThreads, kTmaSmemBytes, st>>>(env->A, env->step_counter, encode_player, static_cast<T*>(d_out), stride, 0u);
+    } else if (encode_player >= 0) {
       k_rollout<T, true><<<grid, kBlockThreads, 0, st>>>(env->A, env->step_counter, encode_player, static_cast<T*>(d_out), stride);
-    else
+    } else {
       k_rollout<T, false><<<grid, kBlockThreads, 0, st>>>(env->A, env->step_counter, 0, static_cast<T*>(nullptr), stride);
+    }
     env->step_counter++;
   }
   return launch_status("k_rollout");

@@ -621,11 +621,12 @@ __device__ __forceinline__ void clear_row(T* row, const uint32_t* rec, int lane)
 // 32 rows (scripts/store_bw_probe.cu: 7.26 vs 6.93 TB/s for pure bulk stores of this shape).
 template <typename T>
 __device__ __forceinline__ void block_encode_info_tma(const uint32_t* block_recs, bool both, T* stage,
-                                                      unsigned char* out_block_bytes, int warp, int lane, int stride) {
+                                                      unsigned char* out_block_bytes, int warp, int lane, int stride,
+                                                      int nwarps = kTmaWarpsPerBlock, bool wait_for_writes = true) {
   constexpr int G = 4 / static_cast<int>(sizeof(T));
   const uint32_t group_bytes = static_cast<uint32_t>(G * stride) * sizeof(T);  // 9968 (stride 2492) or 9984 (2496)
   const int ngroups = (both ? 2 : 1) * kTmaWarpsPerBlock * 32 / G;
-  for (int g = warp; g < ngroups; g += kTmaWarpsPerBlock) {
+  for (int g = warp; g < ngroups; g += nwarps) {
 #pragma unroll
     for (int k = 0; k < G; ++k) {
       const int r = g * G + k;
@@ -644,7 +645,8 @@ __device__ __forceinline__ void block_encode_info_tma(const uint32_t* block_recs
       clear_row<T>(stage + k * stride, block_recs + (both ? (r >> 1) : r) * kRecWords, lane);
     }
   }
-  if (lane == 0) tma_wait_all();
+  // Before the CTA exits the engine must be done with this warp's shared memory (a persistent caller defers this).
+  if (wait_for_writes && lane == 0) tma_wait_all();
 }
 
 // Carves the dynamic shared memory of a staged kernel: [8 stage buffers of 9984 B][8 x 32 records][stats].
@@ -786,13 +788,13 @@ k_rollout(EnvArrays A, uint64_t step, int player_sel, T* __restrict__ out, uint3
 // Same fused step, with the staged (shared memory + bulk store) encoder.
 template <typename T>
 __global__ void __launch_bounds__(kTmaBlockThreads, 2)
-k_rollout_tma(EnvArrays A, uint64_t step, int player_sel, T* __restrict__ out, uint32_t stride) {
+k_rollout_tma(EnvArrays A, uint64_t step, int player_sel, T* __restrict__ out, uint32_t stride, uint32_t env_base) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   TmaSmem sm(smem_raw, warp);
   BlockStats st;
   st.init(sm.stats);
-  const uint32_t b0 = blockIdx.x * (kTmaWarpsPerBlock * 32u);
+  const uint32_t b0 = env_base + blockIdx.x * (kTmaWarpsPerBlock * 32u);
   const uint32_t e0 = b0 + warp * 32u;
   const uint32_t e = e0 + lane;
   const bool active = e < A.n;
@@ -821,6 +823,83 @@ k_rollout_tma(EnvArrays A, uint64_t step, int player_sel, T* __restrict__ out, u
     warp_encode_info<T>(sm.recs, static_cast<int>(min(32u, A.n - e0)), both, reinterpret_cast<U*>(out) + row0 * (stride / 4), lane,
                         static_cast<int>(stride / 4));
   }
+  st.flush(A.stats);
+}
+
+// ---- warp-specialised persistent variant of the fused step --------------------------------------------------
+// One 24-warp CTA per SM loops over 256-env batches. Warps 0..7 run the RULES for batch i+1 (thread per env,
+// one 32-env group each) and leave the encoder records in one half of a double-buffered shared-memory area,
+// while warps 8..23 ENCODE batch i with bulk stores (one staging buffer each, row groups dealt round-robin).
+// The two roles hand batches over through named barriers (full/empty per buffer), so the bulk-store stream never
+// pauses for a rules phase -- in k_rollout_tma every warp of a CTA stops storing while it steps its envs.
+constexpr int kWsWarps = 24, kWsRulesWarps = 8, kWsEncWarps = kWsWarps - kWsRulesWarps;
+constexpr int kWsThreads = kWsWarps * 32;
+constexpr int kWsBatch = kTmaWarpsPerBlock * 32;                       // 256 envs
+constexpr int kWsRecBytes = kWsBatch * kRecWords * 4;                  // 21 504 B per record buffer
+constexpr int kWsSmemBytes = kWsEncWarps * kStageBytes + 2 * kWsRecBytes + COUP_STATS_LEN * 4;
+enum { kBarFull0 = 1, kBarFull1 = 2, kBarEmpty0 = 3, kBarEmpty1 = 4, kBarRules = 5 };
+
+__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+template <typename T>
+__global__ void __launch_bounds__(kWsThreads, 1)
+k_rollout_ws(EnvArrays A, uint64_t step, int player_sel, T* __restrict__ out, uint32_t stride, uint32_t n_batches,
+             unsigned int* __restrict__ batch_counter) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ int s_batch[2];   // batch held by each record buffer, -1 = no more work
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned char* stage_base = smem_raw;
+  uint32_t* const rec0 = reinterpret_cast<uint32_t*>(smem_raw + kWsEncWarps * kStageBytes);
+  BlockStats st;
+  st.init(reinterpret_cast<uint32_t*>(smem_raw + kWsEncWarps * kStageBytes + 2 * kWsRecBytes));
+  const bool both = player_sel == COUP_PLAYER_BOTH;
+  const bool rules = warp < kWsRulesWarps;
+  unsigned char* stage = rules ? nullptr : stage_base + static_cast<size_t>(warp - kWsRulesWarps) * kStageBytes;
+  if (!rules) zero_stage(stage, lane);
+  // Batches are handed out dynamically (global counter): SMs differ by ~20 % in achieved store bandwidth, so a
+  // static split would leave the fast ones idle at the end.
+  for (int it = 0;; ++it) {
+    const int buf = it & 1;
+    uint32_t* recs = rec0 + buf * (kWsRecBytes / 4);
+    if (rules) {
+      if (it >= 2) named_bar_sync(kBarEmpty0 + buf, kWsThreads);       // the encoders are done with this buffer
+      if (warp == 0 && lane == 0) {
+        const unsigned int b = atomicAdd(batch_counter, 1u);
+        s_batch[buf] = b < n_batches ? static_cast<int>(b) : -1;
+      }
+      named_bar_sync(kBarRules, kWsRulesWarps * 32);
+      const int b = s_batch[buf];
+      if (b >= 0) {
+        for (int sub = warp; sub < kWsBatch / 32; sub += kWsRulesWarps) {
+          const uint32_t e = static_cast<uint32_t>(b) * kWsBatch + sub * 32 + lane;
+          Env s = load_env(A.state + e);
+          uint32_t* hist_row = A.history + static_cast<size_t>(e) * kHistoryWords;
+          const StepResult r = step_env<true>(s, hist_row, 0, nullptr, A, e, step);
+          store_env(A.state + e, s);
+          write_outputs(A, e, r);
+          fill_record(recs + (sub * 32 + lane) * kRecWords, s, hist_row, player_sel);
+          account(st, r, true);
+        }
+      }
+      __threadfence_block();
+      named_bar_arrive(kBarFull0 + buf, kWsThreads);                    // records (or the stop mark) are ready
+      if (b < 0) {
+        if (it >= 1) named_bar_sync(kBarEmpty0 + (buf ^ 1), kWsThreads);  // drain the last hand-back
+        break;
+      }
+    } else {
+      named_bar_sync(kBarFull0 + buf, kWsThreads);
+      const int b = s_batch[buf];
+      if (b < 0) break;
+      block_encode_info_tma<T>(recs, both, reinterpret_cast<T*>(stage),
+                               reinterpret_cast<unsigned char*>(out) +
+                                   static_cast<size_t>(b) * kWsBatch * (both ? 2 : 1) * stride * sizeof(T),
+                               warp - kWsRulesWarps, lane, static_cast<int>(stride), kWsEncWarps, /*wait_for_writes=*/false);
+      named_bar_arrive(kBarEmpty0 + buf, kWsThreads);                   // hand the record buffer back
+    }
+  }
+  if (!rules && lane == 0) tma_wait_all();
   st.flush(A.stats);
 }
 

@@ -93,10 +93,11 @@ def test_sample_step_until_all_done(oracle, plain):
     env.check_errors()
 
 
-@pytest.mark.parametrize("plain", [False, True], ids=["staged-tma", "plain-stores"])
-def test_fused_rollout_equals_sample_then_step(oracle, plain):
+@pytest.mark.parametrize("plain,ws", [(False, True), (False, False), (True, False)],
+                         ids=["warp-specialised", "staged-tma", "plain-stores"])
+def test_fused_rollout_equals_sample_then_step(oracle, plain, ws):
     a_env = CoupVectorEnv(4096 + 37, seed=99, auto_reset=True, plain_store_encoder=not plain)   # ragged tail
-    b_env = CoupVectorEnv(4096 + 37, seed=99, auto_reset=True, plain_store_encoder=plain)
+    b_env = CoupVectorEnv(4096 + 37, seed=99, auto_reset=True, plain_store_encoder=plain, warp_specialised=ws)
     out = torch.empty((a_env.num_envs, INFO), dtype=torch.float32, device=a_env.device)
     for step in range(80):
         acts = a_env.sample_uniform()
@@ -649,10 +650,11 @@ def test_ragged_sizes(oracle, n):
     check_env_against_oracle(oracle, env, expect_done=False)
 
 
-def test_full_size_properties():
+@pytest.mark.parametrize("n,ws", [(1 << 20, True), ((1 << 20) + 300, True), (1 << 20, False)],
+                         ids=["warp-specialised", "warp-specialised-ragged", "cta-per-256-envs"])
+def test_full_size_properties(n, ws):
     """BASELINE config 2 size (2^20 envs): properties that do not need the oracle."""
-    n = 1 << 20
-    env = CoupVectorEnv(n, seed=1234, auto_reset=True)
+    env = CoupVectorEnv(n, seed=1234, auto_reset=True, warp_specialised=ws)
     out = torch.empty((n, INFO), dtype=torch.float32, device=env.device)
     env.rollout(30, _lib.PLAYER_CURRENT, out=out)
     s = env.stats()
