@@ -36,6 +36,8 @@ UNIT = "env steps/s"
 #   env-only 42 B = state 16 R + 16 W, legal mask 4, action 1, rewards+done+cur_player 4, log append 1.41
 #   + dense info-state row (2492 elements) + ~11 B of history read by the encoder
 BYTES_PER_STEP = {"d32": 42 + 9968 + 11, "bf16": 42 + 4984 + 11, "d8": 42 + 2492 + 11, "env": 42}
+# incremental contract (persistent [N,2,2492] fp32 buffer, only changed elements rewritten): SURVEY.md section 8(d)
+BYTES_PER_STEP_INCREMENTAL_F32 = 945
 CONTRACT_DTYPE = {"d32": "f32", "bf16": "bf16", "d8": "u8", "env": "u32"}
 
 
@@ -280,7 +282,20 @@ def main():
             v2 = kk * n * world / (m2 * 1e-3)
             extra[name] = {"steps_per_s": v2, "hbm_gbs": BYTES_PER_STEP[name] * v2 / world / 1e9}
             del buf
+        # contract I: persistent fp32 buffer with both views of every env, updated in place
+        if out is not None:
+            del out
+            torch.cuda.empty_cache()
+        inc = torch.empty((2 * n, 2492), dtype=torch.float32, device=dev)
+        env.information_state_tensor(_lib.PLAYER_BOTH, out=inc)
+        env.rollout_incremental(5, inc)
+        m2 = timed(lambda k: env.rollout_incremental(k, inc), ke)
+        v2 = ke * n * world / (m2 * 1e-3)
+        extra["incremental_f32_both_views"] = {"steps_per_s": v2, "hbm_gbs": BYTES_PER_STEP_INCREMENTAL_F32 * v2 / world / 1e9,
+                                               "bytes_per_step": BYTES_PER_STEP_INCREMENTAL_F32}
+        del inc
         torch.cuda.empty_cache()
+        out = None if torch_dtype is None else torch.empty((n, 2492), dtype=torch_dtype, device=dev)
 
     # ---- end to end through the host-buffer C-ABI call -------------------------------------------
     # The slab is driven as `args.e2e_slabs` sub-slabs, each with its own handle, stream and pinned host

@@ -183,6 +183,13 @@ int coup_vec_sample_policy(coup_vec_env* env, const void* d_logits, int dtype, f
 int coup_vec_rollout(coup_vec_env* env, int n_steps, int encode_player, int dtype, void* d_tensor_out,
                      void* stream);
 
+/* Fused random rollout with the INCREMENTAL tensor contract (contract I): d_buf is a
+ * persistent dtype[num_envs][2][row_stride] buffer that already holds both players' info-state rows of every env
+ * (fill it once with coup_vec_information_state_tensor_strided(COUP_PLAYER_BOTH)); every step rewrites only the
+ * elements that changed (head, the new history rows, and zeros over a finished episode's rows), so the buffer always
+ * equals what the dense encoder would write. Re-fill it after coup_vec_reset / coup_vec_restore. */
+int coup_vec_rollout_incremental(coup_vec_env* env, int n_steps, int dtype, void* d_buf, uint32_t row_stride, void* stream);
+
 /* ---- per-env outputs of the last reset/step (device pointers owned by the handle) --------------- */
 const uint32_t* coup_vec_legal_mask(const coup_vec_env* env);  /* LegalActions() as bit a, coup.cc:824-938 */
 const int8_t* coup_vec_current_player(const coup_vec_env* env); /* 0, 1 or -4 terminal, coup.cc:458-466 */

@@ -38,7 +38,7 @@ EXPORTED_SYMBOLS = [
     "coup_last_error", "coup_device_count", "coup_vec_create", "coup_vec_destroy", "coup_vec_num_envs",
     "coup_vec_reset", "coup_vec_step", "coup_vec_new_initial_state", "coup_vec_apply_move", "coup_vec_copy_env", "coup_env_new_initial_state", "coup_env_apply_action", "coup_env_clone", "coup_env_read",
     "coup_env_information_state_tensor", "coup_env_observation_tensor",
-    "coup_vec_sample_uniform", "coup_vec_sample_policy", "coup_vec_rollout",
+    "coup_vec_sample_uniform", "coup_vec_sample_policy", "coup_vec_rollout", "coup_vec_rollout_incremental",
     "coup_vec_legal_mask", "coup_vec_current_player", "coup_vec_done", "coup_vec_rewards",
     "coup_vec_returns", "coup_vec_step_word", "coup_vec_state", "coup_vec_history", "coup_vec_legal_actions_mask",
     "coup_vec_information_state_tensor", "coup_vec_observation_tensor",
@@ -97,6 +97,7 @@ def load():
     lib.coup_env_observation_tensor.argtypes = [vp, C.c_uint32, C.c_int, vp, C.c_int]
     lib.coup_vec_sample_uniform.argtypes = [vp, u8p, vp]
     lib.coup_vec_sample_policy.argtypes = [vp, vp, C.c_int, vp, vp, vp]
+    lib.coup_vec_rollout_incremental.argtypes = [vp, C.c_int, C.c_int, vp, C.c_uint32, vp]
     lib.coup_vec_rollout.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp]
     for name in ("coup_vec_legal_mask", "coup_vec_current_player", "coup_vec_done", "coup_vec_rewards",
                  "coup_vec_returns", "coup_vec_state", "coup_vec_history", "coup_vec_stats_device", "coup_vec_step_word"):

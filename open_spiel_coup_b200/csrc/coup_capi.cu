@@ -131,6 +131,16 @@ int encode_info_typed(coup_vec_env* env, int player, void* d_out, uint32_t strid
   return launch_status("k_encode_info");
 }
 
+template <typename T>
+int rollout_incremental_typed(coup_vec_env* env, int n_steps, void* d_buf, uint32_t stride, cudaStream_t st) {
+  const unsigned grid = blocks_for(env->A.n);
+  for (int i = 0; i < n_steps; ++i) {
+    k_rollout_incremental<T><<<grid, kBlockThreads, 0, st>>>(env->A, env->step_counter, static_cast<T*>(d_buf), stride);
+    env->step_counter++;
+  }
+  return launch_status("k_rollout_incremental");
+}
+
 }  // namespace
 
 extern "C" {
@@ -350,6 +360,17 @@ int coup_vec_rollout_strided(coup_vec_env* env, int n_steps, int encode_player, 
 
 int coup_vec_rollout(coup_vec_env* env, int n_steps, int encode_player, int dtype, void* d_tensor_out, void* stream) {
   return coup_vec_rollout_strided(env, n_steps, encode_player, dtype, d_tensor_out, COUP_INFO_STATE_SIZE, stream);
+}
+
+int coup_vec_rollout_incremental(coup_vec_env* env, int n_steps, int dtype, void* d_buf, uint32_t row_stride, void* stream) {
+  if (!env || n_steps < 0 || !d_buf || !valid_dtype(dtype) || !valid_stride(row_stride))
+    return fail(COUP_ERR_INVALID_ARG, "coup_vec_rollout_incremental: bad arguments");
+  DeviceGuard guard(env->opts.device);
+  switch (dtype) {
+    case COUP_DTYPE_F32: return rollout_incremental_typed<float>(env, n_steps, d_buf, row_stride, S(stream));
+    case COUP_DTYPE_U8: return rollout_incremental_typed<uint8_t>(env, n_steps, d_buf, row_stride, S(stream));
+    default: return rollout_incremental_typed<__nv_bfloat16>(env, n_steps, d_buf, row_stride, S(stream));
+  }
 }
 
 const uint32_t* coup_vec_legal_mask(const coup_vec_env* env) { return env ? env->A.legal : nullptr; }

@@ -152,6 +152,15 @@ class CoupVectorEnv:
                                                  self._ptr(out), self._row_stride(out), _stream_ptr(self.device)))
         return out
 
+    def rollout_incremental(self, n_steps, buf):
+        """Fused random rollout that keeps `buf` ([2*num_envs, >=2492], both views of every env, previously filled by
+        information_state_tensor(PLAYER_BOTH, out=buf)) up to date by rewriting only the changed elements."""
+        if buf.shape[0] != 2 * self.num_envs:
+            raise ValueError("incremental buffer must have 2 * num_envs rows")
+        check(self._lib.coup_vec_rollout_incremental(self._h, n_steps, _TORCH_TO_DTYPE[buf.dtype], self._ptr(buf),
+                                                     self._row_stride(buf), _stream_ptr(self.device)))
+        return buf
+
     def step_host(self, h_actions, h_legal_mask=None, h_current_player=None, h_done=None, h_rewards=None,
                   tensor_out=None):
         """Host-buffer path: numpy/pinned-torch buffers in and out, tensors stay on the device."""

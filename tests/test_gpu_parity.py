@@ -705,3 +705,26 @@ def test_snapshot_restore_resumes_bit_identically(oracle):
         acts = [int(x) for x in texts[e].split("\n") if x]
         s = oracle.state_from_actions(acts)
         assert oracle.legal_mask(s) == int(env.legal_mask[e]) & 0xFFFFFFFF
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.uint8])
+@pytest.mark.parametrize("auto_reset,width,n", [(True, 2492, 3000), (True, 2496, 1000 + 7), (False, 2492, 2048)])
+def test_incremental_contract_equals_dense_encoder(dtype, auto_reset, width, n):
+    """SURVEY.md section 8(d) contract I: a persistent both-views buffer updated in place (head, new history rows,
+    cleared rows after a re-deal) must equal the dense encoder's output after every step."""
+    env = CoupVectorEnv(n, seed=5, auto_reset=auto_reset)
+    twin = CoupVectorEnv(n, seed=5, auto_reset=auto_reset)
+    buf = torch.full((2 * n, width), 9, dtype=dtype, device=env.device)
+    env.information_state_tensor(_lib.PLAYER_BOTH, out=buf)
+    dense = torch.empty_like(buf)
+    for step in range(120 if not auto_reset else 70):
+        env.rollout_incremental(1, buf)
+        twin.rollout(1)
+        assert torch.equal(env.state, twin.state) and torch.equal(env.step_word, twin.step_word)
+        if step % 3 == 0 or step > 60:
+            env.information_state_tensor(_lib.PLAYER_BOTH, out=dense)
+            assert torch.equal(buf, dense), f"step {step}"
+    env.rollout_incremental(25, buf)
+    env.information_state_tensor(_lib.PLAYER_BOTH, out=dense)
+    assert torch.equal(buf, dense)
+    assert env.stats()["episodes"] >= n and env.stats()["illegal"] == 0
