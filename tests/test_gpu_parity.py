@@ -728,3 +728,27 @@ def test_incremental_contract_equals_dense_encoder(dtype, auto_reset, width, n):
     env.information_state_tensor(_lib.PLAYER_BOTH, out=dense)
     assert torch.equal(buf, dense)
     assert env.stats()["episodes"] >= n and env.stats()["illegal"] == 0
+
+
+def test_partial_reset_only_touches_selected_envs(oracle):
+    """SyncVectorEnv.reset(envs_to_reset) (vector_env.py:68-78): unselected envs keep their state and outputs."""
+    n = 4096
+    env = CoupVectorEnv(n, seed=41)
+    for _ in range(12):
+        env.step(env.sample_uniform())
+    before_state, before_hist, before_word = env.state.clone(), env.history.clone(), env.step_word.clone()
+    mask = (torch.arange(n, device=env.device) % 3 == 0).to(torch.uint8)
+    env.reset(envs_to_reset=mask)
+    keep = mask == 0
+    assert torch.equal(env.state[keep], before_state[keep]) and torch.equal(env.history[keep], before_hist[keep])
+    assert torch.equal(env.step_word[keep], before_word[keep])
+    moves = env.move_numbers()
+    assert (moves[mask == 1] == 4).all() and (env.current_player[mask == 1] == 0).all() and (env.done[mask == 1] == 0).all()
+    assert (env.legal_mask[mask == 1] == sum(1 << a for a in (0, 1, 3, 5, 6))).all()
+    check_env_against_oracle(oracle, env, expect_done=False)
+    # forced deals go to P1, P2, P1, P2 in this order (coup.cc:424-427)
+    deals = torch.tensor([[4, 0, 2, 3]], dtype=torch.uint8).repeat(n, 1)
+    env.reset(forced_deals=deals)
+    st = unpack_states(env.state.cpu().numpy())
+    assert (st["hands"][:, 0, :2] == [2 << 1, 4 << 1]).all() and (st["hands"][:, 1, :2] == [0 << 1, 3 << 1]).all()
+    assert (st["deck"] == [2, 3, 2, 2, 2]).all()

@@ -193,3 +193,45 @@ def test_illegal_moves_raise(game):
     with pytest.raises(SpielError):
         state.chance_outcomes()
     assert state.legal_actions() == [0, 1, 3, 5, 6]
+
+
+def test_rl_environment_mirror(oracle):
+    """open_spiel/python/rl_environment.py semantics on the GPU-backed game: FIRST/MID/LAST, rewards None at FIRST,
+    discounts zeroed at LAST, legal actions empty for the non-acting player, step after LAST resets
+    (rl_environment.py:219-367), and every time step equal to what the oracle produces for the same history."""
+    from open_spiel_coup_b200 import rl_environment
+    env = rl_environment.Environment("coup", discount=0.9)
+    env.seed(7)
+    assert env.num_players == 2 and env.is_turn_based and env.name == "coup"
+    assert env.observation_spec()["info_state"] == (2492,) and env.action_spec()["num_actions"] == 18
+    rng = np.random.default_rng(0)
+    for ep in range(6):
+        ts = env.reset()
+        assert ts.first() and ts.rewards is None and ts.discounts is None
+        n_steps = 0
+        while not ts.last():
+            cur = ts.observations["current_player"]
+            hist = env.get_state.history()
+            s = oracle.state_from_actions(hist)
+            assert cur == oracle.current_player(s)
+            assert ts.observations["legal_actions"][cur] == oracle.legal_actions(s)
+            assert ts.observations["legal_actions"][1 - cur] == []
+            for p in (0, 1):
+                np.testing.assert_array_equal(np.array(ts.observations["info_state"][p], np.float32), oracle.info_state(s, p))
+            la = ts.observations["legal_actions"][cur]
+            ts = env.step([int(la[rng.integers(len(la))])])
+            n_steps += 1
+            if not ts.last():
+                assert ts.mid() and ts.discounts == [0.9, 0.9]
+            s2 = oracle.state_from_actions(env.get_state.history())
+            assert ts.rewards == oracle.rewards(s2)
+        assert ts.discounts == [0.0, 0.0] and ts.observations["current_player"] == -4
+        assert ts.observations["legal_actions"] == [[], []]
+        again = env.step([0])          # a step after LAST starts a new sequence and ignores the action
+        assert again.first()
+    obs_env = rl_environment.Environment("coup", observation_type=rl_environment.ObservationType.OBSERVATION,
+                                         enable_legality_check=True, include_full_state=True)
+    ts = obs_env.reset()
+    assert len(ts.observations["info_state"][0]) == 98 and ts.observations["serialized_state"].startswith("# Automatically")
+    with pytest.raises(RuntimeError):
+        obs_env.step([9])
