@@ -152,6 +152,20 @@ int coup_vec_new_initial_state(coup_vec_env* env, const uint8_t* d_mask, void* s
 int coup_vec_apply_move(coup_vec_env* env, const uint8_t* d_moves, void* stream);
 int coup_vec_copy_env(coup_vec_env* env, uint32_t src, uint32_t dst, void* stream);
 
+/* Batched `state.child(action)` (spiel.h:365-370 Clone + ApplyAction), the tree-expansion step of the sampled
+ * CFR traversals (python/algorithms/deep_cfr.py:415-497; every recursive call there is one child). For
+ * i < count: env i of `dst` becomes a copy of env d_parent[i] of `src` (state + history) with player action
+ * d_actions[i] applied and every following chance node resolved, exactly like coup_vec_step but NEVER
+ * auto-resetting (a terminal child stays terminal so that its Returns() can be read). The chance draws come from
+ * dst's Philox stream (dst seed, dst global env id of slot i, dst step counter, which advances by one), so
+ * siblings forked from one parent draw independently, as np.random.choice does per recursive call
+ * (deep_cfr.py:432-434). d_forced_chance as in coup_vec_step (uint8[count][4] or NULL). Envs >= count of `dst`
+ * are left untouched; all per-env outputs of `dst` are refreshed for i < count. A terminal parent or an illegal
+ * action sets the child's sticky error bit. `dst` and `src` must be different handles on the same device with
+ * count <= num_envs(dst) and every d_parent[i] < num_envs(src) (out-of-range parents set the error bit). */
+int coup_vec_fork(coup_vec_env* dst, const coup_vec_env* src, const uint32_t* d_parent, const uint8_t* d_actions,
+                  const uint8_t* d_forced_chance, uint32_t count, void* stream);
+
 /* Single-env accessors with HOST buffers, following rust_open_spiel.h one to one (GameNewInitialState :41,
  * StateApplyAction :62, StateClone :49, StateInformationStateTensor / StateObservationTensor :73-76: tensors
  * are written into a caller-provided buffer of explicit length). `slot` indexes an env of the handle; these

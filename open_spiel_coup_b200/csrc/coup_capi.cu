@@ -258,6 +258,23 @@ int coup_vec_copy_env(coup_vec_env* env, uint32_t src, uint32_t dst, void* strea
   return launch_status("k_copy_env");
 }
 
+int coup_vec_fork(coup_vec_env* dst, const coup_vec_env* src, const uint32_t* d_parent, const uint8_t* d_actions,
+                  const uint8_t* d_forced_chance, uint32_t count, void* stream) {
+  if (!dst || !src || dst == src || (count && (!d_parent || !d_actions)))
+    return fail(COUP_ERR_INVALID_ARG, "coup_vec_fork: null argument or dst == src");
+  if (dst->opts.device != src->opts.device) return fail(COUP_ERR_INVALID_ARG, "coup_vec_fork: handles on different devices");
+  if (count > dst->A.n) return fail(COUP_ERR_INVALID_ARG, "coup_vec_fork: count exceeds num_envs of dst");
+  DeviceGuard guard(dst->opts.device);
+  if (count) {
+    EnvArrays D = dst->A;
+    D.flags &= ~static_cast<uint32_t>(COUP_FLAG_AUTO_RESET);
+    k_fork<<<blocks_for(count), kBlockThreads, 0, S(stream)>>>(D, src->A.state, src->A.history, src->A.n, d_parent, d_actions,
+                                                             d_forced_chance, count, dst->step_counter);
+  }
+  dst->step_counter++;
+  return launch_status("k_fork");
+}
+
 // ---- single-env accessors with HOST buffers, in the style of rust_open_spiel.h ------------------------
 static int one_move(coup_vec_env* env, uint32_t slot, uint32_t mv, int mode) {
   if (!env || slot >= env->A.n) return fail(COUP_ERR_INVALID_ARG, "coup_env_*: bad handle or slot");

@@ -361,6 +361,44 @@ __global__ void k_copy_env(EnvArrays A, uint32_t src, uint32_t dst) {
   }
 }
 
+// ---- batched state.child(action): dst[i] = step(copy of src[parent[i]], action[i]) without auto-reset ------
+// One thread per child: 16 B state + 64 B history row gathered from the parent slab (four 16 B loads), stepped in
+// registers, written to the child's own row. D.flags arrives with COUP_FLAG_AUTO_RESET cleared.
+__global__ void __launch_bounds__(kBlockThreads)
+k_fork(EnvArrays D, const uint4* __restrict__ src_state, const uint32_t* __restrict__ src_history, uint32_t src_n,
+       const uint32_t* __restrict__ parent, const uint8_t* __restrict__ actions, const uint8_t* __restrict__ forced,
+       uint32_t count, uint64_t step) {
+  __shared__ uint32_t s_stats[COUP_STATS_LEN];
+  BlockStats st;
+  st.init(s_stats);
+  const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = e < count;
+  StepResult r = {};
+  if (active) {
+    const uint32_t p = parent[e];
+    uint32_t* hist_row = D.history + static_cast<size_t>(e) * kHistoryWords;
+    Env s;
+    if (p < src_n) {
+      const uint4* src_row = reinterpret_cast<const uint4*>(src_history + static_cast<size_t>(p) * kHistoryWords);
+      uint4* dst_row = reinterpret_cast<uint4*>(hist_row);
+#pragma unroll
+      for (int k = 0; k < kHistoryWords / 4; ++k) dst_row[k] = src_row[k];
+      s = load_env(src_state + p);
+      const bool parent_terminal = is_terminal(s);
+      r = step_env<false>(s, hist_row, actions[e], forced ? forced + static_cast<size_t>(e) * 4 : nullptr, D, e, step);
+      if (parent_terminal) { s.g |= kBitError; r.illegal = true; }   // a terminal state has no children
+    } else {
+      s = initial_state();
+      s.g |= kBitError;
+      r.illegal = true; r.done = false; r.legal = 0; r.cur_player = COUP_CHANCE_PLAYER_ID;
+    }
+    store_env(D.state + e, s);
+    write_outputs(D, e, r);
+  }
+  account(st, r, active);
+  st.flush(D.stats);
+}
+
 // ---- uniform-random legal action (same draw the fused rollout would use at this step counter) ------
 __global__ void __launch_bounds__(kBlockThreads)
 k_sample_uniform(EnvArrays A, uint8_t* __restrict__ actions_out, uint64_t step) {

@@ -1,0 +1,531 @@
+"""Deep CFR on Coup with the game-tree traversals batched on the device.
+
+Mirror of the reference's `open_spiel/python/algorithms/deep_cfr.py` (`DeepCFRSolver`, as driven by
+`coup_experiments/scripts/deep_cfr.py:86-124`): same constructor arguments, the same three sampling methods
+(`external`, `outcome`, `e-outcome`), the same memory records and losses. What changes is HOW the tree is walked.
+The reference recurses one `state.child(action)` at a time in Python and calls the advantage network with a batch
+of one at every node (`deep_cfr.py:415-497,499-525`). Here `num_traversals` roots are expanded level by level:
+
+  level L (M nodes resident in one env slab)
+    -> info-state rows of the player to move             (coup_vec_information_state_tensor_gather, u8)
+    -> advantage nets on all rows at once, regret matching (`regret_matching`, :499-525)
+    -> traverser nodes: every legal action (external) or a sample without replacement (outcome, :441-466);
+       opponent nodes: one action from the matched regrets (:482-492)
+    -> coup_vec_fork: all children of the level in one launch into the other slab (chance nodes are resolved
+       inside the fork from the child's own Philox stream, :430-434)
+  then one backward sweep over the levels computes expected payoffs, counterfactual values and sampled regrets
+  (:468-480) and appends `AdvantageMemory` / `StrategyMemory` records to device-resident reservoir buffers.
+
+Only the per-level bookkeeping (a few dozen small torch ops) runs from Python; states never leave HBM.
+"""
+import collections
+import math
+import os
+
+import torch
+from torch import nn
+
+from ._lib import INFO_STATE_SIZE, NUM_DISTINCT_ACTIONS, PLAYER_CURRENT
+from .vector_env import CoupVectorEnv
+
+AdvantageMemory = collections.namedtuple("AdvantageMemory", "info_state iteration advantage action")   # deep_cfr.py:36-37
+StrategyMemory = collections.namedtuple("StrategyMemory", "info_state iteration strategy_action_probs")  # deep_cfr.py:39-40
+
+
+def _legal_bool(legal_bits):
+    """uint32 legal masks [M] -> bool [M, 18]."""
+    bits = torch.arange(NUM_DISTINCT_ACTIONS, device=legal_bits.device, dtype=torch.int32)
+    return ((legal_bits.view(-1, 1).to(torch.int32) >> bits) & 1).to(torch.bool)
+
+
+def regret_matching(advantages, legal):
+    """`_sample_action_from_advantage` (deep_cfr.py:499-525) for a batch: positive parts of the advantages over the
+    legal actions, normalised; when none is positive, probability one on the legal action with the largest raw
+    advantage (the first such action, as Python's `max` over the ascending legal list returns)."""
+    pos = advantages.clamp_min(0.0) * legal
+    total = pos.sum(-1, keepdim=True)
+    best = torch.where(legal, advantages, torch.full_like(advantages, -math.inf)).argmax(-1)
+    fallback = torch.zeros_like(pos).scatter_(-1, best.view(-1, 1), 1.0)
+    return torch.where(total > 0, pos / total.clamp_min(1e-38), fallback)
+
+
+class MLP(nn.Module):
+    """`simple_nets.MLP` (simple_nets.py:84-120): Linear+ReLU hidden layers, linear head, weights drawn from a
+    normal truncated at two standard deviations with stddev 1/sqrt(fan_in), zero biases (simple_nets.py:44-52)."""
+
+    def __init__(self, input_size, hidden_sizes, output_size):
+        super().__init__()
+        layers, prev = [], input_size
+        for h in hidden_sizes:
+            layers += [nn.Linear(prev, h), nn.ReLU()]
+            prev = h
+        layers.append(nn.Linear(prev, output_size))
+        self.net = nn.Sequential(*layers)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        for m in self.net:
+            if isinstance(m, nn.Linear):
+                std = 1.0 / math.sqrt(m.in_features)
+                nn.init.trunc_normal_(m.weight, mean=0.0, std=std, a=-2 * std, b=2 * std)
+                nn.init.zeros_(m.bias)
+
+    def forward(self, x):
+        return self.net(x)
+
+
+class ReservoirBuffer:
+    """`deep_cfr.ReservoirBuffer` (deep_cfr.py:43-99) on the device and batched: element number t (0-based count
+    of everything ever added) fills slot t while t < capacity and afterwards replaces slot randint(0, t) when that
+    is < capacity; inside one batch the later element wins a slot, as it would sequentially. Info-state rows are
+    kept as uint8 (every value of the tensor is an integer in 0..12, coup.cc:150-287): 2.5 KB per record."""
+
+    def __init__(self, capacity, device, fields, seed=0):
+        self.capacity = int(capacity)
+        self.device = torch.device(device)
+        self._fields = dict(fields)
+        self._data = {}          # allocated on first add, grown geometrically up to `capacity`
+        self._allocated = 0
+        self.add_calls = 0
+        self.size = 0
+        self._gen = torch.Generator(device=self.device)
+        self._gen.manual_seed(seed)
+
+    def _ensure(self, rows):
+        if rows <= self._allocated:
+            return
+        new = min(self.capacity, max(rows, 2 * self._allocated, 1024))
+        for name, (shape, dtype) in self._fields.items():
+            buf = torch.zeros((new, *shape), dtype=dtype, device=self.device)
+            if self._allocated:
+                buf[: self._allocated] = self._data[name]
+            self._data[name] = buf
+        self._allocated = new
+
+    def add(self, **columns):
+        b = int(next(iter(columns.values())).shape[0])
+        if b == 0:
+            return
+        self._ensure(min(self.capacity, self.add_calls + b))
+        if self.add_calls + b <= self.capacity:        # still filling: element t goes to slot t
+            for name, (_, dtype) in self._fields.items():
+                self._data[name][self.add_calls: self.add_calls + b] = columns[name].to(dtype)
+            self.add_calls += b
+            self.size = self.add_calls
+            return
+        t = self.add_calls + torch.arange(b, device=self.device)
+        draw = (torch.rand(b, device=self.device, generator=self._gen, dtype=torch.float64) * (t + 1).double()).long()
+        slot = torch.where(t < self.capacity, t, draw)
+        keep = slot < self.capacity
+        slot, src = slot[keep], torch.arange(b, device=self.device)[keep]
+        winner = torch.full((self.capacity,), -1, dtype=torch.long, device=self.device)
+        winner.scatter_reduce_(0, slot, torch.arange(src.numel(), device=self.device), reduce="amax", include_self=True)
+        chosen = winner[winner >= 0]
+        dst, src = slot[chosen], src[chosen]
+        for name, (_, dtype) in self._fields.items():
+            self._data[name][dst] = columns[name][src].to(dtype)
+        self.add_calls += b
+        self.size = min(self.capacity, self.add_calls)
+
+    def sample(self, num_samples):
+        """`ReservoirBuffer.sample` (deep_cfr.py:78-92): `num_samples` distinct records, uniformly."""
+        if num_samples > self.size:
+            raise ValueError("{} elements could not be sampled from size {}".format(num_samples, self.size))
+        j = torch.randperm(self.size, device=self.device, generator=self._gen)[:num_samples]
+        return {name: buf[j] for name, buf in self._data.items()}
+
+    def all(self):
+        return {name: buf[: self.size] for name, buf in self._data.items()}
+
+    def clear(self):
+        self.add_calls = 0
+        self.size = 0
+
+    def __len__(self):
+        return self.size
+
+
+_ADV_FIELDS = {"info_state": ((INFO_STATE_SIZE,), torch.uint8), "iteration": ((), torch.int32),
+               "advantage": ((NUM_DISTINCT_ACTIONS,), torch.float32), "action": ((), torch.uint8)}
+_STRAT_FIELDS = {"info_state": ((INFO_STATE_SIZE,), torch.uint8), "iteration": ((), torch.int32),
+                 "strategy_action_probs": ((NUM_DISTINCT_ACTIONS,), torch.float32)}
+
+
+class DeepCFRSolver:
+    """`deep_cfr.DeepCFRSolver` (deep_cfr.py:102-640) for game "coup". Arguments as in the reference (:118-188);
+    additions: `device`, `seed`, `max_nodes` (size of each of the two scratch env slabs; a level with more nodes is
+    expanded in slab-sized pieces, so the width of a tree is limited by HBM at ~200 B per node, not by the slabs),
+    `roots_per_batch` (how many of the `num_traversals` roots are expanded together), `max_tree_nodes` (a batch whose
+    trees grow past this many nodes raises instead of exhausting memory) and `record_tree` (keep the
+    per-level bookkeeping of the last batch in `last_tree` for inspection and tests)."""
+
+    def __init__(self, game=None, policy_network_layers=(256, 256), advantage_network_layers=(128, 128),
+                 num_iterations=100, num_traversals=20, learning_rate=1e-4, batch_size_advantage=None,
+                 batch_size_strategy=None, memory_capacity=int(1e6), policy_network_train_steps=1,
+                 advantage_network_train_steps=1, reinitialize_advantage_networks=True, sampling_method="external",
+                 outcome_samp_expl=0.6, outcome_factor=1, e_outcome=0, iter_net_train=False, adv_net_reinit_every=1,
+                 eval_func=None, eval_every=10, eval_train_episodes=10000, eval_test_every=5000,
+                 eval_test_episodes=1000, use_checkpoints=False, checkpoint_dir=None, save_every=None,
+                 device=0, seed=0, max_nodes=1 << 18, roots_per_batch=None, max_tree_nodes=1 << 26, record_tree=False):
+        if sampling_method not in ("external", "outcome", "e-outcome"):
+            raise ValueError(f"Unknown sampling method '{sampling_method}'.")           # deep_cfr.py:229-230
+        if outcome_factor <= 0:
+            raise ValueError("Outcome factor must be greater than 0.")                 # deep_cfr.py:233-234
+        self._game = game
+        self.device = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
+        self._num_players = 2
+        self._num_actions = NUM_DISTINCT_ACTIONS
+        self._embedding_size = INFO_STATE_SIZE
+        self._batch_size_advantage = batch_size_advantage
+        self._batch_size_strategy = batch_size_strategy
+        self._policy_network_train_steps = policy_network_train_steps
+        self._advantage_network_train_steps = advantage_network_train_steps
+        self._num_iterations = num_iterations
+        self._num_traversals = num_traversals
+        self._reinitialize_advantage_networks = reinitialize_advantage_networks
+        self._iteration = 1
+        self._environment_steps = 0
+        self._sampling_method = sampling_method
+        self._expl = outcome_samp_expl
+        self._outcome_factor = outcome_factor
+        self._e_outcome = e_outcome
+        self._iter_net_train = iter_net_train
+        self._adv_net_reinit_every = adv_net_reinit_every
+        self._eval_func = eval_func
+        self._eval_every = eval_every
+        self._eval_train_episodes = eval_train_episodes
+        self._eval_test_every = eval_test_every
+        self._eval_test_episodes = eval_test_episodes
+        self._use_checkpoints = use_checkpoints
+        self._checkpoint_dir = checkpoint_dir
+        self._save_every = save_every
+        self._record_tree = record_tree
+        self.last_tree = None
+
+        torch.manual_seed(seed)
+        self._gen = torch.Generator(device=self.device)
+        self._gen.manual_seed(seed)
+        self._policy_network = MLP(self._embedding_size, list(policy_network_layers), self._num_actions).to(self.device)
+        self._optimizer_policy = torch.optim.Adam(self._policy_network.parameters(), lr=learning_rate)
+        self._strategy_memories = ReservoirBuffer(memory_capacity, self.device, _STRAT_FIELDS, seed=seed + 1)
+        self._advantage_memories = [ReservoirBuffer(memory_capacity, self.device, _ADV_FIELDS, seed=seed + 2 + p)
+                                    for p in range(self._num_players)]
+        self._advantage_networks = [MLP(self._embedding_size, list(advantage_network_layers), self._num_actions).to(self.device)
+                                    for _ in range(self._num_players)]
+        # one optimiser per network for the whole run: re-initialising a network keeps its Adam moments, as
+        # re-running only the variable initialisers does in the reference (deep_cfr.py:343-349)
+        self._optimizer_advantages = [torch.optim.Adam(net.parameters(), lr=learning_rate) for net in self._advantage_networks]
+
+        self._max_nodes = max(int(max_nodes), 7)
+        self._max_tree_nodes = int(max_tree_nodes)
+        self._roots_per_batch = int(roots_per_batch or min(num_traversals, self._max_nodes))
+        dev_index = self.device.index or 0
+        self._slabs = [CoupVectorEnv(self._max_nodes, seed=seed + 101 + i, device=dev_index, auto_reset=False)
+                       for i in range(2)]
+        self._arange = torch.arange(self._max_nodes, device=self.device)
+
+    # ---- the reference's accessors -------------------------------------------------------------------
+    @property
+    def advantage_buffers(self):
+        return self._advantage_memories
+
+    @property
+    def strategy_buffer(self):
+        return self._strategy_memories
+
+    @property
+    def policy_network(self):
+        return self._policy_network
+
+    @property
+    def advantage_networks(self):
+        return self._advantage_networks
+
+    @property
+    def iteration(self):
+        return self._iteration
+
+    def clear_advantage_buffers(self):
+        for m in self._advantage_memories:
+            m.clear()
+
+    def reinitialize_advantage_networks(self):
+        for p in range(self._num_players):
+            self.reinitialize_advantage_network(p)
+
+    def reinitialize_advantage_network(self, player):
+        self._advantage_networks[player].reset_parameters()
+
+    def _reinitialize_policy_network(self):
+        self._policy_network.reset_parameters()
+
+    def get_environment_steps(self):
+        return self._environment_steps
+
+    def save_policy_network(self, checkpoint_dir, checkpoint_id):
+        os.makedirs(checkpoint_dir, exist_ok=True)
+        path = os.path.join(checkpoint_dir, "policy_network" + checkpoint_id + ".pt")
+        torch.save(self._policy_network.state_dict(), path)
+        return path
+
+    def has_checkpoint(self, checkpoint_dir, checkpoint_id):
+        return os.path.exists(os.path.join(checkpoint_dir, "policy_network" + checkpoint_id + ".pt"))
+
+    def restore_policy_network(self, checkpoint_dir, checkpoint_id):
+        path = os.path.join(checkpoint_dir, "policy_network" + checkpoint_id + ".pt")
+        self._policy_network.load_state_dict(torch.load(path, map_location=self.device))
+
+    # ---- solve (deep_cfr.py:360-410) -----------------------------------------------------------------
+    def solve(self):
+        advantage_losses = collections.defaultdict(list)
+        policy_loss = None
+        for _ in range(self._num_iterations):
+            for p in range(self._num_players):
+                self.traverse(p, self._num_traversals)
+                if self._reinitialize_advantage_networks and self._iteration % self._adv_net_reinit_every == 0:
+                    self.reinitialize_advantage_network(p)
+                advantage_losses[p].append(self._learn_advantage_network(p))
+            if self._iter_net_train:
+                policy_loss = self._learn_strategy_network()
+            if (self._eval_func is not None and self._iteration % self._eval_every == 0
+                    and self._iteration != self._num_iterations):
+                if not self._iter_net_train:
+                    policy_loss = self._learn_strategy_network()
+                self._eval_func(exploitee=self, num_train_episodes=self._eval_train_episodes,
+                                eval_every=self._eval_test_every, eval_episodes=self._eval_test_episodes)
+                if self._use_checkpoints and self._save_every and self._iteration % self._save_every == 0:
+                    self.save_policy_network(self._checkpoint_dir, f"iter{self._iteration}")
+                if not self._iter_net_train:
+                    self._reinitialize_policy_network()
+            self._iteration += 1
+        policy_loss = self._learn_strategy_network()
+        if self._eval_func is not None:
+            self._eval_func(exploitee=self, num_train_episodes=self._eval_train_episodes,
+                            eval_every=self._eval_test_every, eval_episodes=self._eval_test_episodes)
+        if self._use_checkpoints:
+            self.save_policy_network(self._checkpoint_dir, f"iter{self._iteration - 1}")
+        return self._policy_network, advantage_losses, policy_loss
+
+    # ---- traversal -----------------------------------------------------------------------------------
+    def traverse(self, player, num_traversals):
+        """`num_traversals` calls of `_traverse_game_tree(root, player)` (deep_cfr.py:363-365). Returns the mean
+        root value (the reference discards it) and the number of nodes expanded."""
+        done, total_value, total_nodes = 0, 0.0, 0
+        while done < num_traversals:
+            r = min(self._roots_per_batch, num_traversals - done)
+            values, nodes = self._traverse_batch(player, r)
+            total_value += float(values.sum())
+            total_nodes += nodes
+            done += r
+        return total_value / max(num_traversals, 1), total_nodes
+
+    @torch.no_grad()
+    def _advantages(self, rows_u8, cur_player):
+        x = rows_u8.float()
+        out = torch.empty((x.shape[0], self._num_actions), dtype=torch.float32, device=self.device)
+        for p in range(self._num_players):
+            idx = (cur_player == p).nonzero(as_tuple=True)[0]
+            if idx.numel():
+                out[idx] = self._advantage_networks[p](x[idx])
+        return out
+
+    def _load(self, slab, state, history):
+        k = state.shape[0]
+        slab.state[:k] = state
+        slab.history[:k] = history
+        return k
+
+    def _encode_saved(self, state, history):
+        """Info-state rows (uint8, player to move) of packed states kept since the forward pass."""
+        slab = self._slabs[0]
+        out = torch.empty((state.shape[0], INFO_STATE_SIZE), dtype=torch.uint8, device=self.device)
+        for a in range(0, state.shape[0], self._max_nodes):
+            k = self._load(slab, state[a: a + self._max_nodes], history[a: a + self._max_nodes])
+            slab.information_state_tensor_gather(self._arange[:k], player=PLAYER_CURRENT, out=out[a: a + k])
+        return out
+
+    def _children_of_traverser(self, strategy, legal):
+        """bool [m, 18]: which actions of each traverser node are expanded (deep_cfr.py:438-466)."""
+        if self._sampling_method == "external":
+            return legal
+        m = legal.shape[0]
+        n_legal = legal.sum(-1)
+        if self._sampling_method == "e-outcome":
+            multi = torch.rand(m, device=self.device, generator=self._gen) < self._e_outcome
+            factor = torch.where(multi, self._outcome_factor, 1)
+        else:
+            factor = torch.full((m,), self._outcome_factor, device=self.device)
+        num_to_sample = torch.minimum(n_legal, factor)
+        uniform = legal / n_legal.clamp_min(1).view(-1, 1)
+        probs = self._expl * uniform + (1.0 - self._expl) * strategy
+        probs = probs / probs.sum(-1, keepdim=True)
+        # np.random.choice(size=k, replace=False, p=probs) draws sequentially without replacement, which is the
+        # Plackett-Luce order of the Gumbel-perturbed log-probabilities: take the k largest keys
+        u = torch.rand(probs.shape, device=self.device, generator=self._gen, dtype=torch.float64).clamp_min(1e-300)
+        keys = torch.where(legal & (probs > 0), probs.double().log() - (-u.log()).log(), torch.full_like(u, -math.inf))
+        rank = keys.argsort(-1, descending=True).argsort(-1)
+        return legal & (rank < num_to_sample.view(-1, 1))
+
+    def _expand_chunk(self, player, state, history, word):
+        """One slab-full of non-terminal nodes of a level: strategies, which children to expand, and the children
+        themselves (packed state, history, step word), in parent order."""
+        src, dst = self._slabs
+        k = self._load(src, state, history)
+        legal = _legal_bool(word & 0x3FFFF)
+        cp = (word >> 18) & 1
+        rows = src.information_state_tensor_gather(self._arange[:k], player=PLAYER_CURRENT, dtype=torch.uint8)
+        strategy = regret_matching(self._advantages(rows, cp), legal)
+        is_trav = cp == player
+        # opponent nodes: one action from the matched regrets, renormalised (:482-492), and a StrategyMemory record
+        probs = strategy / strategy.sum(-1, keepdim=True)
+        sampled = torch.multinomial(probs, 1, generator=self._gen).view(-1)
+        opp = (~is_trav).nonzero(as_tuple=True)[0]
+        if opp.numel():
+            self._strategy_memories.add(info_state=rows[opp], strategy_action_probs=strategy[opp],
+                                        iteration=torch.full((opp.numel(),), self._iteration, device=self.device))
+        expand = torch.zeros_like(legal).scatter_(1, sampled.view(-1, 1), True)
+        trav = is_trav.nonzero(as_tuple=True)[0]
+        if trav.numel():
+            expand[trav] = self._children_of_traverser(strategy[trav], legal[trav])
+        local, action = expand.nonzero(as_tuple=True)              # row-major: children grouped by parent
+        c = dst.fork_from(src, local, action.to(torch.uint8))
+        # the reference's record keeps the loop variable `action` of its last `for`, i.e. the largest legal id (:479)
+        last_legal = (NUM_DISTINCT_ACTIONS - 1) - legal.flip(-1).to(torch.int32).argmax(-1)
+        info = {"local": local, "action": action, "strategy": strategy, "legal": legal, "is_trav": is_trav,
+                "last_legal": last_legal}
+        return info, dst.state[:c].clone(), dst.history[:c].clone(), dst.step_word[:c].clone()
+
+    @torch.no_grad()
+    def _traverse_batch(self, player, num_roots, roots=None):
+        """One batch of traversals for `player`. `roots`: None for `num_roots` freshly dealt games (the reference's
+        `_root_node` followed by its four chance nodes), or the (state, history, step_word) tensors of a
+        CoupVectorEnv to start from arbitrary decision nodes."""
+        stats_before = [int(s.stats_device[1]) for s in self._slabs]
+        if roots is None:
+            if num_roots > self._max_nodes:
+                raise ValueError("roots_per_batch exceeds max_nodes")
+            root = self._slabs[0]
+            root.reset(envs_to_reset=(self._arange < num_roots).to(torch.uint8))     # root + its 4 deals (:430-434)
+            roots = root.state[:num_roots], root.history[:num_roots], root.step_word[:num_roots]
+        state, history, word = (t.clone() for t in roots)
+        levels = []
+        sign = 1.0 if player == 0 else -1.0
+        chunk = self._max_nodes // 7            # a node has at most 7 legal actions (coup.cc:838-872), so the children fit
+        total = 0
+        while state.shape[0] > 0:
+            m = state.shape[0]
+            total += m
+            if total > self._max_tree_nodes:
+                # multi-outcome and external sampling grow exponentially with the length of a Coup game (5-7 actions
+                # per turn, up to 91 moves): stop before the bookkeeping (~200 B per node) exhausts HBM
+                raise RuntimeError(f"traversal batch grew past max_tree_nodes={self._max_tree_nodes} at level "
+                                   f"{len(levels)} ({m} nodes wide): use fewer roots per batch or a smaller outcome_factor")
+            terminal = ((word >> 19) & 1).bool()
+            ret_p = sign * (((word >> 24) & 7) - 2).double()
+            nt = (~terminal).nonzero(as_tuple=True)[0]
+            lvl = {"m": m, "terminal": terminal, "ret_p": ret_p, "nt": nt, "children": 0}
+            if self._record_tree:
+                lvl.update(history=history, moves=(state[:, 3] & 127).to(torch.int64), word=word)
+            levels.append(lvl)
+            if nt.numel() == 0:
+                break
+            infos, kids, offset = [], [], 0
+            for a in range(0, nt.numel(), chunk):
+                idx = nt[a: a + chunk]
+                info, cs, ch, cw = self._expand_chunk(player, state[idx], history[idx], word[idx])
+                info["local"] = info["local"] + a
+                infos.append(info)
+                kids.append((cs, ch, cw))
+            lvl.update({k: torch.cat([i[k] for i in infos]) for k in infos[0]})
+            trav = lvl["is_trav"].nonzero(as_tuple=True)[0]
+            # traverser nodes wait for their regrets until the backward sweep: keep the packed state + history (80 B)
+            # rather than the 2.5 KB row and encode again then
+            lvl.update(trav=trav, trav_state=state[nt[trav]], trav_history=history[nt[trav]],
+                       children=int(lvl["local"].numel()))
+            state, history, word = (torch.cat([k[i] for k in kids]) for i in range(3))
+        # ---- backward sweep (:468-480) ----
+        child_values = None
+        for lvl in reversed(levels):
+            value = torch.where(lvl["terminal"], lvl["ret_p"], torch.zeros_like(lvl["ret_p"]))
+            if lvl["children"]:
+                payoff = torch.zeros(lvl["legal"].shape, dtype=torch.float64, device=self.device)
+                payoff[lvl["local"], lvl["action"]] = child_values
+                cfv = (lvl["strategy"].double() * payoff * lvl["legal"]).sum(-1)
+                value[lvl["nt"]] = torch.where(lvl["is_trav"], cfv, payoff.sum(-1))
+                trav = lvl["trav"]
+                if trav.numel():
+                    regret = ((payoff[trav] - cfv[trav].view(-1, 1)) * lvl["legal"][trav]).float()
+                    rows = self._encode_saved(lvl["trav_state"], lvl["trav_history"])
+                    self._advantage_memories[player].add(
+                        info_state=rows, advantage=regret, action=lvl["last_legal"][trav],
+                        iteration=torch.full((trav.numel(),), self._iteration, device=self.device))
+                    if self._record_tree:
+                        lvl["regret"] = regret
+                        if trav.numel() <= 4096:
+                            lvl["rows"] = rows
+            lvl["value"] = value
+            child_values = value
+        nodes = sum(l["m"] for l in levels)
+        chance = sum(int(s.stats_device[1]) - b for s, b in zip(self._slabs, stats_before))
+        self._environment_steps += nodes + chance        # every recursive call, chance nodes included (:427)
+        self.last_level_widths = [l["m"] for l in levels]
+        if self._record_tree:
+            self.last_tree = levels
+        return levels[0]["value"], nodes
+
+    # ---- learning (deep_cfr.py:549-616) -----------------------------------------------------------------
+    def _learn_advantage_network(self, player):
+        memory, net, opt = self._advantage_memories[player], self._advantage_networks[player], self._optimizer_advantages[player]
+        loss = None
+        for _ in range(self._advantage_network_train_steps):
+            if self._batch_size_advantage:
+                if self._batch_size_advantage > len(memory):
+                    return None                                                     # not enough samples (:562-564)
+                batch = memory.sample(self._batch_size_advantage)
+            else:
+                batch = memory.all()
+            if batch["info_state"].shape[0] == 0:
+                return None
+            w = batch["iteration"].float().sqrt().view(-1, 1)
+            pred = net(batch["info_state"].float())
+            loss = torch.mean((w * batch["advantage"] - w * pred) ** 2)
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            opt.step()
+        return None if loss is None else float(loss.detach())
+
+    def _learn_strategy_network(self):
+        memory = self._strategy_memories
+        loss = None
+        for _ in range(self._policy_network_train_steps):
+            if self._batch_size_strategy:
+                if self._batch_size_strategy > len(memory):
+                    return None
+                batch = memory.sample(self._batch_size_strategy)
+            else:
+                batch = memory.all()
+            if batch["info_state"].shape[0] == 0:
+                return None
+            w = batch["iteration"].float().sqrt().view(-1, 1)
+            probs = torch.softmax(self._policy_network(batch["info_state"].float()), dim=-1)
+            loss = torch.mean((w * batch["strategy_action_probs"] - w * probs) ** 2)
+            self._optimizer_policy.zero_grad(set_to_none=True)
+            loss.backward()
+            self._optimizer_policy.step()
+        return None if loss is None else float(loss.detach())
+
+    # ---- acting (deep_cfr.py:527-547) -------------------------------------------------------------------
+    @torch.no_grad()
+    def action_probs(self, info_state, legal_bits):
+        """Batched `action_probabilities`: softmax of the policy network, illegal actions removed, renormalised."""
+        probs = torch.softmax(self._policy_network(info_state.float()), dim=-1) * _legal_bool(legal_bits)
+        return probs / probs.sum(-1, keepdim=True)
+
+    def action_probabilities(self, state, player_id=None):
+        """Single-state form for a `spiel.CoupState`: {action: probability} over the legal actions."""
+        cur_player = state.current_player()
+        legal_actions = state.legal_actions(cur_player)
+        info = torch.tensor(state.information_state_tensor(), dtype=torch.float32, device=self.device).view(1, -1)
+        bits = torch.tensor([sum(1 << a for a in legal_actions)], dtype=torch.int32, device=self.device)
+        probs = self.action_probs(info, bits)[0].tolist()
+        return {a: probs[a] for a in legal_actions}

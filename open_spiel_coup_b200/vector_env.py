@@ -124,6 +124,18 @@ class CoupVectorEnv:
         f = self._u8(forced_chance, (self.num_envs, 4), "forced_chance")
         check(self._lib.coup_vec_step(self._h, self._ptr(a), self._ptr(f), _stream_ptr(self.device)))
 
+    def fork_from(self, src, parents, actions, forced_chance=None):
+        """Batched `state.child(action)` (deep_cfr.py:415-497): env i of THIS handle becomes a copy of env
+        parents[i] of `src` with actions[i] applied and the following chance nodes resolved, never auto-reset.
+        Envs >= len(parents) keep their contents. Returns the number of children."""
+        parents = parents.to(device=self.device, dtype=torch.int32).contiguous()
+        count = int(parents.numel())
+        a = self._u8(actions, (count,), "actions")
+        f = self._u8(forced_chance, (count, 4), "forced_chance")
+        check(self._lib.coup_vec_fork(self._h, src._h, self._ptr(parents) if count else None,
+                                      self._ptr(a) if count else None, self._ptr(f), count, _stream_ptr(self.device)))
+        return count
+
     def sample_uniform(self, out=None):
         if out is None:
             out = torch.empty(self.num_envs, dtype=torch.uint8, device=self.device)
