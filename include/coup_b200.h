@@ -152,7 +152,7 @@ int coup_vec_new_initial_state(coup_vec_env* env, const uint8_t* d_mask, void* s
 int coup_vec_apply_move(coup_vec_env* env, const uint8_t* d_moves, void* stream);
 int coup_vec_copy_env(coup_vec_env* env, uint32_t src, uint32_t dst, void* stream);
 
-/* Batched `state.child(action)` (spiel.h:365-370 Clone + ApplyAction), the tree-expansion step of the sampled
+/* Batched `state.child(action)` (spiel.h:565-570 Clone + ApplyAction), the tree-expansion step of the sampled
  * CFR traversals (python/algorithms/deep_cfr.py:415-497; every recursive call there is one child). For
  * i < count: env i of `dst` becomes a copy of env d_parent[i] of `src` (state + history) with player action
  * d_actions[i] applied and every following chance node resolved, exactly like coup_vec_step but NEVER

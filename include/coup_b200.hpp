@@ -53,6 +53,11 @@ class VectorEnv {
   void Step(const uint8_t* d_actions, const uint8_t* d_forced_chance = nullptr, void* stream = nullptr) {
     Check(coup_vec_step(env_, d_actions, d_forced_chance, stream));
   }
+  // state.child(action) for `count` (parent, action) pairs: children land in slots 0..count-1 of THIS slab
+  void ForkFrom(const VectorEnv& src, const uint32_t* d_parent, const uint8_t* d_actions, uint32_t count,
+                const uint8_t* d_forced_chance = nullptr, void* stream = nullptr) {
+    Check(coup_vec_fork(env_, src.env_, d_parent, d_actions, d_forced_chance, count, stream));
+  }
   void SampleUniform(uint8_t* d_actions_out, void* stream = nullptr) { Check(coup_vec_sample_uniform(env_, d_actions_out, stream)); }
   void SamplePolicy(const void* d_logits, int dtype, float* d_probs_out, uint8_t* d_actions_out, void* stream = nullptr) {
     Check(coup_vec_sample_policy(env_, d_logits, dtype, d_probs_out, d_actions_out, stream));
