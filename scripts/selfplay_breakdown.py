@@ -26,3 +26,20 @@ print("sample_policy             %.3f ms" % timeit(lambda: env.sample_policy(log
 print("copies (player, legal)    %.3f ms" % timeit(lambda: (gen.acting_player.copy_(env.current_player), gen.legal_before.copy_(env.legal_mask))))
 env.sample_policy(logits, actions_out=gen.actions)
 print("whole step                %.3f ms" % timeit(gen.step))
+
+# dense vs move-number-bucketed first layer (selfplay.bucketed_policy_forward), same envs
+from open_spiel_coup_b200.selfplay import bucketed_policy_forward, _BUCKET_MOVES
+gen.run(30)                                   # states reached under the policy itself
+moves = env.move_numbers()
+print("move numbers under policy play: mean %.1f, bucket counts %s" % (
+    float(moves.float().mean()), torch.bincount(torch.bucketize(moves, torch.tensor(_BUCKET_MOVES[:-1], device=moves.device)), minlength=9).tolist()))
+print("bucketed forward (sort+encode+9 GEMMs+rest+unsort) %.3f ms" % timeit(lambda: bucketed_policy_forward(env, gen.policy, gen.info_state)))
+def dense():
+    env.information_state_tensor(_lib.PLAYER_CURRENT, out=gen.info_state)
+    with torch.no_grad():
+        return gen.policy(gen.info_state)
+print("dense forward (encode+policy)                      %.3f ms" % timeit(dense))
+gen.bucketed_first_layer = True
+print("whole step, bucketed      %.3f ms" % timeit(gen.step))
+gen.bucketed_first_layer = False
+print("whole step, dense         %.3f ms" % timeit(gen.step))

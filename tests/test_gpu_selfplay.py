@@ -151,3 +151,35 @@ def test_replay_recorder_matches_reference_bookkeeping(oracle):
                      rb.is_final_step[:rb.total].cpu().tolist(), rb.legal_actions_mask[:rb.total].cpu().tolist()))
     assert got == sorted(expected)
     assert sum(len(g) for g in games) > 0 and rb.is_final_step[:rb.total].sum() > 0
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-4), (torch.bfloat16, 6e-2)])
+def test_bucketed_first_layer_equals_dense_forward(dtype, tol):
+    """The K-truncated first layer (selfplay.bucketed_policy_forward) drops only exact zeros: its logits equal the
+    dense forward of a plain PyTorch fp32 reference up to summation order (tolerance 2e-4 in fp32; bf16 inputs and
+    weights are compared with the bf16 dense forward at 6e-2 on logits of magnitude ~1)."""
+    from open_spiel_coup_b200.selfplay import PADDED_INFO_STATE_SIZE, _BUCKET_K, _BUCKET_MOVES, bucketed_policy_forward
+    n = 20000
+    env = CoupVectorEnv(n, seed=77, auto_reset=True)
+    torch.manual_seed(0)
+    policy = MLPPolicy(hidden_sizes=(256, 128), padded_input_size=PADDED_INFO_STATE_SIZE).to("cuda", dtype).eval()
+    buf = torch.zeros((n, PADDED_INFO_STATE_SIZE), dtype=dtype, device="cuda")
+    dense_in = torch.zeros_like(buf)
+    for steps in (0, 3, 40):                       # fresh deals, early game, desynchronised mid-games
+        env.rollout(steps)
+        logits, perm, rows = bucketed_policy_forward(env, policy, buf)
+        env.information_state_tensor(_lib.PLAYER_CURRENT, out=dense_in)
+        assert torch.equal(rows, dense_in[perm])                                   # rows are the env rows, permuted
+        assert torch.equal(torch.sort(perm).values, torch.arange(n, device="cuda"))
+        moves = env.move_numbers()[perm]
+        assert bool((torch.bucketize(moves, torch.tensor(_BUCKET_MOVES[:-1], device="cuda")).diff() >= 0).all())
+        with torch.no_grad():
+            ref = policy.float()(dense_in.float()) if dtype == torch.float32 else policy(dense_in).float()
+        assert float((logits.float() - ref).abs().max()) < tol
+        policy.to(dtype)
+    # every bucket's K covers its move numbers
+    assert all(k >= min(PADDED_INFO_STATE_SIZE, 62 + 18 * m) for k, m in zip(_BUCKET_K, _BUCKET_MOVES))
+    # nothing non-zero beyond 62 + 18 * move_number (the property the truncation relies on)
+    cols = torch.arange(PADDED_INFO_STATE_SIZE, device="cuda").view(1, -1)
+    beyond = cols >= (62 + 18 * env.move_numbers()).view(-1, 1)
+    assert float(dense_in.float()[beyond].abs().sum()) == 0.0
