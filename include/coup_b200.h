@@ -134,7 +134,8 @@ int coup_vec_reset(coup_vec_env* env, const uint8_t* d_reset_mask, const uint8_t
  * every following chance node resolved as rl_environment._sample_external_events does,
  * rl_environment.py:369-382). d_actions: uint8[num_envs] action ids on the device. d_forced_chance:
  * uint8[num_envs][4] outcomes for the chance nodes that follow (0xFF = sample), or NULL.
- * Envs that are already terminal ignore their action (rl_environment.py:301-302). After the call the
+ * Envs that are already terminal ignore their action (rl_environment.py:301-302); the action id 0xFF makes an
+ * env sit the step out (state and outputs untouched), for callers that advance only part of a slab. After the call the
  * per-env outputs below describe the new state. Returns COUP_ERR_ILLEGAL_ACTION only from
  * coup_vec_check_errors (the launch itself is asynchronous). */
 int coup_vec_step(coup_vec_env* env, const uint8_t* d_actions, const uint8_t* d_forced_chance,

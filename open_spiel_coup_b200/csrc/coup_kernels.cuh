@@ -251,7 +251,7 @@ k_step(EnvArrays A, const uint8_t* __restrict__ actions, const uint8_t* __restri
   BlockStats st;
   st.init(s_stats);
   const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool active = e < A.n;
+  const bool active = e < A.n && actions[e] != 0xFFu;   // 0xFF: this env sits the step out, outputs keep their values
   StepResult r = {};
   if (active) {
     Env s = load_env(A.state + e);
