@@ -641,15 +641,18 @@ __device__ __forceinline__ void poke_row(T* row, const uint32_t* rec, int view, 
   }
 }
 
-// Erases a row again: every non-zero lives in the first 62 + 18*len elements, so instead of recomputing the
-// poked positions the warp zero-fills that prefix with four-element stores (2 store instructions for len ~ 10).
+// Erases a row again: every non-zero lives in the first 62 + 18*len elements, so instead of recomputing the poked
+// positions the warp zero-fills that prefix, widened to 16-byte boundaries, with uint4 stores (one or two store
+// instructions per row for any element type). The widening can only touch the zero tail of the previous row of the
+// same staging buffer or later elements of this row, all of which are zero once the group has been erased.
 template <typename T>
 __device__ __forceinline__ void clear_row(T* row, const uint32_t* rec, int lane) {
-  using U = typename Unit4<T>::type;
-  const int units = min(kUnitsPerInfoRow, static_cast<int>((62u + 18u * (rec[20] & 255u) + 3u) >> 2));
-  const U zero = Unit4<T>::make(0, 0, 0, 0);
-  U* r4 = reinterpret_cast<U*>(row);
-  for (int q = lane; q < units; q += 32) r4[q] = zero;
+  const uint32_t saddr = static_cast<uint32_t>(__cvta_generic_to_shared(row));
+  const uint32_t lo = saddr & ~15u;
+  const uint32_t hi = (saddr + (62u + 18u * (rec[20] & 255u)) * static_cast<uint32_t>(sizeof(T)) + 15u) & ~15u;
+  uint4* p = reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(row) - (saddr - lo));
+  const int units = static_cast<int>((hi - lo) >> 4);
+  for (int q = lane; q < units; q += 32) p[q] = make_uint4(0u, 0u, 0u, 0u);
 }
 
 // Full block (8 warps x 32 records): the block's rows form one contiguous span of the output, written in groups
