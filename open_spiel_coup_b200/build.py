@@ -41,7 +41,8 @@ def build(force=False, verbose=False):
         if res.returncode != 0:
             raise RuntimeError("host compile failed:\n" + " ".join(cc) + "\n" + res.stdout + res.stderr)
         objs.append(obj)
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES] + objs
+    extra = os.environ.get("COUP_B200_NVCC_EXTRA", "").split()      # e.g. -DCOUP_WS_DEBUG for the cycle counters
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES] + objs
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)

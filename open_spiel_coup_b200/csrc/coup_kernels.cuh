@@ -873,12 +873,17 @@ k_rollout_tma(EnvArrays A, uint64_t step, int player_sel, T* __restrict__ out, u
 // while warps 8..23 ENCODE batch i with bulk stores (one staging buffer each, row groups dealt round-robin).
 // The two roles hand batches over through named barriers (full/empty per buffer), so the bulk-store stream never
 // pauses for a rules phase -- in k_rollout_tma every warp of a CTA stops storing while it steps its envs.
+// The record area is double-buffered (kWsBufs). In-kernel cycle counters (-DCOUP_WS_DEBUG, scripts/ws_debug_probe.py)
+// show neither role ever waiting for the other: next to the saturated store stream the rules warps' loads queue
+// behind it, a rules phase stretches to one batch time (15 / 28 / 54 us for u8 / bf16 / f32) and finishes as the
+// encoders do; a third record buffer changed nothing (1.538 / 0.806 / 0.430 ms per step either way).
 constexpr int kWsWarps = 24, kWsRulesWarps = 8, kWsEncWarps = kWsWarps - kWsRulesWarps;
 constexpr int kWsThreads = kWsWarps * 32;
 constexpr int kWsBatch = kTmaWarpsPerBlock * 32;                       // 256 envs
 constexpr int kWsRecBytes = kWsBatch * kRecWords * 4;                  // 21 504 B per record buffer
-constexpr int kWsSmemBytes = kWsEncWarps * kStageBytes + 2 * kWsRecBytes + COUP_STATS_LEN * 4;
-enum { kBarFull0 = 1, kBarFull1 = 2, kBarEmpty0 = 3, kBarEmpty1 = 4, kBarRules = 5 };
+constexpr int kWsBufs = 2;
+constexpr int kWsSmemBytes = kWsEncWarps * kStageBytes + kWsBufs * kWsRecBytes + COUP_STATS_LEN * 4;
+enum { kBarFull0 = 1, kBarEmpty0 = kBarFull0 + kWsBufs, kBarRules = kBarEmpty0 + kWsBufs };   // named barriers 1..5
 
 __device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
@@ -888,23 +893,38 @@ __global__ void __launch_bounds__(kWsThreads, 1)
 k_rollout_ws(EnvArrays A, uint64_t step, int player_sel, T* __restrict__ out, uint32_t stride, uint32_t n_batches,
              unsigned int* __restrict__ batch_counter) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ int s_batch[2];   // batch held by each record buffer, -1 = no more work
+  __shared__ int s_batch[kWsBufs];   // batch held by each record buffer, -1 = no more work
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   unsigned char* stage_base = smem_raw;
   uint32_t* const rec0 = reinterpret_cast<uint32_t*>(smem_raw + kWsEncWarps * kStageBytes);
   BlockStats st;
-  st.init(reinterpret_cast<uint32_t*>(smem_raw + kWsEncWarps * kStageBytes + 2 * kWsRecBytes));
+  st.init(reinterpret_cast<uint32_t*>(smem_raw + kWsEncWarps * kStageBytes + kWsBufs * kWsRecBytes));
   const bool both = player_sel == COUP_PLAYER_BOTH;
   const bool rules = warp < kWsRulesWarps;
   unsigned char* stage = rules ? nullptr : stage_base + static_cast<size_t>(warp - kWsRulesWarps) * kStageBytes;
   if (!rules) zero_stage(stage, lane);
   // Batches are handed out dynamically (global counter): SMs differ by ~20 % in achieved store bandwidth, so a
   // static split would leave the fast ones idle at the end.
+#ifdef COUP_WS_DEBUG
+  // Cycle counters of one rules warp and one encoder warp per CTA, summed into the spare statistics slots 24..29:
+  // rules busy / rules waiting for a free record buffer / encoder waiting for records / encoder busy / CTA total /
+  // batches. Build with COUP_B200_NVCC_EXTRA=-DCOUP_WS_DEBUG; read with coup_vec_stats.
+  long long dbg_busy = 0, dbg_wait = 0, dbg_t, dbg_t0 = clock64();
+  int dbg_batches = 0;
+#define WS_DBG_MARK() (dbg_t = clock64())
+#define WS_DBG_ADD(var) ((var) += clock64() - dbg_t)
+#else
+#define WS_DBG_MARK()
+#define WS_DBG_ADD(var)
+#endif
   for (int it = 0;; ++it) {
-    const int buf = it & 1;
+    const int buf = it % kWsBufs;
     uint32_t* recs = rec0 + buf * (kWsRecBytes / 4);
     if (rules) {
-      if (it >= 2) named_bar_sync(kBarEmpty0 + buf, kWsThreads);       // the encoders are done with this buffer
+      WS_DBG_MARK();
+      if (it >= kWsBufs) named_bar_sync(kBarEmpty0 + buf, kWsThreads);  // the encoders are done with this buffer
+      WS_DBG_ADD(dbg_wait);
+      WS_DBG_MARK();
       if (warp == 0 && lane == 0) {
         const unsigned int b = atomicAdd(batch_counter, 1u);
         s_batch[buf] = b < n_batches ? static_cast<int>(b) : -1;
@@ -925,23 +945,42 @@ k_rollout_ws(EnvArrays A, uint64_t step, int player_sel, T* __restrict__ out, ui
       }
       __threadfence_block();
       named_bar_arrive(kBarFull0 + buf, kWsThreads);                    // records (or the stop mark) are ready
+      WS_DBG_ADD(dbg_busy);
       if (b < 0) {
-        if (it >= 1) named_bar_sync(kBarEmpty0 + (buf ^ 1), kWsThreads);  // drain the last hand-back
+        // drain the hand-backs nobody will wait for any more (the last kWsBufs - 1 encoded batches)
+        for (int back = 1; back < kWsBufs; ++back)
+          if (it - back >= 0) named_bar_sync(kBarEmpty0 + (it - back) % kWsBufs, kWsThreads);
         break;
       }
     } else {
+      WS_DBG_MARK();
       named_bar_sync(kBarFull0 + buf, kWsThreads);
+      WS_DBG_ADD(dbg_wait);
       const int b = s_batch[buf];
       if (b < 0) break;
+      WS_DBG_MARK();
       block_encode_info_tma<T>(recs, both, reinterpret_cast<T*>(stage),
                                reinterpret_cast<unsigned char*>(out) +
                                    static_cast<size_t>(b) * kWsBatch * (both ? 2 : 1) * stride * sizeof(T),
                                warp - kWsRulesWarps, lane, static_cast<int>(stride), kWsEncWarps, /*wait_for_writes=*/false);
       named_bar_arrive(kBarEmpty0 + buf, kWsThreads);                   // hand the record buffer back
+      WS_DBG_ADD(dbg_busy);
+#ifdef COUP_WS_DEBUG
+      ++dbg_batches;
+#endif
     }
   }
   if (!rules && lane == 0) tma_wait_all();
   st.flush(A.stats);
+#ifdef COUP_WS_DEBUG
+  if (lane == 0 && (warp == 0 || warp == kWsRulesWarps)) {
+    const int base = warp == 0 ? 24 : 26;   // rules: busy, wait | encoder: wait, busy
+    atomicAdd(&A.stats[base], static_cast<unsigned long long>(warp == 0 ? dbg_busy : dbg_wait));
+    atomicAdd(&A.stats[base + 1], static_cast<unsigned long long>(warp == 0 ? dbg_wait : dbg_busy));
+    if (warp == 0) atomicAdd(&A.stats[28], static_cast<unsigned long long>(clock64() - dbg_t0));
+    else atomicAdd(&A.stats[29], static_cast<unsigned long long>(dbg_batches));
+  }
+#endif
 }
 
 // ---- incremental info-state contract ------------------------------------------------------------------------------
