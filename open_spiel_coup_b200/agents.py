@@ -594,3 +594,29 @@ def train_nfsp(num_train_episodes, hidden_layers_sizes, num_envs=1024, eval_ever
             eval_func(joint_avg_policy, ep, [a.loss for a in agents])
     env.close()
     return agents
+
+
+def agent_cmp(policy_a, policy_b, cmp_test_eps, num_envs=4096, device=0, seed=0):
+    """`coup_experiments/scripts/agent_cmp.py:123-149`: two fixed policies against each other, `cmp_test_eps` games
+    with `policy_a` in seat 0 and as many with the seats swapped. Policies: anything `PolicyAgent` accepts (an
+    `nn.Module` giving logits, `UniformRandomPolicy`, `FirstActionPolicy`, an object with `action_probs` such as a
+    `DeepCFRSolver` or an MCCFR `AveragePolicy`) or agents with a batched `step` (`NFSPPolicies(...).agents()[seat]`).
+    Returns `policy_a`'s mean reward (the other's is its negative) and the mean episode length in moves, chance
+    nodes included, as the reference counts them."""
+    dev = torch.device("cuda", device)
+    env = CoupVectorEnv(min(num_envs, cmp_test_eps), seed=seed + 1, device=device, auto_reset=False)
+
+    def agent(policy, seat):
+        return policy if hasattr(policy, "step") else PolicyAgent(seat, policy, dev, seed)
+
+    total_reward, total_moves = 0.0, 0
+    for a_seat in (0, 1):
+        players = [None, None]
+        players[a_seat], players[1 - a_seat] = agent(policy_a, a_seat), agent(policy_b, 1 - a_seat)
+        env.clear_stats()
+        totals, _ = run_episodes(env, players, cmp_test_eps, is_evaluation=True)
+        stats = env.stats()
+        total_reward += float(totals[a_seat])
+        total_moves += stats["decision_steps"] + stats["chance_moves"]
+    env.close()
+    return total_reward / (2 * cmp_test_eps), total_moves / (2 * cmp_test_eps)

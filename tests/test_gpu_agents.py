@@ -190,7 +190,7 @@ def test_learning_rules_equal_plain_pytorch_restatement():
     a0 = copy.deepcopy(nf.avg_network)
     loss = nf._learn()
     ref = -(res["action_probs"] * torch.log_softmax(a0(res["info_state"].float()), -1)).sum(-1).mean()
-    assert abs(loss - float(ref)) < 1e-5
+    assert abs(loss - float(ref.detach())) < 1e-5
 
 
 def test_rl_resp_exploits_the_first_action_bot():
@@ -219,3 +219,12 @@ def test_train_nfsp_runs_and_evaluates():
     # the joint average policy can be handed to rl_resp as the exploitee, as the reference script does
     recs = A.rl_resp(exploitee=A.NFSPPolicies(agents), num_train_episodes=512, eval_every=512, eval_episodes=256, num_envs=256)
     assert len(recs) == 1 and -4 <= recs[0]["value"] <= 4
+
+
+def test_agent_cmp_both_seats():
+    """agent_cmp.py:123-149: the first-action bot loses to uniform-random play from either seat; a policy against
+    itself scores ~0; episode lengths count chance nodes."""
+    mean, length = A.agent_cmp(UniformRandomPolicy(), A.FirstActionPolicy(), 2000, num_envs=1024, seed=2)
+    assert mean > 0.5 and 8 < length < 91
+    mean2, length2 = A.agent_cmp(UniformRandomPolicy(), UniformRandomPolicy(), 4000, num_envs=2048, seed=3)
+    assert abs(mean2) < 0.12 and abs(length2 - 21.2) < 1.0          # 21.2 moves per uniform-random episode (SURVEY 6)
