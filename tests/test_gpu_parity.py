@@ -752,3 +752,25 @@ def test_partial_reset_only_touches_selected_envs(oracle):
     st = unpack_states(env.state.cpu().numpy())
     assert (st["hands"][:, 0, :2] == [2 << 1, 4 << 1]).all() and (st["hands"][:, 1, :2] == [0 << 1, 3 << 1]).all()
     assert (st["deck"] == [2, 3, 2, 2, 2]).all()
+
+
+def test_chance_distribution_matches_chance_outcomes():
+    """a-5: the device sampler must draw card c with probability deck_[c] / sum(deck_) (coup.cc:1062-1077). Over 2^20
+    freshly dealt games: the first deal is uniform over the 5 card types (3 of 15 each), and the second, given the
+    first, has probability 2/14 for the same type and 3/14 for each other type; 5-sigma bands on the counts."""
+    n = 1 << 20
+    env = CoupVectorEnv(n, seed=2024)
+    hist = env.history[:, 0].cpu().numpy().view(np.uint32).astype(np.int64)
+    c0 = (hist & 31) - 18                      # deal to player 0: codes 18..22
+    c1 = ((hist >> 5) & 31) - 23               # deal to player 1: codes 23..27
+    assert c0.min() >= 0 and c0.max() <= 4 and c1.min() >= 0 and c1.max() <= 4
+    first = np.bincount(c0, minlength=5)
+    sigma = np.sqrt(n * 0.2 * 0.8)
+    assert np.abs(first - n * 0.2).max() < 5 * sigma
+    for c in range(5):
+        sel = c0 == c
+        m = int(sel.sum())
+        second = np.bincount(c1[sel], minlength=5)
+        for d in range(5):
+            p = (2 if d == c else 3) / 14
+            assert abs(second[d] - m * p) < 5 * np.sqrt(m * p * (1 - p)), (c, d, second[d], m * p)
