@@ -97,7 +97,7 @@ int rollout_typed(coup_vec_env* env, int n_steps, int encode_player, void* d_out
   for (int i = 0; i < n_steps; ++i) {
     if (specialised) {
       // persistent, warp-specialised: one CTA per SM over the full 256-env batches, then the ragged tail (if any)
-      cudaMemsetAsync(env->d_scratch + 2, 0, sizeof(uint32_t), st);   // the dynamic batch counter
+      CUDA_TRY(cudaMemsetAsync(env->d_scratch + 2, 0, sizeof(uint32_t), st));   // the dynamic batch counter
       k_rollout_ws<T><<<std::min<unsigned>(sms, n_batches), kWsThreads, kWsSmemBytes, st>>>(
           env->A, env->step_counter, encode_player, static_cast<T*>(d_out), stride, n_batches, env->d_scratch + 2);
       if (tail_base < env->A.n)
