@@ -61,7 +61,10 @@ def parse_args():
     ap.add_argument("--no-extra-contracts", action="store_true")
     ap.add_argument("--no-selfplay", action="store_true")
     ap.add_argument("--no-host-tensor", action="store_true")
-    ap.add_argument("--e2e-slabs", type=int, default=4, help="sub-slabs (handles/streams) of the host-buffer leg")
+    ap.add_argument("--e2e-slabs", type=int, default=0,
+                    help="sub-slabs (handles/streams) of the host-buffer leg; 0 = 16 with >= 12 host-policy threads per rank, else 8")
+    ap.add_argument("--host-threads", type=int, default=0, help="threads of the host policy per rank (0 = host cores / ranks)")
+    ap.add_argument("--blocking-sync", action="store_true", help="host-buffer calls sleep instead of spinning while they wait")
     ap.add_argument("--fused", default="ws", choices=["ws", "cta"],
                     help="fused rollout kernel: persistent warp-specialised (rules warps + encoder warps), or one CTA per 256 envs")
     ap.add_argument("--encoder", default="staged", choices=["staged", "plain"],
@@ -302,15 +305,18 @@ def main():
     # buffers, so that the host-side policy and the PCIe copies of one sub-slab overlap the encoder
     # of the other (what a host-driven caller does to keep the GPU busy). Same total number of envs.
     lib = _lib.load()
-    threads = max(1, (os.cpu_count() or 1) // world)
-    S_ = max(1, args.e2e_slabs)
+    threads = args.host_threads or max(1, (os.cpu_count() or 1) // world)
+    # Measured (profiles/README.md): finer sub-slabs hide the host policy and the PCIe round trip better (1 GPU, 16 threads:
+    # 6.55e8 / 6.67e8 / 6.80e8 steps/s with 4 / 8 / 16), until the per-call cost of waking a small thread pool shows
+    # (8 GPUs, 4 threads per rank: 4.77e9 / 5.28e9 / 4.44e9).
+    S_ = args.e2e_slabs if args.e2e_slabs > 0 else (16 if threads >= 12 else 8)
     ns = n // S_
     del env
     torch.cuda.empty_cache()
     slabs = []
     for i in range(S_):
         ev = CoupVectorEnv(ns, seed=args.seed, device=local, global_env_offset=slab_offset + i * ns, auto_reset=True,
-                           plain_store_encoder=(args.encoder == "plain"))
+                           plain_store_encoder=(args.encoder == "plain"), blocking_sync=args.blocking_sync)
         ev.rollout(100)
         h_act = torch.empty(ns, dtype=torch.uint8).pin_memory()
         h_words = torch.empty(ns, dtype=torch.int32).pin_memory()

@@ -78,6 +78,8 @@ enum {
                                     of the default shared-memory staging + bulk (TMA) stores; same bytes */
   , COUP_FLAG_NO_WARP_SPECIALISATION = 1u << 2 /* fused rollout: one CTA per 256 envs instead of the default
                                     persistent kernel whose rules warps and encoder warps overlap; same bytes */
+  , COUP_FLAG_BLOCKING_SYNC = 1u << 3 /* the host-buffer calls (coup_vec_step_host*) sleep instead of spinning while
+                                    they wait for the device: for hosts with fewer cores than threads */
 };
 
 typedef struct coup_vec_opts {

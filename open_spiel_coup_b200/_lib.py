@@ -28,6 +28,7 @@ OK, ERR_INVALID_ARG, ERR_CUDA, ERR_NO_DEVICE, ERR_ILLEGAL_ACTION = 0, 1, 2, 3, 4
 FLAG_AUTO_RESET = 1
 FLAG_PLAIN_STORE_ENCODER = 2
 FLAG_NO_WARP_SPECIALISATION = 4
+FLAG_BLOCKING_SYNC = 8
 PLAYER_0, PLAYER_1, PLAYER_CURRENT, PLAYER_BOTH = 0, 1, 2, 3
 DTYPE_F32, DTYPE_U8, DTYPE_BF16 = 0, 1, 2
 STAT_DECISION_STEPS, STAT_CHANCE_MOVES, STAT_EPISODES, STAT_TRUNCATED = 0, 1, 2, 3

@@ -191,7 +191,9 @@ int coup_vec_create(const coup_vec_opts* opts, coup_vec_env** out) {
   alloc(reinterpret_cast<void**>(&env->d_actions), n);
   alloc(reinterpret_cast<void**>(&env->d_scratch), 4 * sizeof(uint32_t));
   alloc(reinterpret_cast<void**>(&env->d_row), 2 * 2496 * sizeof(float));
-  if (err == cudaSuccess) err = cudaEventCreateWithFlags(&env->host_outputs_ready, cudaEventDisableTiming);
+  if (err == cudaSuccess)
+    err = cudaEventCreateWithFlags(&env->host_outputs_ready,
+                                   cudaEventDisableTiming | ((opts->flags & COUP_FLAG_BLOCKING_SYNC) ? cudaEventBlockingSync : 0));
   if (err == cudaSuccess) err = cudaMemset(A.stats, 0, COUP_STATS_LEN * sizeof(unsigned long long));
   if (err == cudaSuccess) err = cudaMemset(A.history, 0, n * kHistoryWords * sizeof(uint32_t));
   if (err != cudaSuccess) {

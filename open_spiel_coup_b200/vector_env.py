@@ -46,7 +46,7 @@ class CoupVectorEnv:
     observation_size = OBSERVATION_SIZE
 
     def __init__(self, num_envs, seed=1234, device=0, global_env_offset=0, auto_reset=False,
-                 plain_store_encoder=False, warp_specialised=True):
+                 plain_store_encoder=False, warp_specialised=True, blocking_sync=False):
         self._lib = _lib.load()
         if not torch.cuda.is_available():
             raise CoupError("CoupVectorEnv needs a CUDA device (there is no CPU fallback)")
@@ -58,7 +58,8 @@ class CoupVectorEnv:
         opts = _lib.VecOpts(self.num_envs, self.device.index, seed, global_env_offset,
                             (FLAG_AUTO_RESET if auto_reset else 0)
                             | (_lib.FLAG_PLAIN_STORE_ENCODER if plain_store_encoder else 0)
-                            | (0 if warp_specialised else _lib.FLAG_NO_WARP_SPECIALISATION), 0)
+                            | (0 if warp_specialised else _lib.FLAG_NO_WARP_SPECIALISATION)
+                            | (_lib.FLAG_BLOCKING_SYNC if blocking_sync else 0), 0)
         self._h = C.c_void_p()
         check(self._lib.coup_vec_create(C.byref(opts), C.byref(self._h)))
         n, L, d = self.num_envs, self._lib, self.device
