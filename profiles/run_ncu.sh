@@ -21,5 +21,9 @@ CMDE="python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-extra-contrac
 $CMDE > $OUT/ncu_plain_env_$TAG.json 2> $OUT/ncu_plain_env_$TAG.err && \
 ncu --set full --clock-control none --import-source on -k regex:k_rollout -s 110 -c 1 -f -o $OUT/prof_${TAG}_rollout_env $CMDE > $OUT/ncu_full_env_$TAG.log 2>&1
 echo "full env rc=$?"
+CMDB="python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-extra-contracts --no-selfplay --no-host-tensor --contract bf16"
+$CMDB > $OUT/ncu_plain_bf16_$TAG.json 2> $OUT/ncu_plain_bf16_$TAG.err && \
+ncu --set full --clock-control none --import-source on -k regex:k_rollout -s 110 -c 1 -f -o $OUT/prof_${TAG}_rollout_bf16 $CMDB > $OUT/ncu_full_bf16_$TAG.log 2>&1
+echo "full bf16 rc=$?"
 ls -la $OUT
 cp open_spiel_coup_b200/libcoup_b200.so $OUT/libcoup_b200_$TAG.so   # for scripts/ncu_hotspots.py (SASS <-> source lines)
