@@ -169,6 +169,22 @@ int coup_vec_copy_env(coup_vec_env* env, uint32_t src, uint32_t dst, void* strea
 int coup_vec_fork(coup_vec_env* dst, const coup_vec_env* src, const uint32_t* d_parent, const uint8_t* d_actions,
                   const uint8_t* d_forced_chance, uint32_t count, void* stream);
 
+/* One level of a sampled CFR traversal, for `count` nodes at once (python/algorithms/deep_cfr.py:415-525). Inputs:
+ * the advantage-network outputs of the player to move (float[count][18]) and the nodes' step words
+ * (coup_vec_step_word: legal mask + current player). coup_cfr_expand writes the regret-matched strategy
+ * (`_sample_action_from_advantage`, :499-525) and, as a bit mask per node, the children to expand: every legal action
+ * of the traverser with `external` != 0 (:438-441), else min(n_legal, k) actions drawn without replacement from
+ * expl * uniform + (1 - expl) * strategy with k = outcome_factor, or -- when e_outcome >= 0 -- outcome_factor with
+ * probability e_outcome and 1 otherwise (:442-466); one action drawn from the strategy at the opponent's nodes
+ * (:482-487). Draws come from Philox4x32-10 keyed by (seed, node index) at `counter`. d_child_count_out[i] is the
+ * number of bits set. coup_cfr_children turns the masks into the (parent, action) lists coup_vec_fork consumes, given
+ * the exclusive prefix sum d_offsets of the child counts (int64[count]). Device pointers; not tied to a handle. */
+int coup_cfr_expand(const float* d_advantages, const uint32_t* d_step_words, uint32_t count, int traverser, int external,
+                    uint32_t outcome_factor, float e_outcome, float expl, uint64_t seed, uint64_t counter,
+                    float* d_strategy_out, uint32_t* d_expand_out, uint32_t* d_child_count_out, void* stream);
+int coup_cfr_children(const uint32_t* d_expand, const int64_t* d_offsets, uint32_t count, uint32_t* d_parent_out,
+                      uint8_t* d_action_out, void* stream);
+
 /* Single-env accessors with HOST buffers, following rust_open_spiel.h one to one (GameNewInitialState :41,
  * StateApplyAction :62, StateClone :49, StateInformationStateTensor / StateObservationTensor :73-76: tensors
  * are written into a caller-provided buffer of explicit length). `slot` indexes an env of the handle; these

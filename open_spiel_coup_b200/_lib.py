@@ -37,7 +37,7 @@ STAT_EPISODE_MOVES, STAT_ILLEGAL, STAT_RETURN_HIST, STAT_LEGAL_HIST, STATS_LEN =
 # Every symbol include/coup_b200.h declares (tests check that the built library exports all of them).
 EXPORTED_SYMBOLS = [
     "coup_last_error", "coup_device_count", "coup_vec_create", "coup_vec_destroy", "coup_vec_num_envs",
-    "coup_vec_reset", "coup_vec_step", "coup_vec_new_initial_state", "coup_vec_apply_move", "coup_vec_copy_env", "coup_vec_fork", "coup_env_new_initial_state", "coup_env_apply_action", "coup_env_clone", "coup_env_read",
+    "coup_vec_reset", "coup_vec_step", "coup_vec_new_initial_state", "coup_vec_apply_move", "coup_vec_copy_env", "coup_vec_fork", "coup_cfr_expand", "coup_cfr_children", "coup_env_new_initial_state", "coup_env_apply_action", "coup_env_clone", "coup_env_read",
     "coup_env_information_state_tensor", "coup_env_observation_tensor",
     "coup_vec_sample_uniform", "coup_vec_sample_policy", "coup_vec_rollout", "coup_vec_rollout_incremental",
     "coup_vec_legal_mask", "coup_vec_current_player", "coup_vec_done", "coup_vec_rewards",
@@ -91,6 +91,8 @@ def load():
     lib.coup_vec_apply_move.argtypes = [vp, u8p, vp]
     lib.coup_vec_copy_env.argtypes = [vp, C.c_uint32, C.c_uint32, vp]
     lib.coup_vec_fork.argtypes = [vp, vp, vp, u8p, u8p, C.c_uint32, vp]
+    lib.coup_cfr_expand.argtypes = [vp, vp, C.c_uint32, C.c_int, C.c_int, C.c_uint32, C.c_float, C.c_float, C.c_uint64, C.c_uint64, vp, vp, vp, vp]
+    lib.coup_cfr_children.argtypes = [vp, vp, C.c_uint32, vp, vp, vp]
     lib.coup_env_new_initial_state.argtypes = [vp, C.c_uint32]
     lib.coup_env_apply_action.argtypes = [vp, C.c_uint32, C.c_int]
     lib.coup_env_clone.argtypes = [vp, C.c_uint32, C.c_uint32]

@@ -277,6 +277,27 @@ int coup_vec_fork(coup_vec_env* dst, const coup_vec_env* src, const uint32_t* d_
   return launch_status("k_fork");
 }
 
+int coup_cfr_expand(const float* d_advantages, const uint32_t* d_step_words, uint32_t count, int traverser, int external,
+                    uint32_t outcome_factor, float e_outcome, float expl, uint64_t seed, uint64_t counter,
+                    float* d_strategy_out, uint32_t* d_expand_out, uint32_t* d_child_count_out, void* stream) {
+  if (count == 0) return COUP_OK;
+  if (!d_advantages || !d_step_words || !d_strategy_out || !d_expand_out || !d_child_count_out || outcome_factor == 0 ||
+      (traverser != 0 && traverser != 1))
+    return fail(COUP_ERR_INVALID_ARG, "coup_cfr_expand: bad arguments");
+  k_cfr_expand<<<blocks_for(count), kBlockThreads, 0, S(stream)>>>(d_advantages, d_step_words, count, traverser, external,
+                                                                  outcome_factor, e_outcome, expl, seed, counter,
+                                                                  d_strategy_out, d_expand_out, d_child_count_out);
+  return launch_status("k_cfr_expand");
+}
+
+int coup_cfr_children(const uint32_t* d_expand, const int64_t* d_offsets, uint32_t count, uint32_t* d_parent_out,
+                      uint8_t* d_action_out, void* stream) {
+  if (count == 0) return COUP_OK;
+  if (!d_expand || !d_offsets || !d_parent_out || !d_action_out) return fail(COUP_ERR_INVALID_ARG, "coup_cfr_children: null argument");
+  k_cfr_children<<<blocks_for(count), kBlockThreads, 0, S(stream)>>>(d_expand, d_offsets, count, d_parent_out, d_action_out);
+  return launch_status("k_cfr_children");
+}
+
 // ---- single-env accessors with HOST buffers, in the style of rust_open_spiel.h ------------------------
 static int one_move(coup_vec_env* env, uint32_t slot, uint32_t mv, int mode) {
   if (!env || slot >= env->A.n) return fail(COUP_ERR_INVALID_ARG, "coup_env_*: bad handle or slot");

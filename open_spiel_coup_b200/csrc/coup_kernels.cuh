@@ -399,6 +399,115 @@ k_fork(EnvArrays D, const uint4* __restrict__ src_state, const uint32_t* __restr
   st.flush(D.stats);
 }
 
+// ---- one level of a sampled CFR traversal (python/algorithms/deep_cfr.py:415-525), thread per node ------------------
+// From the advantage-network outputs of the player to move: regret matching (positive parts over the legal actions,
+// normalised; if none is positive, probability one on the legal action with the largest raw advantage, :499-525),
+// then which children to expand: at the traverser's nodes every legal action (external sampling, :438-441) or
+// min(n_legal, k) actions drawn without replacement from expl * uniform + (1 - expl) * strategy (outcome sampling,
+// :442-466; k = outcome_factor, or per node outcome_factor with probability e_outcome and 1 otherwise); at the
+// opponent's nodes one action drawn from the strategy (:482-487). Sampling without replacement is the Gumbel-top-k
+// order of the log-probabilities, i.e. the sequential renormalised draw of np.random.choice(replace=False).
+__device__ __forceinline__ float u01(uint32_t r) { return (static_cast<float>(r >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+
+__global__ void __launch_bounds__(kBlockThreads)
+k_cfr_expand(const float* __restrict__ advantages, const uint32_t* __restrict__ step_words, uint32_t count,
+             int traverser, int external, uint32_t outcome_factor, float e_outcome, float expl, uint64_t seed,
+             uint64_t counter, float* __restrict__ strategy_out, uint32_t* __restrict__ expand_out,
+             uint32_t* __restrict__ count_out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const uint32_t word = step_words[i];
+  const uint32_t legal = word & 0x3FFFFu;
+  const int player = (word >> 18) & 1u;
+  const int n_legal = __popc(legal);
+  float adv[18];
+#pragma unroll
+  for (int a = 0; a < 18; ++a) adv[a] = advantages[static_cast<size_t>(i) * 18 + a];
+  float total = 0.f, best = -INFINITY;
+  int best_a = 0;
+#pragma unroll
+  for (int a = 0; a < 18; ++a) {
+    if ((legal >> a) & 1u) {
+      total += fmaxf(adv[a], 0.f);
+      if (adv[a] > best) { best = adv[a]; best_a = a; }
+    }
+  }
+  float strat[18];
+#pragma unroll
+  for (int a = 0; a < 18; ++a) {
+    const bool ok = (legal >> a) & 1u;
+    strat[a] = !ok ? 0.f : total > 0.f ? fmaxf(adv[a], 0.f) / total : (a == best_a ? 1.f : 0.f);
+    strategy_out[static_cast<size_t>(i) * 18 + a] = strat[a];
+  }
+  uint32_t expand = 0;
+  if (n_legal > 0) {
+    const uint4 r0 = env_random(seed, i, counter, 2), r1 = env_random(seed, i, counter, 3), r2 = env_random(seed, i, counter, 4);
+    if (player != traverser) {
+      float sum = 0.f;
+#pragma unroll
+      for (int a = 0; a < 18; ++a) sum += strat[a];
+      const float target = u01(r0.x) * sum;
+      float acc = 0.f;
+      int pick = best_a;
+#pragma unroll
+      for (int a = 17; a >= 0; --a) if (strat[a] > 0.f) pick = a;           // fall-back: first action with mass
+      bool done = false;
+#pragma unroll
+      for (int a = 0; a < 18; ++a) {
+        if (!done && strat[a] > 0.f) { acc += strat[a]; pick = a; if (target < acc) done = true; }
+      }
+      expand = 1u << pick;
+    } else if (external) {
+      expand = legal;
+    } else {
+      uint32_t k = outcome_factor;
+      if (e_outcome >= 0.f) k = u01(r0.y) < e_outcome ? outcome_factor : 1u;
+      k = min(k, static_cast<uint32_t>(n_legal));
+      float key[18];
+      int slot = 0;                                                          // legal actions draw r0.z, r0.w, r1.*, r2.* in order
+#pragma unroll
+      for (int a = 0; a < 18; ++a) {
+        key[a] = -INFINITY;
+        if ((legal >> a) & 1u) {
+          const uint32_t r = slot == 0 ? r0.z : slot == 1 ? r0.w : slot == 2 ? r1.x : slot == 3 ? r1.y : slot == 4 ? r1.z
+                           : slot == 5 ? r1.w : slot == 6 ? r2.x : slot == 7 ? r2.y : slot == 8 ? r2.z : r2.w;
+          ++slot;
+          const float p = expl / n_legal + (1.f - expl) * strat[a];
+          if (p > 0.f) key[a] = logf(p) - logf(-logf(u01(r)));
+        }
+      }
+      for (uint32_t t = 0; t < k; ++t) {
+        int arg = -1;
+        float m = -INFINITY;
+#pragma unroll
+        for (int a = 0; a < 18; ++a) if (!((expand >> a) & 1u) && key[a] > m) { m = key[a]; arg = a; }
+        if (arg < 0) break;
+        expand |= 1u << arg;
+      }
+    }
+  }
+  expand_out[i] = expand;
+  count_out[i] = __popc(expand);
+}
+
+// Children of a level in parent order: child j of node i (j-th set bit of expand[i]) lands at offsets[i] + j, where
+// offsets is the exclusive prefix sum of the child counts.
+__global__ void __launch_bounds__(kBlockThreads)
+k_cfr_children(const uint32_t* __restrict__ expand, const int64_t* __restrict__ offsets, uint32_t count,
+               uint32_t* __restrict__ parent_out, uint8_t* __restrict__ action_out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  uint32_t bits = expand[i];
+  int64_t pos = offsets[i];
+  while (bits) {
+    const int a = __ffs(bits) - 1;
+    bits &= bits - 1;
+    parent_out[pos] = i;
+    action_out[pos] = static_cast<uint8_t>(a);
+    ++pos;
+  }
+}
+
 // ---- uniform-random legal action (same draw the fused rollout would use at this step counter) ------
 __global__ void __launch_bounds__(kBlockThreads)
 k_sample_uniform(EnvArrays A, uint8_t* __restrict__ actions_out, uint64_t step) {

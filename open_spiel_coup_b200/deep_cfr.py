@@ -22,10 +22,12 @@ import collections
 import math
 import os
 
+import ctypes
+
 import torch
 from torch import nn
 
-from ._lib import INFO_STATE_SIZE, NUM_DISTINCT_ACTIONS, PLAYER_CURRENT
+from ._lib import INFO_STATE_SIZE, NUM_DISTINCT_ACTIONS, PLAYER_CURRENT, check
 from .vector_env import CoupVectorEnv
 
 AdvantageMemory = collections.namedtuple("AdvantageMemory", "info_state iteration advantage action")   # deep_cfr.py:36-37
@@ -155,7 +157,8 @@ class DeepCFRSolver:
     """`deep_cfr.DeepCFRSolver` (deep_cfr.py:102-640) for game "coup". Arguments as in the reference (:118-188);
     additions: `device`, `seed`, `max_nodes` (size of each of the two scratch env slabs; a level with more nodes is
     expanded in slab-sized pieces, so the width of a tree is limited by HBM at ~200 B per node, not by the slabs),
-    `roots_per_batch` (how many of the `num_traversals` roots are expanded together), `max_tree_nodes` (a batch whose
+    `fused_expand` (regret matching and child selection of a level in one CUDA kernel, `coup_cfr_expand`, instead of
+    ~35 PyTorch ops), `roots_per_batch` (how many of the `num_traversals` roots are expanded together), `max_tree_nodes` (a batch whose
     trees grow past this many nodes raises instead of exhausting memory) and `record_tree` (keep the
     per-level bookkeeping of the last batch in `last_tree` for inspection and tests)."""
 
@@ -166,7 +169,8 @@ class DeepCFRSolver:
                  outcome_samp_expl=0.6, outcome_factor=1, e_outcome=0, iter_net_train=False, adv_net_reinit_every=1,
                  eval_func=None, eval_every=10, eval_train_episodes=10000, eval_test_every=5000,
                  eval_test_episodes=1000, use_checkpoints=False, checkpoint_dir=None, save_every=None,
-                 device=0, seed=0, max_nodes=1 << 18, roots_per_batch=None, max_tree_nodes=1 << 26, record_tree=False):
+                 device=0, seed=0, max_nodes=1 << 18, roots_per_batch=None, max_tree_nodes=1 << 26, record_tree=False,
+                 fused_expand=True):
         if sampling_method not in ("external", "outcome", "e-outcome"):
             raise ValueError(f"Unknown sampling method '{sampling_method}'.")           # deep_cfr.py:229-230
         if outcome_factor <= 0:
@@ -200,6 +204,8 @@ class DeepCFRSolver:
         self._checkpoint_dir = checkpoint_dir
         self._save_every = save_every
         self._record_tree = record_tree
+        self._fused_expand = fused_expand       # regret matching + child selection in one CUDA kernel (coup_cfr_expand)
+        self._expand_seed, self._expand_counter = seed * 2654435761 % (1 << 63) + 17, 0
         self.last_tree = None
 
         torch.manual_seed(seed)
@@ -322,6 +328,8 @@ class DeepCFRSolver:
     @torch.no_grad()
     def _advantages(self, rows_u8, cur_player):
         x = rows_u8.float()
+        if x.shape[0] <= 8192:      # small levels are launch-bound: both networks on every row, then select
+            return torch.where((cur_player == 0).view(-1, 1), self._advantage_networks[0](x), self._advantage_networks[1](x))
         out = torch.empty((x.shape[0], self._num_actions), dtype=torch.float32, device=self.device)
         for p in range(self._num_players):
             idx = (cur_player == p).nonzero(as_tuple=True)[0]
@@ -366,6 +374,29 @@ class DeepCFRSolver:
         rank = keys.argsort(-1, descending=True).argsort(-1)
         return legal & (rank < num_to_sample.view(-1, 1))
 
+    def _select_children(self, player, adv, word):
+        """Fused path (coup_cfr_expand + coup_cfr_children): strategy [k, 18] and the (parent, action) lists of the
+        children, in parent order, from the advantages and step words of k nodes."""
+        lib, k, dev = self._slabs[0]._lib, int(word.numel()), self.device
+        stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        ptr = lambda t: ctypes.c_void_p(t.data_ptr())
+        adv = adv.contiguous()
+        word = word.contiguous()
+        strategy = torch.empty((k, NUM_DISTINCT_ACTIONS), dtype=torch.float32, device=dev)
+        expand = torch.empty(k, dtype=torch.int32, device=dev)
+        counts = torch.empty(k, dtype=torch.int32, device=dev)
+        e_outcome = float(self._e_outcome) if self._sampling_method == "e-outcome" else -1.0
+        check(lib.coup_cfr_expand(ptr(adv), ptr(word), k, player, int(self._sampling_method == "external"),
+                                  int(self._outcome_factor), e_outcome, float(self._expl), self._expand_seed,
+                                  self._expand_counter, ptr(strategy), ptr(expand), ptr(counts), stream))
+        self._expand_counter += 1
+        ends = torch.cumsum(counts, 0, dtype=torch.int64)
+        c = int(ends[-1])
+        parent = torch.empty(c, dtype=torch.int32, device=dev)
+        action = torch.empty(c, dtype=torch.uint8, device=dev)
+        check(lib.coup_cfr_children(ptr(expand), ptr(ends - counts), k, ptr(parent), ptr(action), stream))
+        return strategy, parent.long(), action.long()
+
     def _expand_chunk(self, player, state, history, word):
         """One slab-full of non-terminal nodes of a level: strategies, which children to expand, and the children
         themselves (packed state, history, step word), in parent order."""
@@ -374,20 +405,24 @@ class DeepCFRSolver:
         legal = _legal_bool(word & 0x3FFFF)
         cp = (word >> 18) & 1
         rows = src.information_state_tensor_gather(self._arange[:k], player=PLAYER_CURRENT, dtype=torch.uint8)
-        strategy = regret_matching(self._advantages(rows, cp), legal)
+        adv = self._advantages(rows, cp)
         is_trav = cp == player
-        # opponent nodes: one action from the matched regrets, renormalised (:482-492), and a StrategyMemory record
-        probs = strategy / strategy.sum(-1, keepdim=True)
-        sampled = torch.multinomial(probs, 1, generator=self._gen).view(-1)
-        opp = (~is_trav).nonzero(as_tuple=True)[0]
+        if self._fused_expand:
+            strategy, local, action = self._select_children(player, adv, word)
+        else:
+            strategy = regret_matching(adv, legal)
+            # opponent nodes: one action from the matched regrets, renormalised (:482-492)
+            probs = strategy / strategy.sum(-1, keepdim=True)
+            sampled = torch.multinomial(probs, 1, generator=self._gen).view(-1)
+            expand = torch.zeros_like(legal).scatter_(1, sampled.view(-1, 1), True)
+            trav = is_trav.nonzero(as_tuple=True)[0]
+            if trav.numel():
+                expand[trav] = self._children_of_traverser(strategy[trav], legal[trav])
+            local, action = expand.nonzero(as_tuple=True)          # row-major: children grouped by parent
+        opp = (~is_trav).nonzero(as_tuple=True)[0]                 # a StrategyMemory record per opponent node
         if opp.numel():
             self._strategy_memories.add(info_state=rows[opp], strategy_action_probs=strategy[opp],
                                         iteration=torch.full((opp.numel(),), self._iteration, device=self.device))
-        expand = torch.zeros_like(legal).scatter_(1, sampled.view(-1, 1), True)
-        trav = is_trav.nonzero(as_tuple=True)[0]
-        if trav.numel():
-            expand[trav] = self._children_of_traverser(strategy[trav], legal[trav])
-        local, action = expand.nonzero(as_tuple=True)              # row-major: children grouped by parent
         c = dst.fork_from(src, local, action.to(torch.uint8))
         # the reference's record keeps the loop variable `action` of its last `for`, i.e. the largest legal id (:479)
         last_legal = (NUM_DISTINCT_ACTIONS - 1) - legal.flip(-1).to(torch.int32).argmax(-1)
@@ -418,6 +453,8 @@ class DeepCFRSolver:
             if total > self._max_tree_nodes:
                 # multi-outcome and external sampling grow exponentially with the length of a Coup game (5-7 actions
                 # per turn, up to 91 moves): stop before the bookkeeping (~200 B per node) exhausts HBM
+                if self._record_tree:
+                    self.last_tree = levels          # forward part only (no values): what was expanded so far
                 raise RuntimeError(f"traversal batch grew past max_tree_nodes={self._max_tree_nodes} at level "
                                    f"{len(levels)} ({m} nodes wide): use fewer roots per batch or a smaller outcome_factor")
             terminal = ((word >> 19) & 1).bool()

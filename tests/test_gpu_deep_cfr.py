@@ -148,11 +148,12 @@ def _check_batch(oracle, solver, player, roots, method, factor, rng, start=None)
     return tree
 
 
-@pytest.mark.parametrize("method,factor,roots", [("outcome", 1, 64), ("outcome", 2, 8), ("e-outcome", 3, 8)])
-def test_traversal_tree_matches_recursion_on_oracle(oracle, method, factor, roots):
+@pytest.mark.parametrize("method,factor,roots,fused", [("outcome", 1, 64, True), ("outcome", 1, 64, False), ("outcome", 2, 8, True),
+                                                       ("outcome", 2, 8, False), ("e-outcome", 3, 8, True)])
+def test_traversal_tree_matches_recursion_on_oracle(oracle, method, factor, roots, fused):
     solver = DeepCFRSolver(policy_network_layers=(32,), advantage_network_layers=(32,), num_traversals=roots,
                            sampling_method=method, outcome_factor=factor, e_outcome=0.25, memory_capacity=1 << 20,
-                           max_nodes=1 << 12, max_tree_nodes=1 << 20, seed=11, record_tree=True)
+                           max_nodes=1 << 12, max_tree_nodes=1 << 20, seed=11, record_tree=True, fused_expand=fused)
     rng = np.random.default_rng(0)
     done = 0
     for attempt in range(12):         # multi-outcome trees of a long game can outgrow the node budget: draw again
@@ -239,3 +240,39 @@ def test_solver_runs_and_learns_something():
     from open_spiel_coup_b200.selfplay import UniformRandomPolicy, evaluate_policies
     means, steps = evaluate_policies([copy.deepcopy(policy_net), UniformRandomPolicy()], 2000, device=0, seed=1)
     assert abs(means[0] + means[1]) < 1e-9 and -2 <= means[0] <= 2 and steps > 2000
+
+
+def _inclusion_probability_top2(p):
+    """P(action a is among the first two of a sequential draw without replacement with probabilities p)."""
+    out = np.zeros_like(p)
+    for a in range(len(p)):
+        out[a] = p[a] + sum(p[b] * p[a] / (1 - p[b]) for b in range(len(p)) if b != a and p[b] < 1)
+    return out
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_outcome_sampling_without_replacement_distribution(fused):
+    """The traverser's children at the root (outcome sampling, factor 2): inclusion frequencies against the analytic
+    probabilities of np.random.choice(size=2, replace=False, p=0.6 uniform + 0.4 strategy) (deep_cfr.py:455-466),
+    summed over the 2^14 roots with their individual strategies; 5-sigma band."""
+    solver = DeepCFRSolver(policy_network_layers=(16,), advantage_network_layers=(16,), sampling_method="outcome", outcome_factor=2,
+                           num_traversals=1 << 14, max_nodes=1 << 17, max_tree_nodes=1 << 24, seed=8, record_tree=True,
+                           fused_expand=fused)
+    try:
+        solver.traverse(0, 1 << 14)                      # player 0 moves first: every root is a traverser node
+    except RuntimeError as err:                          # deeper levels may outgrow the budget; the root level is recorded
+        assert "max_tree_nodes" in str(err)
+    rec = solver.last_tree[0]
+    assert bool(rec["is_trav"].all())
+    strategy = rec["strategy"].double().cpu().numpy()
+    legal = rec["legal"].cpu().numpy()
+    expect = np.zeros(18)
+    for s, l in zip(strategy, legal):
+        idx = np.flatnonzero(l)
+        p = 0.6 / len(idx) + 0.4 * s[idx]
+        expect[idx] += _inclusion_probability_top2(p / p.sum())
+    counts = np.bincount(rec["action"].cpu().numpy(), minlength=18).astype(np.float64)
+    per_parent = np.bincount(rec["local"].cpu().numpy(), minlength=len(legal))
+    assert (per_parent == np.minimum(legal.sum(1), 2)).all()
+    z = (counts - expect) / np.sqrt(np.maximum(expect, 1.0))
+    assert np.abs(z).max() < 5.0, (counts, expect)
