@@ -12,10 +12,12 @@ info-state tensor of the player to move (the reference's benchmark_game.cc:53-60
 One "step" of this script = one such pass over all envs of a rank (one kernel launch).
 
 `value`  : decision steps/s, tensors and state resident in HBM, CUDA-event timed, max over ranks.
-`e2e`    : the same metric through the host-buffer C-ABI call (coup_vec_step_host): actions come from
-           pinned HOST memory every step, legal masks / current player / done / rewards go back to
-           HOST memory every step, the info-state tensor stays device-resident for the on-device
-           consumer (the policy network of north_star config 4).
+`e2e`    : the same metric through the host-buffer C-ABI call (coup_vec_step_host_packed) on 8-16 sub-slabs
+           with a stream each: actions come from pinned HOST memory every step, one step word per env (legal
+           mask, current player, done, reward, return) goes back to pinned HOST memory every step, the host
+           policy (coup_host_sample_uniform) turns the words into the next actions, and the info-state tensor
+           is encoded every step and stays device-resident for the on-device consumer (the policy network of
+           north_star config 4).
 """
 import argparse
 import ctypes as C
