@@ -51,6 +51,33 @@ def regret_matching(advantages, legal):
     return torch.where(total > 0, pos / total.clamp_min(1e-38), fallback)
 
 
+def backward_sweep(levels):
+    """The return path of `_traverse_game_tree` (deep_cfr.py:468-480, 492-497) over a level-ordered tree. Each level is a
+    dict with `terminal` [m] bool, `ret_p` [m] float64 (the traverser's return where terminal), `nt` (indices of the
+    non-terminal nodes) and -- when it has `children` -- per non-terminal node `strategy` [k, 18], `legal` [k, 18] bool,
+    `is_trav` [k] bool, `trav` (indices into the non-terminal list of the traverser's nodes) and the child lists
+    `local` / `action` (child j of the level is node j of the next level). Sets `value` [m] on every level: the
+    return at terminal nodes, the sampled child's value at the opponent's nodes, sum_a strategy[a] * payoff[a] at the
+    traverser's (unsampled actions count as payoff 0, as in the reference). Yields (level, sampled regrets [t, 18]
+    float32 of its traverser nodes: payoff[a] - value on the legal actions) from the deepest level up."""
+    child_values = None
+    for lvl in reversed(levels):
+        value = torch.where(lvl["terminal"], lvl["ret_p"], torch.zeros_like(lvl["ret_p"]))
+        regret = None
+        if lvl["children"]:
+            payoff = torch.zeros(lvl["legal"].shape, dtype=torch.float64, device=value.device)
+            payoff[lvl["local"], lvl["action"]] = child_values
+            cfv = (lvl["strategy"].double() * payoff * lvl["legal"]).sum(-1)
+            value[lvl["nt"]] = torch.where(lvl["is_trav"], cfv, payoff.sum(-1))
+            trav = lvl["trav"]
+            if trav.numel():
+                regret = ((payoff[trav] - cfv[trav].view(-1, 1)) * lvl["legal"][trav]).float()
+        lvl["value"] = value
+        child_values = value
+        if regret is not None:
+            yield lvl, regret
+
+
 class MLP(nn.Module):
     """`simple_nets.MLP` (simple_nets.py:84-120): Linear+ReLU hidden layers, linear head, weights drawn from a
     normal truncated at two standard deviations with stddev 1/sqrt(fan_in), zero biases (simple_nets.py:44-52)."""
@@ -481,27 +508,16 @@ class DeepCFRSolver:
                        children=int(lvl["local"].numel()))
             state, history, word = (torch.cat([k[i] for k in kids]) for i in range(3))
         # ---- backward sweep (:468-480) ----
-        child_values = None
-        for lvl in reversed(levels):
-            value = torch.where(lvl["terminal"], lvl["ret_p"], torch.zeros_like(lvl["ret_p"]))
-            if lvl["children"]:
-                payoff = torch.zeros(lvl["legal"].shape, dtype=torch.float64, device=self.device)
-                payoff[lvl["local"], lvl["action"]] = child_values
-                cfv = (lvl["strategy"].double() * payoff * lvl["legal"]).sum(-1)
-                value[lvl["nt"]] = torch.where(lvl["is_trav"], cfv, payoff.sum(-1))
-                trav = lvl["trav"]
-                if trav.numel():
-                    regret = ((payoff[trav] - cfv[trav].view(-1, 1)) * lvl["legal"][trav]).float()
-                    rows = self._encode_saved(lvl["trav_state"], lvl["trav_history"])
-                    self._advantage_memories[player].add(
-                        info_state=rows, advantage=regret, action=lvl["last_legal"][trav],
-                        iteration=torch.full((trav.numel(),), self._iteration, device=self.device))
-                    if self._record_tree:
-                        lvl["regret"] = regret
-                        if trav.numel() <= 4096:
-                            lvl["rows"] = rows
-            lvl["value"] = value
-            child_values = value
+        for lvl, regret in backward_sweep(levels):
+            trav = lvl["trav"]
+            rows = self._encode_saved(lvl["trav_state"], lvl["trav_history"])
+            self._advantage_memories[player].add(
+                info_state=rows, advantage=regret, action=lvl["last_legal"][trav],
+                iteration=torch.full((trav.numel(),), self._iteration, device=self.device))
+            if self._record_tree:
+                lvl["regret"] = regret
+                if trav.numel() <= 4096:
+                    lvl["rows"] = rows
         nodes = sum(l["m"] for l in levels)
         chance = sum(int(s.stats_device[1]) - b for s, b in zip(self._slabs, stats_before))
         self._environment_steps += nodes + chance        # every recursive call, chance nodes included (:427)

@@ -75,3 +75,45 @@ def test_mlp_initialiser_and_shape():
     before = first.weight.clone()
     net.reset_parameters()
     assert not torch.equal(before, first.weight)
+
+
+def test_backward_sweep_on_a_hand_made_tree():
+    """deep_cfr.py:468-480 on a three-level tree: traverser root with actions {0, 1, 3} all expanded (external
+    sampling), child 0 terminal (+1), child 1 an opponent node whose sampled action leads to a terminal (-2), child 3 a
+    traverser node with legal {2, 5} of which only 5 was sampled (outcome sampling), leading to a terminal (+2)."""
+    from open_spiel_coup_b200.deep_cfr import backward_sweep
+    T, F = True, False
+
+    def legal(*acts):
+        row = torch.zeros(18, dtype=torch.bool)
+        row[list(acts)] = True
+        return row
+
+    def strat(d):
+        row = torch.zeros(18)
+        for a, p in d.items():
+            row[a] = p
+        return row
+
+    l0 = {"m": 1, "terminal": torch.tensor([F]), "ret_p": torch.zeros(1, dtype=torch.float64), "nt": torch.tensor([0]), "children": 3,
+          "strategy": strat({0: 0.5, 1: 0.25, 3: 0.25}).view(1, -1), "legal": legal(0, 1, 3).view(1, -1), "is_trav": torch.tensor([T]),
+          "trav": torch.tensor([0]), "local": torch.tensor([0, 0, 0]), "action": torch.tensor([0, 1, 3])}
+    l1 = {"m": 3, "terminal": torch.tensor([T, F, F]), "ret_p": torch.tensor([1.0, 0.0, 0.0], dtype=torch.float64), "nt": torch.tensor([1, 2]),
+          "children": 2, "strategy": torch.stack([strat({9: 0.7, 10: 0.3}), strat({2: 0.4, 5: 0.6})]),
+          "legal": torch.stack([legal(9, 10), legal(2, 5)]), "is_trav": torch.tensor([F, T]), "trav": torch.tensor([1]),
+          "local": torch.tensor([0, 1]), "action": torch.tensor([10, 5])}
+    l2 = {"m": 2, "terminal": torch.tensor([T, T]), "ret_p": torch.tensor([-2.0, 2.0], dtype=torch.float64), "nt": torch.zeros(0, dtype=torch.long),
+          "children": 0}
+    out = list(backward_sweep([l0, l1, l2]))
+    assert [id(lvl) for lvl, _ in out] == [id(l1), id(l0)]
+    # level 1: opponent passes its sampled child's value through; traverser node: cfv = 0.6 * 2, unsampled action 2 counts as 0
+    np.testing.assert_allclose(l1["value"].numpy(), [1.0, -2.0, 1.2])
+    r1 = out[0][1].numpy()[0]
+    np.testing.assert_allclose(r1[[2, 5]], [0.0 - 1.2, 2.0 - 1.2], rtol=1e-6)
+    assert (np.delete(r1, [2, 5]) == 0).all()
+    # root: cfv = 0.5 * 1 + 0.25 * (-2) + 0.25 * 1.2
+    cfv = 0.5 - 0.5 + 0.3
+    np.testing.assert_allclose(l0["value"].numpy(), [cfv])
+    r0 = out[1][1].numpy()[0]
+    np.testing.assert_allclose(r0[[0, 1, 3]], [1 - cfv, -2 - cfv, 1.2 - cfv], rtol=1e-6)
+    np.testing.assert_allclose(l2["value"].numpy(), [-2.0, 2.0])
