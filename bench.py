@@ -271,6 +271,19 @@ def main():
     value = steps_done / (ms * 1e-3)
     per_launch_s = ms * 1e-3 / K
 
+    # Context for the roofline: what a pure zero-fill of the same output buffer reaches on this GPU right now (the
+    # driver's peak is a COPY, half reads; this path only writes). Not a denominator, just reported beside `frac`.
+    write_only_gbs = None
+    if out is not None and rank == 0:
+        out.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            out.zero_()
+        e1.record()
+        torch.cuda.synchronize()
+        write_only_gbs = out.numel() * out.element_size() * 10 / (e0.elapsed_time(e1) * 1e-3) / 1e9
+
     # Other contracts on the same slab (short runs), reported beside the headline.
     extra = {}
     if not args.no_extra_contracts:
@@ -428,7 +441,9 @@ def main():
             },
             "roofline": {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic(contract), "peak_source": peak_src,
-                         "bytes_per_launch": bytes_per_launch, "launch_ms": per_launch_s * 1e3},
+                         "bytes_per_launch": bytes_per_launch, "launch_ms": per_launch_s * 1e3,
+                         "write_only_fill_gbs": write_only_gbs,
+                         "frac_of_write_only_fill": None if not write_only_gbs else achieved / write_only_gbs},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": ns * S_, "d2h_bytes_per_step": 4 * ns * S_,
                     "steps": Ke, "host_policy_threads": threads, "sub_slabs": S_,
                     "note": "coup_vec_step_host_packed on %d sub-slabs (own stream each): uint8 actions from pinned host memory in, "
