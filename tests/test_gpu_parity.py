@@ -487,14 +487,16 @@ def test_step_host_path():
         assert torch.equal(tensor, ref.information_state_tensor(_lib.PLAYER_CURRENT))
 
 
-def test_step_host_packed_and_host_policy():
+@pytest.mark.parametrize("blocking_sync", [False, True], ids=["spin-wait", "blocking-sync"])
+def test_step_host_packed_and_host_policy(blocking_sync):
     """One-copy host path: the packed step word carries legal mask / current player / done / rewards /
-    returns, and the host-side uniform policy draws exactly what the device sampler draws."""
+    returns, and the host-side uniform policy draws exactly what the device sampler draws. Same results whether the
+    call spins or sleeps (COUP_FLAG_BLOCKING_SYNC) while it waits for the device."""
     import ctypes as C
     n = 5000
     lib = _lib.load()
     seed, offset = 4242, 1 << 20
-    env = CoupVectorEnv(n, seed=seed, auto_reset=True, global_env_offset=offset)
+    env = CoupVectorEnv(n, seed=seed, auto_reset=True, global_env_offset=offset, blocking_sync=blocking_sync)
     ref = CoupVectorEnv(n, seed=seed, auto_reset=True, global_env_offset=offset)
     h_act = torch.empty(n, dtype=torch.uint8).pin_memory()
     h_words = torch.empty(n, dtype=torch.int32).pin_memory()
