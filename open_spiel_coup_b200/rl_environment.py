@@ -91,26 +91,25 @@ class Environment:
     def seed(self, seed=None):
         self._chance_event_sampler.seed(seed)
 
-    def get_time_step(self):
-        """rl_environment.py:219-268."""
-        observations = {"info_state": [], "legal_actions": [], "current_player": [], "serialized_state": []}
-        rewards = []
-        step_type = StepType.LAST if self._state.is_terminal() else StepType.MID
-        self._should_reset = step_type == StepType.LAST
-        cur_rewards = self._state.rewards()
-        for player_id in range(self.num_players):
-            rewards.append(cur_rewards[player_id])
-            observations["info_state"].append(
-                self._state.observation_tensor(player_id) if self._use_observation
-                else self._state.information_state_tensor(player_id))
-            observations["legal_actions"].append(self._state.legal_actions(player_id))
-        observations["current_player"] = self._state.current_player()
-        discounts = self._discounts
-        if step_type == StepType.LAST:
-            discounts = [0. for _ in discounts]
+    def _observations(self):
+        """The `observations` dict of a time step (rl_environment.py:224-262): per player the tensor and the legal
+        actions (empty for the player who is not to move), then the mover and, on request, the serialised state."""
+        state = self._state
+        tensor = state.observation_tensor if self._use_observation else state.information_state_tensor
+        players = range(self.num_players)
+        obs = {"info_state": [tensor(p) for p in players], "legal_actions": [state.legal_actions(p) for p in players],
+               "current_player": state.current_player(), "serialized_state": []}
         if self._include_full_state:
-            observations["serialized_state"] = spiel.serialize_game_and_state(self._game, self._state)
-        return TimeStep(observations=observations, rewards=rewards, discounts=discounts, step_type=step_type)
+            obs["serialized_state"] = spiel.serialize_game_and_state(self._game, state)
+        return obs
+
+    def get_time_step(self):
+        """rl_environment.py:219-268: MID, or LAST (discounts zeroed) once the state is terminal."""
+        last = self._state.is_terminal()
+        self._should_reset = last
+        return TimeStep(observations=self._observations(), rewards=list(self._state.rewards()),
+                        discounts=[0.0] * self.num_players if last else self._discounts,
+                        step_type=StepType.LAST if last else StepType.MID)
 
     def _check_legality(self, actions):
         legal_actions = self._state.legal_actions()
@@ -129,20 +128,11 @@ class Environment:
         return self.get_time_step()
 
     def reset(self):
-        """rl_environment.py:324-367."""
+        """rl_environment.py:324-367: a new initial state with its chance nodes resolved; FIRST carries no rewards."""
         self._should_reset = False
         self._state = self._game.new_initial_state()
         self._sample_external_events()
-        observations = {"info_state": [], "legal_actions": [], "current_player": [], "serialized_state": []}
-        for player_id in range(self.num_players):
-            observations["info_state"].append(
-                self._state.observation_tensor(player_id) if self._use_observation
-                else self._state.information_state_tensor(player_id))
-            observations["legal_actions"].append(self._state.legal_actions(player_id))
-        observations["current_player"] = self._state.current_player()
-        if self._include_full_state:
-            observations["serialized_state"] = spiel.serialize_game_and_state(self._game, self._state)
-        return TimeStep(observations=observations, rewards=None, discounts=None, step_type=StepType.FIRST)
+        return TimeStep(observations=self._observations(), rewards=None, discounts=None, step_type=StepType.FIRST)
 
     def _sample_external_events(self):
         """rl_environment.py:369-382."""
