@@ -427,7 +427,7 @@ def main():
         achieved = bytes_per_launch / per_launch_s / 1e9
         kname = ("k_rollout_ws<%s>" if args.fused == "ws" else "k_rollout_tma<%s>") if args.encoder == "staged" else "k_rollout<%s,true>"
         kernel = {"d32": kname % "float", "bf16": kname % "__nv_bfloat16", "d8": kname % "uint8_t",
-                  "env": "k_rollout<float,false>"}[contract]
+                  "env": "k_rollout_env_multi"}[contract]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -451,7 +451,8 @@ def main():
                             "every step; the host policy (coup_host_sample_uniform) picks the next actions from those words; the "
                             "info-state tensor is encoded every step and left in HBM for the on-device consumer" % S_},
             "e2e_tensor_to_host": e2e_host_tensor,
-            "gpu_launches": K,
+            # one launch per step with a tensor contract; the env-only contract runs up to 64 steps per launch
+            "gpu_launches": K if contract != "env" else -(-K // 64),
             "clocks": clocks,
             "contracts": extra,
             "selfplay": selfplay,

@@ -94,6 +94,15 @@ int rollout_typed(coup_vec_env* env, int n_steps, int encode_player, void* d_out
     if (err != cudaSuccess) return fail(COUP_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(err));
   }
   const uint32_t n_batches = env->A.n / kWsBatch, tail_base = n_batches * kWsBatch;
+  if (encode_player < 0) {   // no tensor: up to 64 steps per launch, the env stays in registers in between
+    for (int done = 0; done < n_steps;) {
+      const int k = std::min(64, n_steps - done);
+      k_rollout_env_multi<<<grid, kBlockThreads, 0, st>>>(env->A, env->step_counter, k);
+      env->step_counter += static_cast<uint64_t>(k);
+      done += k;
+    }
+    return launch_status("k_rollout_env_multi");
+  }
   for (int i = 0; i < n_steps; ++i) {
     if (specialised) {
       // persistent, warp-specialised: one CTA per SM over the full 256-env batches, then the ragged tail (if any)

@@ -935,6 +935,31 @@ k_rollout(EnvArrays A, uint64_t step, int player_sel, T* __restrict__ out, uint3
   st.flush(A.stats);
 }
 
+// Env-only rollout of `n_steps` steps in ONE launch: envs are independent, so a thread keeps its env in registers across
+// steps (one 16-byte load and store, one set of outputs, one launch instead of n_steps of each); the history row and
+// the statistics are updated every step exactly as k_rollout<T, false> does, and step k uses Philox counter step + k.
+__global__ void __launch_bounds__(kBlockThreads, 5)
+k_rollout_env_multi(EnvArrays A, uint64_t step, int n_steps) {
+  __shared__ uint32_t s_stats[COUP_STATS_LEN];
+  BlockStats st;
+  st.init(s_stats);
+  const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = e < A.n;
+  Env s = {};
+  uint32_t* hist_row = A.history + static_cast<size_t>(active ? e : 0) * kHistoryWords;
+  if (active) s = load_env(A.state + e);
+  StepResult r = {};
+  for (int k = 0; k < n_steps; ++k) {
+    if (active) r = step_env<true>(s, hist_row, 0, nullptr, A, e, step + static_cast<uint64_t>(k));
+    account(st, r, active);
+  }
+  if (active) {
+    store_env(A.state + e, s);
+    write_outputs(A, e, r);
+  }
+  st.flush(A.stats);
+}
+
 // Same fused step, with the staged (shared memory + bulk store) encoder.
 template <typename T>
 __global__ void __launch_bounds__(kTmaBlockThreads, 2)
