@@ -69,35 +69,52 @@ __attribute__((target("avx2"))) void philox_x_avx2(uint64_t seed, uint64_t env, 
   for (; i < count; ++i) out[i] = philox_x_scalar(seed, env + i, step);
 }
 
-__attribute__((target("avx512f"))) inline __m512i mulhi_epu32_512(__m512i a, __m512i b) {
-  const __m512i even = _mm512_mul_epu32(a, b);
-  const __m512i odd = _mm512_mul_epu32(_mm512_srli_epi64(a, 32), _mm512_srli_epi64(b, 32));
-  return _mm512_mask_blend_epi32(0xAAAA, _mm512_srli_epi64(even, 32), odd);
+// 32x32 -> 64-bit products of 16 lanes from two VPMULUDQ (even and odd lanes); hi and lo halves are both taken from
+// them (VPMULLD is a slow two-uop instruction on every AVX-512 core).
+struct Mul512 {
+  __m512i hi, lo;
+};
+__attribute__((target("avx512f"))) inline Mul512 mul_hilo_512(__m512i m, __m512i c) {
+  const __m512i even = _mm512_mul_epu32(m, c);
+  const __m512i odd = _mm512_mul_epu32(m, _mm512_srli_epi64(c, 32));   // m is a broadcast constant: same in odd lanes
+  Mul512 r;
+  r.hi = _mm512_mask_blend_epi32(0xAAAA, _mm512_srli_epi64(even, 32), odd);
+  r.lo = _mm512_mask_blend_epi32(0xAAAA, even, _mm512_slli_epi64(odd, 32));
+  return r;
 }
 
-// Sixteen consecutive envs per iteration (same stream as the scalar and AVX2 versions).
+// 32 consecutive envs per iteration: two independent 16-lane Philox states interleaved, so that the multiplier
+// pipeline is busy while the other state's round result is still in flight (same stream as the scalar version).
 __attribute__((target("avx512f"))) void philox_x_avx512(uint64_t seed, uint64_t env, uint64_t step, uint32_t count, uint32_t* out) {
   const __m512i m0 = _mm512_set1_epi32(static_cast<int>(kM0)), m1 = _mm512_set1_epi32(static_cast<int>(kM1));
   const __m512i w0 = _mm512_set1_epi32(static_cast<int>(kW0)), w1 = _mm512_set1_epi32(static_cast<int>(kW1));
   const __m512i iota = _mm512_setr_epi32(0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15);
+  const __m512i s0 = _mm512_set1_epi32(static_cast<int>(static_cast<uint32_t>(step)));
+  const __m512i s1 = _mm512_set1_epi32(static_cast<int>(static_cast<uint32_t>(step >> 32)));
+  const __m512i s3 = _mm512_set1_epi32(static_cast<int>(static_cast<uint32_t>(seed >> 32)));
   uint32_t i = 0;
-  for (; i + 16 <= count; i += 16) {
-    __m512i c0 = _mm512_set1_epi32(static_cast<int>(static_cast<uint32_t>(step)));
-    __m512i c1 = _mm512_set1_epi32(static_cast<int>(static_cast<uint32_t>(step >> 32)));
-    __m512i c2 = _mm512_setzero_si512();
-    __m512i c3 = _mm512_set1_epi32(static_cast<int>(static_cast<uint32_t>(seed >> 32)));
-    __m512i k0 = _mm512_add_epi32(_mm512_set1_epi32(static_cast<int>(static_cast<uint32_t>(env + i))), iota);
-    __m512i k1 = _mm512_set1_epi32(static_cast<int>(static_cast<uint32_t>((env + i) >> 32) ^ static_cast<uint32_t>(seed)));
+  for (; i + 32 <= count; i += 32) {
+    __m512i a0 = s0, a1 = s1, a2 = _mm512_setzero_si512(), a3 = s3;
+    __m512i b0 = s0, b1 = s1, b2 = _mm512_setzero_si512(), b3 = s3;
+    __m512i ka0 = _mm512_add_epi32(_mm512_set1_epi32(static_cast<int>(static_cast<uint32_t>(env + i))), iota);
+    __m512i kb0 = _mm512_add_epi32(_mm512_set1_epi32(static_cast<int>(static_cast<uint32_t>(env + i + 16))), iota);
+    __m512i ka1 = _mm512_set1_epi32(static_cast<int>(static_cast<uint32_t>((env + i) >> 32) ^ static_cast<uint32_t>(seed)));
+    __m512i kb1 = _mm512_set1_epi32(static_cast<int>(static_cast<uint32_t>((env + i + 16) >> 32) ^ static_cast<uint32_t>(seed)));
+#pragma GCC unroll 10
     for (int r = 0; r < 10; ++r) {
-      const __m512i hi0 = mulhi_epu32_512(m0, c0), lo0 = _mm512_mullo_epi32(m0, c0);
-      const __m512i hi1 = mulhi_epu32_512(m1, c2), lo1 = _mm512_mullo_epi32(m1, c2);
-      const __m512i n0 = _mm512_xor_si512(_mm512_xor_si512(hi1, c1), k0);
-      const __m512i n2 = _mm512_xor_si512(_mm512_xor_si512(hi0, c3), k1);
-      c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
-      k0 = _mm512_add_epi32(k0, w0);
-      k1 = _mm512_add_epi32(k1, w1);
+      const Mul512 pa0 = mul_hilo_512(m0, a0), pa1 = mul_hilo_512(m1, a2);
+      const Mul512 pb0 = mul_hilo_512(m0, b0), pb1 = mul_hilo_512(m1, b2);
+      a0 = _mm512_xor_si512(_mm512_xor_si512(pa1.hi, a1), ka0);
+      a2 = _mm512_xor_si512(_mm512_xor_si512(pa0.hi, a3), ka1);
+      a1 = pa1.lo; a3 = pa0.lo;
+      b0 = _mm512_xor_si512(_mm512_xor_si512(pb1.hi, b1), kb0);
+      b2 = _mm512_xor_si512(_mm512_xor_si512(pb0.hi, b3), kb1);
+      b1 = pb1.lo; b3 = pb0.lo;
+      ka0 = _mm512_add_epi32(ka0, w0); ka1 = _mm512_add_epi32(ka1, w1);
+      kb0 = _mm512_add_epi32(kb0, w0); kb1 = _mm512_add_epi32(kb1, w1);
     }
-    _mm512_storeu_si512(out + i, c0);
+    _mm512_storeu_si512(out + i, a0);
+    _mm512_storeu_si512(out + i + 16, b0);
   }
   for (; i < count; ++i) out[i] = philox_x_scalar(seed, env + i, step);
 }
