@@ -8,6 +8,8 @@
 #include <atomic>
 #include <condition_variable>
 #include <cstdint>
+#include <cstdlib>
+#include <string>
 #include <functional>
 #include <mutex>
 #include <thread>
@@ -36,10 +38,16 @@ inline uint32_t philox_x_scalar(uint64_t seed, uint64_t env, uint64_t step) {
   return c0;
 }
 
-__attribute__((target("avx2"))) inline __m256i mulhi_epu32(__m256i a, __m256i b) {
-  const __m256i even = _mm256_mul_epu32(a, b);
-  const __m256i odd = _mm256_mul_epu32(_mm256_srli_epi64(a, 32), _mm256_srli_epi64(b, 32));
-  return _mm256_blend_epi32(_mm256_srli_epi64(even, 32), odd, 0xAA);
+struct Mul256 {
+  __m256i hi, lo;
+};
+__attribute__((target("avx2"))) inline Mul256 mul_hilo_256(__m256i m, __m256i c) {   // see mul_hilo_512
+  const __m256i even = _mm256_mul_epu32(m, c);
+  const __m256i odd = _mm256_mul_epu32(m, _mm256_srli_epi64(c, 32));
+  Mul256 r;
+  r.hi = _mm256_blend_epi32(_mm256_srli_epi64(even, 32), odd, 0xAA);
+  r.lo = _mm256_blend_epi32(even, _mm256_slli_epi64(odd, 32), 0xAA);
+  return r;
 }
 
 // Eight consecutive envs per iteration. Requires that env lo does not wrap inside [env, env+count).
@@ -56,11 +64,10 @@ __attribute__((target("avx2"))) void philox_x_avx2(uint64_t seed, uint64_t env, 
     __m256i k0 = _mm256_add_epi32(_mm256_set1_epi32(static_cast<int>(static_cast<uint32_t>(env + i))), iota);
     __m256i k1 = _mm256_set1_epi32(static_cast<int>(static_cast<uint32_t>((env + i) >> 32) ^ static_cast<uint32_t>(seed)));
     for (int r = 0; r < 10; ++r) {
-      const __m256i hi0 = mulhi_epu32(m0, c0), lo0 = _mm256_mullo_epi32(m0, c0);
-      const __m256i hi1 = mulhi_epu32(m1, c2), lo1 = _mm256_mullo_epi32(m1, c2);
-      const __m256i n0 = _mm256_xor_si256(_mm256_xor_si256(hi1, c1), k0);
-      const __m256i n2 = _mm256_xor_si256(_mm256_xor_si256(hi0, c3), k1);
-      c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+      const Mul256 p0 = mul_hilo_256(m0, c0), p1 = mul_hilo_256(m1, c2);
+      c0 = _mm256_xor_si256(_mm256_xor_si256(p1.hi, c1), k0);
+      c2 = _mm256_xor_si256(_mm256_xor_si256(p0.hi, c3), k1);
+      c1 = p1.lo; c3 = p0.lo;
       k0 = _mm256_add_epi32(k0, w0);
       k1 = _mm256_add_epi32(k1, w1);
     }
@@ -247,8 +254,15 @@ class HostPool {
 
 void sample_uniform(const uint32_t* words, uint32_t n, uint64_t seed, uint64_t global_env_offset, uint64_t step,
                     uint8_t* actions, int threads) {
-  static const CpuFeatures cpu = {static_cast<bool>(__builtin_cpu_supports("avx2")), static_cast<bool>(__builtin_cpu_supports("avx512f")),
-                                  static_cast<bool>(__builtin_cpu_supports("bmi2")) && static_cast<bool>(__builtin_cpu_supports("popcnt"))};
+  static const CpuFeatures detected = {static_cast<bool>(__builtin_cpu_supports("avx2")), static_cast<bool>(__builtin_cpu_supports("avx512f")),
+                                       static_cast<bool>(__builtin_cpu_supports("bmi2")) && static_cast<bool>(__builtin_cpu_supports("popcnt"))};
+  CpuFeatures cpu = detected;
+  // COUP_B200_HOST_ISA=avx2|scalar restricts the vector paths (tests run every path the host has; all give the same stream)
+  if (const char* isa = std::getenv("COUP_B200_HOST_ISA")) {
+    const std::string want(isa);
+    if (want == "avx2") cpu.avx512 = false;
+    if (want == "scalar") cpu.avx512 = cpu.avx2 = cpu.bmi2 = false;
+  }
   constexpr uint32_t kTile = 2048;
   const uint32_t tiles = (n + kTile - 1) / kTile;
   HostPool::instance().parallel_for(tiles, threads, [=](uint32_t t) {

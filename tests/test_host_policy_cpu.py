@@ -38,9 +38,14 @@ def _expected(words, seed, offset, step):
     return out
 
 
+@pytest.mark.parametrize("isa", ["native", "avx2", "scalar"])
 @pytest.mark.parametrize("n,offset,threads", [(5000, 0, 1), (5000, 1 << 20, 3), (4099, (1 << 32) - 1000, 2), (17, (5 << 32) + 7, 1),
                                               (40000, (1 << 40) + 123, 8)])
-def test_host_sampler_equals_numpy_statement(n, offset, threads):
+def test_host_sampler_equals_numpy_statement(n, offset, threads, isa, monkeypatch):
+    if isa == "native":
+        monkeypatch.delenv("COUP_B200_HOST_ISA", raising=False)
+    else:
+        monkeypatch.setenv("COUP_B200_HOST_ISA", isa)          # read on every call: restricts the vector paths
     lib = _lib.load()
     rng = np.random.default_rng(n)
     words = rng.integers(0, 1 << 18, size=n).astype(np.uint32)
