@@ -20,10 +20,9 @@ All episodes of one iteration read the table as it was when the iteration starte
 probabilities, which the reference multiplies into `opp_reach` and `sample_reach` (outcome_sampling_mccfr.py:73-77),
 are recomputed from the deal codes the step appended to the history and the deck it left behind.
 """
-import numpy as np
 import torch
 
-from ._lib import INFO_STATE_SIZE, NUM_DISTINCT_ACTIONS, PLAYER_CURRENT
+from ._lib import NUM_DISTINCT_ACTIONS, PLAYER_CURRENT
 from .deep_cfr import _legal_bool
 from .vector_env import CoupVectorEnv
 

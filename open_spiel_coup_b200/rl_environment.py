@@ -12,7 +12,6 @@ import enum
 import numpy as np
 
 from . import spiel
-from ._lib import CHANCE_PLAYER_ID
 
 SIMULTANEOUS_PLAYER_ID = -2   # pyspiel.PlayerId.SIMULTANEOUS (spiel_globals.h:30)
 
