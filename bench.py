@@ -69,6 +69,8 @@ def parse_args():
     ap.add_argument("--blocking-sync", action="store_true", help="host-buffer calls sleep instead of spinning while they wait")
     ap.add_argument("--fused", default="ws", choices=["ws", "cta"],
                     help="fused rollout kernel: persistent warp-specialised (rules warps + encoder warps), or one CTA per 256 envs")
+    ap.add_argument("--ring", type=int, default=1 << 18,
+                    help="capacity (records, power of two) of the finished-episode ring the timed kernels append to; 0 = off")
     ap.add_argument("--encoder", default="staged", choices=["staged", "plain"],
                     help="info-state encoder: shared-memory staging + bulk (TMA) stores, or per-lane vector stores")
     return ap.parse_args()
@@ -232,7 +234,8 @@ def main():
     contract = args.contract
     torch_dtype = {"d32": torch.float32, "bf16": torch.bfloat16, "d8": torch.uint8, "env": None}[contract]
     env = CoupVectorEnv(n, seed=args.seed, device=local, global_env_offset=slab_offset, auto_reset=True,
-                        plain_store_encoder=(args.encoder == "plain"), warp_specialised=(args.fused == "ws"))
+                        plain_store_encoder=(args.encoder == "plain"), warp_specialised=(args.fused == "ws"),
+                        finished_ring=args.ring)
     out = None if torch_dtype is None else torch.empty((n, 2492), dtype=torch_dtype, device=dev)
     sel = None if out is None else _lib.PLAYER_CURRENT
 
@@ -331,7 +334,8 @@ def main():
     slabs = []
     for i in range(S_):
         ev = CoupVectorEnv(ns, seed=args.seed, device=local, global_env_offset=slab_offset + i * ns, auto_reset=True,
-                           plain_store_encoder=(args.encoder == "plain"), blocking_sync=args.blocking_sync)
+                           plain_store_encoder=(args.encoder == "plain"), blocking_sync=args.blocking_sync,
+                           finished_ring=max(0, args.ring // S_))
         ev.rollout(100)
         h_act = torch.empty(ns, dtype=torch.uint8).pin_memory()
         h_words = torch.empty(ns, dtype=torch.int32).pin_memory()
@@ -355,6 +359,7 @@ def main():
     barrier()
     t0 = time.perf_counter()
     e2e_steps(Ke)
+    torch.cuda.synchronize(dev)     # the encoders of the last step may still be running on the sub-slab streams
     barrier()
     e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
     if world > 1:
@@ -434,7 +439,9 @@ def main():
             "dtype": CONTRACT_DTYPE[contract], "data": "synthetic",
             "config": {
                 "workload": workload_text(contract),
-                "envs_per_gpu": n, "contract": contract, "bytes_per_step": BYTES_PER_STEP[contract], "encoder": args.encoder, "fused_kernel": args.fused,
+                "envs_per_gpu": n, "contract": contract,
+                "finished_ring": ("every finished episode's action+chance log and terminal state appended to a %d-record device ring "
+                                  "inside the timed kernels (auto-reset re-deals in place)" % args.ring) if args.ring else "off", "bytes_per_step": BYTES_PER_STEP[contract], "encoder": args.encoder, "fused_kernel": args.fused,
                 "parallelism": f"env-slab x{world} (no data-path collective; NCCL all-reduce of the stats vector only)",
                 "l2": "per-step working set (%.2f GB written + 80 MB state/history) >> 126 MB L2, no flush needed" % (bytes_per_launch / 1e9)
                       if contract != "env" else "state+history 80 MiB/GPU is L2-resident by design (env-only contract)",

@@ -66,6 +66,11 @@ enum {
  */
 #define COUP_STATE_WORDS 4
 #define COUP_HISTORY_WORDS 16
+/* Packed observation record (finished-episode ring, compact replay / reservoir records): uint32[24], 16-byte aligned:
+ *   [0,16) history words   [16,20) state words   [20,24) meta words (meaning depends on who wrote the record).
+ * Everything both tensor observers can show about a state is a function of these 80 bytes + the observer id, so a record
+ * decodes into the same 2492-element row the dense encoder would have written (coup_records_information_state_tensor). */
+#define COUP_RECORD_WORDS 24
 
 /* ---- options ----------------------------------------------------------------------------------- */
 enum {
@@ -99,7 +104,8 @@ enum {
   COUP_PLAYER_0 = 0,
   COUP_PLAYER_1 = 1,
   COUP_PLAYER_CURRENT = 2, /* cur_player_move_ of each env (benchmark_game.cc:53-60 protocol) */
-  COUP_PLAYER_BOTH = 3     /* rows [env][player] (rl_environment.get_time_step, rl_environment.py:243-249) */
+  COUP_PLAYER_BOTH = 3,    /* rows [env][player] (rl_environment.get_time_step, rl_environment.py:243-249) */
+  COUP_PLAYER_FROM_RECORD = 4 /* record decoders only: the seat stored in bit 31 of meta word 1 of each record */
 };
 /* Element type of encoded tensors. Values are 0, 1 and coin counts <= 12: exact in all three. */
 enum { COUP_DTYPE_F32 = 0, COUP_DTYPE_U8 = 1, COUP_DTYPE_BF16 = 2 };
@@ -246,9 +252,15 @@ int coup_vec_legal_actions_mask(coup_vec_env* env, uint8_t* d_out, void* stream)
 
 /* ---- tensors (CoupState::InformationStateTensor / ObservationTensor, coup.cc:1044-1056, i.e.
  * CoupObserver::WriteTensor coup.cc:248-287). d_out: dtype[rows][2492 or 98] on the device, fully
- * overwritten (the reference's ContiguousAllocator zero-fills first, observer.h:175-177). */
+ * overwritten (the reference's ContiguousAllocator zero-fills first, observer.h:175-177).
+ * Alignment: every tensor output (here, in the rollout calls and in the record decoders) must be aligned to the
+ * four-element store unit of its dtype -- 16 bytes for f32, 8 for bf16, 4 for u8 -- else COUP_ERR_INVALID_ARG. Outputs
+ * that are also 16-byte aligned (any fresh allocation) get the bulk-store encoder; others the plain-store one. */
 int coup_vec_information_state_tensor(coup_vec_env* env, int player, int dtype, void* d_out, void* stream);
 int coup_vec_observation_tensor(coup_vec_env* env, int player, int dtype, void* d_out, void* stream);
+/* Observation rows of a SUBSET of envs (row i, or rows 2i, 2i+1, describe env d_env_ids[i]). */
+int coup_vec_observation_tensor_gather(coup_vec_env* env, const uint32_t* d_env_ids, uint32_t count, int player, int dtype,
+                                       void* d_out, void* stream);
 /* Same tensors with a padded row stride (in elements, a multiple of 4, >= 2492): elements
  * [2492, row_stride) of every row are written as zeros. row_stride 2496 keeps the consumer's first GEMM on
  * its aligned (fast) path: K = 2492 is not a multiple of 8 and costs a bf16 cuBLAS GEMM 5.6x on B200. */
@@ -261,6 +273,45 @@ int coup_vec_rollout_strided(coup_vec_env* env, int n_steps, int encode_player, 
  * envs that just finished (what every agent is stepped with at episode end, coup_experiments/scripts/nfsp.py:141-143). */
 int coup_vec_information_state_tensor_gather(coup_vec_env* env, const uint32_t* d_env_ids, uint32_t count, int player,
                                              int dtype, void* d_out, uint32_t row_stride, void* stream);
+
+/* ---- finished episodes (the `unreset_time_steps` of vector_env.SyncVectorEnv.step, python/vector_env.py:52-66, and
+ * north_star's "every GPU trajectory's action and chance log", in the auto-reset mode that re-deals finished envs in
+ * place). When enabled, every step/rollout kernel appends one packed record per episode that ends -- BEFORE the env is
+ * re-dealt -- to a device ring of `capacity_records` (a power of two; 0 disables and frees) records:
+ *   [0,16)  the finished episode's history (move i = 5-bit code at word i/6, bit 5*(i%6), as in coup_vec_history)
+ *   [16,20) the TERMINAL packed state (layout above: Returns() = face-up counts, Rewards()[0] in w3)
+ *   [20] env slot  [21] move_number_ | (Returns()[0]+2)<<8 | (Rewards()[0]+2)<<12 | truncated<<16
+ *   [22],[23] low / high half of the Philox step counter of the step that ended the episode.
+ * Slots are handed out by one atomic cursor, so records of one step appear in unspecified order. Works with and without
+ * COUP_FLAG_AUTO_RESET (without it an episode is appended once, when it ends). Not part of snapshots.
+ *   coup_vec_finished_ring / _ctrl: device pointers. ctrl is uint64[4]: [0] records ever appended, [1] the value of [0]
+ *     when the most recent step/rollout call began, i.e. that call's episodes are ring positions [ctrl[1], ctrl[0]).
+ *   coup_vec_finished_drain: copies the records not handed out yet (oldest first, at most max_records) to `out_records`
+ *     (host or device memory) and advances the consumer cursor; *h_dropped_out = records lost so far because the
+ *     producer lapped the consumer. Synchronises the stream.
+ *   coup_vec_finished_information_state_tensor: the terminal info-state rows (what every agent is stepped with at
+ *     episode end, coup_experiments/scripts/nfsp.py:141-143; python/algorithms/dqn.py:223-246) of the episodes that
+ *     ended in the most recent step/rollout call, in ring order: row i (rows 2i, 2i+1 for COUP_PLAYER_BOTH) describes
+ *     the i-th of them, d_env_ids_out[i] (may be NULL) is its env slot, *d_count_out (device, may be NULL) their number,
+ *     clipped to max_episodes. The count never visits the host: surplus blocks of the launch exit. */
+int coup_vec_finished_ring_enable(coup_vec_env* env, uint32_t capacity_records);
+const uint32_t* coup_vec_finished_ring(const coup_vec_env* env);
+const uint64_t* coup_vec_finished_ring_ctrl(const coup_vec_env* env);
+uint32_t coup_vec_finished_ring_capacity(const coup_vec_env* env);
+int coup_vec_finished_drain(coup_vec_env* env, void* out_records, uint32_t max_records, uint32_t* h_count_out,
+                            uint64_t* h_dropped_out, void* stream);
+int coup_vec_finished_information_state_tensor(coup_vec_env* env, int player, int dtype, void* d_out, uint32_t row_stride,
+                                               uint32_t max_episodes, uint32_t* d_env_ids_out, uint32_t* d_count_out,
+                                               void* stream);
+int coup_vec_finished_observation_tensor(coup_vec_env* env, int player, int dtype, void* d_out, uint32_t max_episodes,
+                                         uint32_t* d_env_ids_out, uint32_t* d_count_out, void* stream);
+/* Info-state rows of ANY array of packed records on the handle's device: output row i decodes record d_indices[i]
+ * (d_indices NULL: record i). `player` may be COUP_PLAYER_FROM_RECORD. This is how compact replay / reservoir records
+ * (80 bytes instead of a 2492-element row) turn back into network inputs when a batch is sampled. */
+int coup_records_information_state_tensor(coup_vec_env* env, const uint32_t* d_records, const uint32_t* d_indices,
+                                          uint32_t count, int player, int dtype, void* d_out, uint32_t row_stride, void* stream);
+int coup_records_observation_tensor(coup_vec_env* env, const uint32_t* d_records, const uint32_t* d_indices, uint32_t count,
+                                    int player, int dtype, void* d_out, void* stream);
 
 /* ---- host-buffer convenience path (what a host-driven caller such as rl_environment would use):
  * copies uint8[num_envs] actions from (pinned) host memory, steps, optionally encodes the current

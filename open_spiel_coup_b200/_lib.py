@@ -23,13 +23,14 @@ CHANCE_PLAYER_ID = -1
 TERMINAL_PLAYER_ID = -4
 STATE_WORDS = 4
 HISTORY_WORDS = 16
+RECORD_WORDS = 24
 
 OK, ERR_INVALID_ARG, ERR_CUDA, ERR_NO_DEVICE, ERR_ILLEGAL_ACTION = 0, 1, 2, 3, 4
 FLAG_AUTO_RESET = 1
 FLAG_PLAIN_STORE_ENCODER = 2
 FLAG_NO_WARP_SPECIALISATION = 4
 FLAG_BLOCKING_SYNC = 8
-PLAYER_0, PLAYER_1, PLAYER_CURRENT, PLAYER_BOTH = 0, 1, 2, 3
+PLAYER_0, PLAYER_1, PLAYER_CURRENT, PLAYER_BOTH, PLAYER_FROM_RECORD = 0, 1, 2, 3, 4
 DTYPE_F32, DTYPE_U8, DTYPE_BF16 = 0, 1, 2
 STAT_DECISION_STEPS, STAT_CHANCE_MOVES, STAT_EPISODES, STAT_TRUNCATED = 0, 1, 2, 3
 STAT_EPISODE_MOVES, STAT_ILLEGAL, STAT_RETURN_HIST, STAT_LEGAL_HIST, STATS_LEN = 4, 5, 8, 16, 32
@@ -45,6 +46,9 @@ EXPORTED_SYMBOLS = [
     "coup_vec_information_state_tensor", "coup_vec_observation_tensor",
     "coup_vec_information_state_tensor_strided", "coup_vec_rollout_strided", "coup_vec_information_state_tensor_gather", "coup_vec_step_host", "coup_vec_step_host_packed",
     "coup_host_sample_uniform", "coup_vec_stats", "coup_vec_stats_device", "coup_vec_clear_stats", "coup_vec_check_errors",
+    "coup_vec_finished_ring_enable", "coup_vec_finished_ring", "coup_vec_finished_ring_ctrl", "coup_vec_finished_ring_capacity",
+    "coup_vec_finished_drain", "coup_vec_finished_information_state_tensor", "coup_records_information_state_tensor",
+    "coup_vec_finished_observation_tensor", "coup_records_observation_tensor", "coup_vec_observation_tensor_gather",
     "coup_tensor_row_hash", "coup_vec_snapshot_size", "coup_vec_snapshot", "coup_vec_restore", "coup_vec_step_counter", "coup_vec_set_step_counter",
 ]
 
@@ -104,10 +108,20 @@ def load():
     lib.coup_vec_rollout_incremental.argtypes = [vp, C.c_int, C.c_int, vp, C.c_uint32, vp]
     lib.coup_vec_rollout.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp]
     for name in ("coup_vec_legal_mask", "coup_vec_current_player", "coup_vec_done", "coup_vec_rewards",
-                 "coup_vec_returns", "coup_vec_state", "coup_vec_history", "coup_vec_stats_device", "coup_vec_step_word"):
+                 "coup_vec_returns", "coup_vec_state", "coup_vec_history", "coup_vec_stats_device", "coup_vec_step_word",
+                 "coup_vec_finished_ring", "coup_vec_finished_ring_ctrl"):
         getattr(lib, name).argtypes = [vp]
         getattr(lib, name).restype = vp
     lib.coup_vec_legal_actions_mask.argtypes = [vp, vp, vp]
+    lib.coup_vec_finished_ring_enable.argtypes = [vp, C.c_uint32]
+    lib.coup_vec_finished_ring_capacity.argtypes = [vp]
+    lib.coup_vec_finished_ring_capacity.restype = C.c_uint32
+    lib.coup_vec_finished_drain.argtypes = [vp, vp, C.c_uint32, vp, vp, vp]
+    lib.coup_vec_finished_information_state_tensor.argtypes = [vp, C.c_int, C.c_int, vp, C.c_uint32, C.c_uint32, vp, vp, vp]
+    lib.coup_vec_finished_observation_tensor.argtypes = [vp, C.c_int, C.c_int, vp, C.c_uint32, vp, vp, vp]
+    lib.coup_records_observation_tensor.argtypes = [vp, vp, vp, C.c_uint32, C.c_int, C.c_int, vp, vp]
+    lib.coup_vec_observation_tensor_gather.argtypes = [vp, vp, C.c_uint32, C.c_int, C.c_int, vp, vp]
+    lib.coup_records_information_state_tensor.argtypes = [vp, vp, vp, C.c_uint32, C.c_int, C.c_int, vp, C.c_uint32, vp]
     lib.coup_vec_information_state_tensor.argtypes = [vp, C.c_int, C.c_int, vp, vp]
     lib.coup_vec_information_state_tensor_strided.argtypes = [vp, C.c_int, C.c_int, vp, C.c_uint32, vp]
     lib.coup_vec_information_state_tensor_gather.argtypes = [vp, vp, C.c_uint32, C.c_int, C.c_int, vp, C.c_uint32, vp]

@@ -7,6 +7,7 @@
 #include <cstring>
 #include <new>
 #include <algorithm>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -25,9 +26,11 @@ struct coup_vec_env {
   uint8_t* d_actions;   // staging for coup_vec_step_host
   uint32_t* d_scratch;  // [4]: id / illegal flag of the single-env host accessors
   float* d_row;         // [2 * 2496]: one env's info-state rows
-  float* d_obs_all;     // [n][2][98], allocated on first use
   cudaEvent_t host_outputs_ready;
   uint64_t step_counter;
+  uint64_t ring_tail;       // first ring record coup_vec_finished_drain has not handed out yet
+  uint64_t ring_dropped;    // records overwritten before they were drained
+  std::mutex single_env_mutex;   // serialises the coup_env_* accessors (they share d_scratch / d_row)
 };
 
 namespace {
@@ -74,15 +77,35 @@ bool valid_dtype(int d) { return d == COUP_DTYPE_F32 || d == COUP_DTYPE_U8 || d 
 
 // The staged (bulk-store) encoder needs row groups that are multiples of 16 bytes: contiguous rows
 // (stride 2492) or the GEMM-friendly padded stride 2496. Other strides use the plain-store encoder.
-bool use_staged_encoder(const coup_vec_env* env, uint32_t stride) {
-  return (env->opts.flags & COUP_FLAG_PLAIN_STORE_ENCODER) == 0 && (stride == COUP_INFO_STATE_SIZE || stride == 2496u);
+// Bulk stores also need a 16-byte aligned destination: a torch view such as out[1:] of a uint8 tensor (2492-byte rows) is
+// not, and a misaligned cp.async.bulk is a sticky fault. Such outputs take the plain-store encoder, which needs only the
+// alignment of its four-element store unit (16 / 8 / 4 bytes for f32 / bf16 / u8); below that the call is rejected.
+bool use_staged_encoder(const coup_vec_env* env, uint32_t stride, const void* d_out) {
+  return (env->opts.flags & COUP_FLAG_PLAIN_STORE_ENCODER) == 0 && (stride == COUP_INFO_STATE_SIZE || stride == 2496u) &&
+         reinterpret_cast<uintptr_t>(d_out) % 16u == 0;
 }
 bool valid_stride(uint32_t stride) { return stride >= COUP_INFO_STATE_SIZE && stride % 4u == 0 && stride <= 4096u; }
+size_t unit_bytes(int dtype) { return dtype == COUP_DTYPE_F32 ? 16u : dtype == COUP_DTYPE_BF16 ? 8u : 4u; }
+bool aligned_for(int dtype, const void* p) { return reinterpret_cast<uintptr_t>(p) % unit_bytes(dtype) == 0; }
+const char* kMisaligned = "tensor output must be aligned to 16 (f32) / 8 (bf16) / 4 (u8) bytes";
+
+// Device that owns a device pointer (for the entry points that take no handle).
+int device_of(const void* p) {
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) { cudaGetLastError(); return -1; }
+  return attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged ? attr.device : -1;
+}
+
+// In front of every step/rollout launch: k_step_prologue snapshots the ring cursor and re-arms the batch counter.
+void step_prologue(coup_vec_env* env, bool batch_counter, cudaStream_t st) {
+  if (env->A.ring != nullptr || batch_counter)
+    k_step_prologue<<<1, 32, 0, st>>>(env->A.ring_ctrl, batch_counter ? env->d_scratch + 2 : nullptr);
+}
 
 template <typename T>
 int rollout_typed(coup_vec_env* env, int n_steps, int encode_player, void* d_out, uint32_t stride, cudaStream_t st) {
   const unsigned grid = blocks_for(env->A.n);
-  const bool staged = encode_player >= 0 && use_staged_encoder(env, stride);
+  const bool staged = encode_player >= 0 && use_staged_encoder(env, stride, d_out);
   const bool specialised = staged && (env->opts.flags & COUP_FLAG_NO_WARP_SPECIALISATION) == 0 && env->A.n >= kWsBatch;
   int sms = 0;
   if (staged) {
@@ -97,6 +120,7 @@ int rollout_typed(coup_vec_env* env, int n_steps, int encode_player, void* d_out
   if (encode_player < 0) {   // no tensor: up to 64 steps per launch, the env stays in registers in between
     for (int done = 0; done < n_steps;) {
       const int k = std::min(64, n_steps - done);
+      step_prologue(env, false, st);
       k_rollout_env_multi<<<grid, kBlockThreads, 0, st>>>(env->A, env->step_counter, k);
       env->step_counter += static_cast<uint64_t>(k);
       done += k;
@@ -106,15 +130,17 @@ int rollout_typed(coup_vec_env* env, int n_steps, int encode_player, void* d_out
   for (int i = 0; i < n_steps; ++i) {
     if (specialised) {
       // persistent, warp-specialised: one CTA per SM over the full 256-env batches, then the ragged tail (if any)
-      CUDA_TRY(cudaMemsetAsync(env->d_scratch + 2, 0, sizeof(uint32_t), st));   // the dynamic batch counter
+      step_prologue(env, true, st);   // also zeroes the dynamic batch counter
       k_rollout_ws<T><<<std::min<unsigned>(sms, n_batches), kWsThreads, kWsSmemBytes, st>>>(
           env->A, env->step_counter, encode_player, static_cast<T*>(d_out), stride, n_batches, env->d_scratch + 2);
       if (tail_base < env->A.n)
         k_rollout_tma<T><<<1, kTmaBlockThreads, kTmaSmemBytes, st>>>(env->A, env->step_counter, encode_player,
                                                                       static_cast<T*>(d_out), stride, tail_base);
     } else if (staged) {
+      step_prologue(env, false, st);
       k_rollout_tma<T><<<grid, kTmaBlockThreads, kTmaSmemBytes, st>>>(env->A, env->step_counter, encode_player, static_cast<T*>(d_out), stride, 0u);
     } else if (encode_player >= 0) {
+      step_prologue(env, false, st);
       k_rollout<T, true><<<grid, kBlockThreads, 0, st>>>(env->A, env->step_counter, encode_player, static_cast<T*>(d_out), stride);
     } else {
       k_rollout<T, false><<<grid, kBlockThreads, 0, st>>>(env->A, env->step_counter, 0, static_cast<T*>(nullptr), stride);
@@ -124,26 +150,67 @@ int rollout_typed(coup_vec_env* env, int n_steps, int encode_player, void* d_out
   return launch_status("k_rollout");
 }
 
-template <typename T>
-int encode_info_typed(coup_vec_env* env, int player, void* d_out, uint32_t stride, const uint32_t* d_ids, uint32_t count,
-                      cudaStream_t st) {
-  const uint32_t n = d_ids ? count : env->A.n;  // rows to produce (before the x2 of COUP_PLAYER_BOTH)
-  if (n == 0) return COUP_OK;
-  const unsigned grid = (n + 32 * kWarpsPerBlock - 1) / (32 * kWarpsPerBlock);
-  if (use_staged_encoder(env, stride)) {
-    cudaError_t err = cudaFuncSetAttribute(k_encode_info_tma<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmemBytes);
+template <typename T, typename Src>
+int encode_info_typed(coup_vec_env* env, const Src& src, uint32_t max_groups, int player, void* d_out, uint32_t stride,
+                      uint32_t* d_ids_out, uint32_t* d_count_out, cudaStream_t st) {
+  if (max_groups == 0) return COUP_OK;   // rows to produce (before the x2 of COUP_PLAYER_BOTH), an upper bound for ring sources
+  const unsigned grid = (max_groups + 32 * kWarpsPerBlock - 1) / (32 * kWarpsPerBlock);
+  if (use_staged_encoder(env, stride, d_out)) {
+    cudaError_t err = cudaFuncSetAttribute(k_encode_info_tma<T, Src>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmemBytes);
     if (err != cudaSuccess) return fail(COUP_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(err));
-    k_encode_info_tma<T><<<grid, kTmaBlockThreads, kTmaSmemBytes, st>>>(env->A.state, env->A.history, n, player, static_cast<T*>(d_out), stride, d_ids);
+    k_encode_info_tma<T, Src><<<grid, kTmaBlockThreads, kTmaSmemBytes, st>>>(src, player, static_cast<T*>(d_out), stride, d_ids_out, d_count_out);
   } else {
-    k_encode_info<T><<<grid, kBlockThreads, 0, st>>>(env->A.state, env->A.history, n, player, static_cast<T*>(d_out), stride, d_ids);
+    k_encode_info<T, Src><<<grid, kBlockThreads, 0, st>>>(src, player, static_cast<T*>(d_out), stride, d_ids_out, d_count_out);
   }
   return launch_status("k_encode_info");
+}
+
+template <typename Src>
+int encode_info_dispatch(coup_vec_env* env, const Src& src, uint32_t max_groups, int player, int dtype, void* d_out,
+                         uint32_t stride, uint32_t* d_ids_out, uint32_t* d_count_out, cudaStream_t st) {
+  if (!aligned_for(dtype, d_out)) return fail(COUP_ERR_INVALID_ARG, kMisaligned);
+  switch (dtype) {
+    case COUP_DTYPE_F32: return encode_info_typed<float>(env, src, max_groups, player, d_out, stride, d_ids_out, d_count_out, st);
+    case COUP_DTYPE_U8: return encode_info_typed<uint8_t>(env, src, max_groups, player, d_out, stride, d_ids_out, d_count_out, st);
+    default: return encode_info_typed<__nv_bfloat16>(env, src, max_groups, player, d_out, stride, d_ids_out, d_count_out, st);
+  }
+}
+
+template <typename T, typename Src>
+int encode_obs_typed(coup_vec_env* env, const Src& src, uint32_t max_groups, int player, void* d_out, uint32_t* d_ids_out,
+                     uint32_t* d_count_out, cudaStream_t st) {
+  if (max_groups == 0) return COUP_OK;
+  const size_t smem = static_cast<size_t>(kObsWarps) * 32 * (player == COUP_PLAYER_BOTH ? 2 : 1) * COUP_OBSERVATION_SIZE * sizeof(T);
+  int sms = 0;
+  cudaError_t err = cudaFuncSetAttribute(k_encode_obs<T, Src>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (err == cudaSuccess) err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, env->opts.device);
+  if (err != cudaSuccess) return fail(COUP_ERR_CUDA, std::string("k_encode_obs setup: ") + cudaGetErrorString(err));
+  // persistent: as many CTAs as fit at once (shared memory bound, at most 8 per SM), never more than there are groups
+  const unsigned per_sm = static_cast<unsigned>(std::min<size_t>(8, (220 * 1024) / (smem + 1024)));
+  const unsigned groups = (max_groups + 31) / 32;
+  const unsigned grid = std::max(1u, std::min(static_cast<unsigned>(sms) * per_sm, (groups + kObsWarps - 1) / kObsWarps));
+  const int use_bulk = reinterpret_cast<uintptr_t>(d_out) % 16u == 0 && (env->opts.flags & COUP_FLAG_PLAIN_STORE_ENCODER) == 0;
+  k_encode_obs<T, Src><<<grid, kObsThreads, smem, st>>>(src, player, static_cast<T*>(d_out), use_bulk, d_ids_out, d_count_out);
+  return launch_status("k_encode_obs");
+}
+
+template <typename Src>
+int encode_obs_dispatch(coup_vec_env* env, const Src& src, uint32_t max_groups, int player, int dtype, void* d_out,
+                        uint32_t* d_ids_out, uint32_t* d_count_out, cudaStream_t st) {
+  const size_t elem = dtype == COUP_DTYPE_F32 ? 4u : dtype == COUP_DTYPE_BF16 ? 2u : 1u;
+  if (reinterpret_cast<uintptr_t>(d_out) % elem != 0) return fail(COUP_ERR_INVALID_ARG, "observation output must be aligned to its element type");
+  switch (dtype) {
+    case COUP_DTYPE_F32: return encode_obs_typed<float>(env, src, max_groups, player, d_out, d_ids_out, d_count_out, st);
+    case COUP_DTYPE_U8: return encode_obs_typed<uint8_t>(env, src, max_groups, player, d_out, d_ids_out, d_count_out, st);
+    default: return encode_obs_typed<__nv_bfloat16>(env, src, max_groups, player, d_out, d_ids_out, d_count_out, st);
+  }
 }
 
 template <typename T>
 int rollout_incremental_typed(coup_vec_env* env, int n_steps, void* d_buf, uint32_t stride, cudaStream_t st) {
   const unsigned grid = blocks_for(env->A.n);
   for (int i = 0; i < n_steps; ++i) {
+    step_prologue(env, false, st);
     k_rollout_incremental<T><<<grid, kBlockThreads, 0, st>>>(env->A, env->step_counter, static_cast<T*>(d_buf), stride);
     env->step_counter++;
   }
@@ -178,7 +245,7 @@ int coup_vec_create(const coup_vec_opts* opts, coup_vec_env** out) {
   env->d_actions = nullptr;
   env->d_scratch = nullptr;
   env->d_row = nullptr;
-  env->d_obs_all = nullptr;
+  env->ring_tail = env->ring_dropped = 0;
   const size_t n = opts->num_envs;
   EnvArrays& A = env->A;
   std::memset(&A, 0, sizeof(A));
@@ -224,7 +291,8 @@ int coup_vec_destroy(coup_vec_env* env) {
   cudaFree(env->A.state); cudaFree(env->A.history); cudaFree(env->A.legal); cudaFree(env->A.cur_player);
   cudaFree(env->A.done); cudaFree(env->A.rewards); cudaFree(env->A.returns); cudaFree(env->A.stats);
   cudaFree(env->A.step_word);
-  cudaFree(env->d_actions); cudaFree(env->d_scratch); cudaFree(env->d_row); cudaFree(env->d_obs_all);
+  cudaFree(env->A.ring); cudaFree(env->A.ring_ctrl);
+  cudaFree(env->d_actions); cudaFree(env->d_scratch); cudaFree(env->d_row);
   if (env->host_outputs_ready) cudaEventDestroy(env->host_outputs_ready);
   delete env;
   return COUP_OK;
@@ -243,6 +311,7 @@ int coup_vec_reset(coup_vec_env* env, const uint8_t* d_reset_mask, const uint8_t
 int coup_vec_step(coup_vec_env* env, const uint8_t* d_actions, const uint8_t* d_forced_chance, void* stream) {
   if (!env || !d_actions) return fail(COUP_ERR_INVALID_ARG, "coup_vec_step: null argument");
   DeviceGuard guard(env->opts.device);
+  step_prologue(env, false, S(stream));
   k_step<<<blocks_for(env->A.n), kBlockThreads, 0, S(stream)>>>(env->A, d_actions, d_forced_chance, env->step_counter);
   env->step_counter++;
   return launch_status("k_step");
@@ -279,6 +348,7 @@ int coup_vec_fork(coup_vec_env* dst, const coup_vec_env* src, const uint32_t* d_
   if (count) {
     EnvArrays D = dst->A;
     D.flags &= ~static_cast<uint32_t>(COUP_FLAG_AUTO_RESET);
+    D.ring = nullptr;   // children stay terminal and readable in place: nothing to hand over
     k_fork<<<blocks_for(count), kBlockThreads, 0, S(stream)>>>(D, src->A.state, src->A.history, src->A.n, d_parent, d_actions,
                                                              d_forced_chance, count, dst->step_counter);
   }
@@ -293,6 +363,9 @@ int coup_cfr_expand(const float* d_advantages, const uint32_t* d_step_words, uin
   if (!d_advantages || !d_step_words || !d_strategy_out || !d_expand_out || !d_child_count_out || outcome_factor == 0 ||
       (traverser != 0 && traverser != 1))
     return fail(COUP_ERR_INVALID_ARG, "coup_cfr_expand: bad arguments");
+  const int dev = device_of(d_advantages);
+  if (dev < 0) return fail(COUP_ERR_INVALID_ARG, "coup_cfr_expand: d_advantages is not a device pointer");
+  DeviceGuard guard(dev);
   k_cfr_expand<<<blocks_for(count), kBlockThreads, 0, S(stream)>>>(d_advantages, d_step_words, count, traverser, external,
                                                                   outcome_factor, e_outcome, expl, seed, counter,
                                                                   d_strategy_out, d_expand_out, d_child_count_out);
@@ -303,6 +376,9 @@ int coup_cfr_children(const uint32_t* d_expand, const int64_t* d_offsets, uint32
                       uint8_t* d_action_out, void* stream) {
   if (count == 0) return COUP_OK;
   if (!d_expand || !d_offsets || !d_parent_out || !d_action_out) return fail(COUP_ERR_INVALID_ARG, "coup_cfr_children: null argument");
+  const int dev = device_of(d_expand);
+  if (dev < 0) return fail(COUP_ERR_INVALID_ARG, "coup_cfr_children: d_expand is not a device pointer");
+  DeviceGuard guard(dev);
   k_cfr_children<<<blocks_for(count), kBlockThreads, 0, S(stream)>>>(d_expand, d_offsets, count, d_parent_out, d_action_out);
   return launch_status("k_cfr_children");
 }
@@ -310,6 +386,7 @@ int coup_cfr_children(const uint32_t* d_expand, const int64_t* d_offsets, uint32
 // ---- single-env accessors with HOST buffers, in the style of rust_open_spiel.h ------------------------
 static int one_move(coup_vec_env* env, uint32_t slot, uint32_t mv, int mode) {
   if (!env || slot >= env->A.n) return fail(COUP_ERR_INVALID_ARG, "coup_env_*: bad handle or slot");
+  std::lock_guard<std::mutex> lock(env->single_env_mutex);
   DeviceGuard guard(env->opts.device);
   k_single_move_one<<<1, 32>>>(env->A, slot, mv, mode, env->d_scratch + 1);
   uint32_t illegal = 0;
@@ -328,6 +405,8 @@ int coup_env_apply_action(coup_vec_env* env, uint32_t slot, int action) {
 }
 
 int coup_env_clone(coup_vec_env* env, uint32_t src, uint32_t dst) {
+  if (!env) return fail(COUP_ERR_INVALID_ARG, "null handle");
+  std::lock_guard<std::mutex> lock(env->single_env_mutex);
   int rc = coup_vec_copy_env(env, src, dst, nullptr);
   if (rc != COUP_OK) return rc;
   DeviceGuard guard(env->opts.device);
@@ -347,6 +426,7 @@ int coup_env_read(coup_vec_env* env, uint32_t slot, uint32_t* h_state4, uint32_t
 int coup_env_information_state_tensor(coup_vec_env* env, uint32_t slot, int player, float* h_buf, int length) {
   if (!env || slot >= env->A.n || !h_buf || (player != 0 && player != 1) || length != COUP_INFO_STATE_SIZE)
     return fail(COUP_ERR_INVALID_ARG, "coup_env_information_state_tensor: bad arguments");
+  std::lock_guard<std::mutex> lock(env->single_env_mutex);
   DeviceGuard guard(env->opts.device);
   CUDA_TRY(cudaMemcpy(env->d_scratch, &slot, sizeof(slot), cudaMemcpyHostToDevice));
   int rc = coup_vec_information_state_tensor_gather(env, env->d_scratch, 1, player, COUP_DTYPE_F32, env->d_row,
@@ -359,13 +439,12 @@ int coup_env_information_state_tensor(coup_vec_env* env, uint32_t slot, int play
 int coup_env_observation_tensor(coup_vec_env* env, uint32_t slot, int player, float* h_buf, int length) {
   if (!env || slot >= env->A.n || !h_buf || (player != 0 && player != 1) || length != COUP_OBSERVATION_SIZE)
     return fail(COUP_ERR_INVALID_ARG, "coup_env_observation_tensor: bad arguments");
+  std::lock_guard<std::mutex> lock(env->single_env_mutex);
   DeviceGuard guard(env->opts.device);
-  if (!env->d_obs_all)
-    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&env->d_obs_all), static_cast<size_t>(env->A.n) * 2 * COUP_OBSERVATION_SIZE * sizeof(float)));
-  int rc = coup_vec_observation_tensor(env, COUP_PLAYER_BOTH, COUP_DTYPE_F32, env->d_obs_all, nullptr);
+  CUDA_TRY(cudaMemcpy(env->d_scratch, &slot, sizeof(slot), cudaMemcpyHostToDevice));
+  int rc = coup_vec_observation_tensor_gather(env, env->d_scratch, 1, player, COUP_DTYPE_F32, env->d_row, nullptr);
   if (rc != COUP_OK) return rc;
-  CUDA_TRY(cudaMemcpy(h_buf, env->d_obs_all + (static_cast<size_t>(slot) * 2 + player) * COUP_OBSERVATION_SIZE,
-                      COUP_OBSERVATION_SIZE * sizeof(float), cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(h_buf, env->d_row, COUP_OBSERVATION_SIZE * sizeof(float), cudaMemcpyDeviceToHost));
   return COUP_OK;
 }
 
@@ -398,6 +477,7 @@ int coup_vec_rollout_strided(coup_vec_env* env, int n_steps, int encode_player, 
   if (!env || n_steps < 0) return fail(COUP_ERR_INVALID_ARG, "coup_vec_rollout: bad arguments");
   if (encode_player >= 0 && (!valid_player_sel(encode_player) || !valid_dtype(dtype) || !d_tensor_out || !valid_stride(row_stride)))
     return fail(COUP_ERR_INVALID_ARG, "coup_vec_rollout: bad encode arguments");
+  if (encode_player >= 0 && !aligned_for(dtype, d_tensor_out)) return fail(COUP_ERR_INVALID_ARG, kMisaligned);
   DeviceGuard guard(env->opts.device);
   if (encode_player < 0) return rollout_typed<float>(env, n_steps, -1, nullptr, COUP_INFO_STATE_SIZE, S(stream));
   switch (dtype) {
@@ -414,6 +494,7 @@ int coup_vec_rollout(coup_vec_env* env, int n_steps, int encode_player, int dtyp
 int coup_vec_rollout_incremental(coup_vec_env* env, int n_steps, int dtype, void* d_buf, uint32_t row_stride, void* stream) {
   if (!env || n_steps < 0 || !d_buf || !valid_dtype(dtype) || !valid_stride(row_stride))
     return fail(COUP_ERR_INVALID_ARG, "coup_vec_rollout_incremental: bad arguments");
+  if (!aligned_for(dtype, d_buf)) return fail(COUP_ERR_INVALID_ARG, kMisaligned);
   DeviceGuard guard(env->opts.device);
   switch (dtype) {
     case COUP_DTYPE_F32: return rollout_incremental_typed<float>(env, n_steps, d_buf, row_stride, S(stream));
@@ -445,14 +526,8 @@ int coup_vec_information_state_tensor_gather(coup_vec_env* env, const uint32_t* 
       (count > 0 && !d_env_ids))
     return fail(COUP_ERR_INVALID_ARG, "coup_vec_information_state_tensor_gather: bad arguments");
   DeviceGuard guard(env->opts.device);
-  // a NULL id list with count == 0 is an empty gather, not "all envs"
-  static const uint32_t kNoIds = 0;
-  const uint32_t* ids = d_env_ids ? d_env_ids : &kNoIds;
-  switch (dtype) {
-    case COUP_DTYPE_F32: return encode_info_typed<float>(env, player, d_out, row_stride, ids, count, S(stream));
-    case COUP_DTYPE_U8: return encode_info_typed<uint8_t>(env, player, d_out, row_stride, ids, count, S(stream));
-    default: return encode_info_typed<__nv_bfloat16>(env, player, d_out, row_stride, ids, count, S(stream));
-  }
+  const SlabSource src{env->A.state, env->A.history, d_env_ids, count};   // count == 0 is an empty gather, not "all envs"
+  return encode_info_dispatch(env, src, count, player, dtype, d_out, row_stride, nullptr, nullptr, S(stream));
 }
 
 int coup_vec_information_state_tensor_strided(coup_vec_env* env, int player, int dtype, void* d_out,
@@ -460,11 +535,85 @@ int coup_vec_information_state_tensor_strided(coup_vec_env* env, int player, int
   if (!env || !d_out || !valid_player_sel(player) || !valid_dtype(dtype) || !valid_stride(row_stride))
     return fail(COUP_ERR_INVALID_ARG, "coup_vec_information_state_tensor: bad arguments");
   DeviceGuard guard(env->opts.device);
-  switch (dtype) {
-    case COUP_DTYPE_F32: return encode_info_typed<float>(env, player, d_out, row_stride, nullptr, 0, S(stream));
-    case COUP_DTYPE_U8: return encode_info_typed<uint8_t>(env, player, d_out, row_stride, nullptr, 0, S(stream));
-    default: return encode_info_typed<__nv_bfloat16>(env, player, d_out, row_stride, nullptr, 0, S(stream));
+  const SlabSource src{env->A.state, env->A.history, nullptr, env->A.n};
+  return encode_info_dispatch(env, src, env->A.n, player, dtype, d_out, row_stride, nullptr, nullptr, S(stream));
+}
+
+// ---- finished-episode ring ----------------------------------------------------------------------------------------
+int coup_vec_finished_ring_enable(coup_vec_env* env, uint32_t capacity_records) {
+  if (!env || (capacity_records & (capacity_records - 1)) != 0)
+    return fail(COUP_ERR_INVALID_ARG, "coup_vec_finished_ring_enable: capacity must be 0 or a power of two");
+  DeviceGuard guard(env->opts.device);
+  CUDA_TRY(cudaDeviceSynchronize());
+  cudaFree(env->A.ring); cudaFree(env->A.ring_ctrl);
+  env->A.ring = nullptr; env->A.ring_ctrl = nullptr; env->A.ring_mask = 0;
+  env->ring_tail = env->ring_dropped = 0;
+  if (capacity_records == 0) return COUP_OK;
+  CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&env->A.ring), static_cast<size_t>(capacity_records) * kRecordWords * sizeof(uint32_t)));
+  CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&env->A.ring_ctrl), 4 * sizeof(unsigned long long)));
+  CUDA_TRY(cudaMemset(env->A.ring_ctrl, 0, 4 * sizeof(unsigned long long)));
+  env->A.ring_mask = capacity_records - 1;
+  return COUP_OK;
+}
+
+const uint32_t* coup_vec_finished_ring(const coup_vec_env* env) { return env ? env->A.ring : nullptr; }
+const uint64_t* coup_vec_finished_ring_ctrl(const coup_vec_env* env) {
+  return env ? reinterpret_cast<const uint64_t*>(env->A.ring_ctrl) : nullptr;
+}
+uint32_t coup_vec_finished_ring_capacity(const coup_vec_env* env) { return env && env->A.ring ? env->A.ring_mask + 1 : 0; }
+
+int coup_vec_finished_drain(coup_vec_env* env, void* out_records, uint32_t max_records, uint32_t* h_count_out,
+                            uint64_t* h_dropped_out, void* stream) {
+  if (!env || !h_count_out || (max_records && !out_records)) return fail(COUP_ERR_INVALID_ARG, "coup_vec_finished_drain: null argument");
+  *h_count_out = 0;
+  if (h_dropped_out) *h_dropped_out = env->ring_dropped;
+  if (!env->A.ring) return fail(COUP_ERR_INVALID_ARG, "coup_vec_finished_drain: the ring is not enabled");
+  DeviceGuard guard(env->opts.device);
+  cudaStream_t st = S(stream);
+  unsigned long long head = 0;
+  CUDA_TRY(cudaMemcpyAsync(&head, env->A.ring_ctrl, sizeof(head), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  const uint64_t cap = static_cast<uint64_t>(env->A.ring_mask) + 1;
+  if (head - env->ring_tail > cap) {   // the producer lapped the consumer: the oldest records are gone
+    env->ring_dropped += head - env->ring_tail - cap;
+    env->ring_tail = head - cap;
   }
+  const uint64_t n = std::min<uint64_t>(head - env->ring_tail, max_records);
+  const size_t rec_bytes = kRecordWords * sizeof(uint32_t);
+  uint64_t copied = 0;
+  while (copied < n) {                 // at most two pieces (wrap-around)
+    const uint64_t pos = (env->ring_tail + copied) & env->A.ring_mask;
+    const uint64_t piece = std::min<uint64_t>(n - copied, cap - pos);
+    CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(out_records) + copied * rec_bytes, env->A.ring + pos * kRecordWords,
+                             piece * rec_bytes, cudaMemcpyDefault, st));
+    copied += piece;
+  }
+  CUDA_TRY(cudaStreamSynchronize(st));
+  env->ring_tail += n;
+  *h_count_out = static_cast<uint32_t>(n);
+  if (h_dropped_out) *h_dropped_out = env->ring_dropped;
+  return COUP_OK;
+}
+
+int coup_vec_finished_information_state_tensor(coup_vec_env* env, int player, int dtype, void* d_out, uint32_t row_stride,
+                                               uint32_t max_episodes, uint32_t* d_env_ids_out, uint32_t* d_count_out,
+                                               void* stream) {
+  if (!env || !d_out || !valid_player_sel(player) || !valid_dtype(dtype) || !valid_stride(row_stride))
+    return fail(COUP_ERR_INVALID_ARG, "coup_vec_finished_information_state_tensor: bad arguments");
+  if (!env->A.ring) return fail(COUP_ERR_INVALID_ARG, "coup_vec_finished_information_state_tensor: the ring is not enabled");
+  DeviceGuard guard(env->opts.device);
+  const RecordSource src{env->A.ring, nullptr, env->A.ring_ctrl, env->A.ring_mask, max_episodes};
+  return encode_info_dispatch(env, src, max_episodes, player, dtype, d_out, row_stride, d_env_ids_out, d_count_out, S(stream));
+}
+
+int coup_records_information_state_tensor(coup_vec_env* env, const uint32_t* d_records, const uint32_t* d_indices,
+                                          uint32_t count, int player, int dtype, void* d_out, uint32_t row_stride, void* stream) {
+  if (!env || !d_records || !d_out || !(valid_player_sel(player) || player == COUP_PLAYER_FROM_RECORD) || !valid_dtype(dtype) ||
+      !valid_stride(row_stride))
+    return fail(COUP_ERR_INVALID_ARG, "coup_records_information_state_tensor: bad arguments");
+  DeviceGuard guard(env->opts.device);
+  const RecordSource src{d_records, d_indices, nullptr, 0xFFFFFFFFu, count};
+  return encode_info_dispatch(env, src, count, player, dtype, d_out, row_stride, nullptr, nullptr, S(stream));
 }
 
 int coup_vec_information_state_tensor(coup_vec_env* env, int player, int dtype, void* d_out, void* stream) {
@@ -475,19 +624,36 @@ int coup_vec_observation_tensor(coup_vec_env* env, int player, int dtype, void* 
   if (!env || !d_out || !valid_player_sel(player) || !valid_dtype(dtype))
     return fail(COUP_ERR_INVALID_ARG, "coup_vec_observation_tensor: bad arguments");
   DeviceGuard guard(env->opts.device);
-  const unsigned grid = (env->A.n + 32 * kWarpsPerBlock - 1) / (32 * kWarpsPerBlock);
-  switch (dtype) {
-    case COUP_DTYPE_F32:
-      k_encode_obs<float><<<grid, kBlockThreads, 0, S(stream)>>>(env->A.state, env->A.n, player, static_cast<float*>(d_out));
-      break;
-    case COUP_DTYPE_U8:
-      k_encode_obs<uint8_t><<<grid, kBlockThreads, 0, S(stream)>>>(env->A.state, env->A.n, player, static_cast<uint8_t*>(d_out));
-      break;
-    default:
-      k_encode_obs<__nv_bfloat16><<<grid, kBlockThreads, 0, S(stream)>>>(env->A.state, env->A.n, player, static_cast<__nv_bfloat16*>(d_out));
-      break;
-  }
-  return launch_status("k_encode_obs");
+  const SlabSource src{env->A.state, env->A.history, nullptr, env->A.n};
+  return encode_obs_dispatch(env, src, env->A.n, player, dtype, d_out, nullptr, nullptr, S(stream));
+}
+
+int coup_vec_observation_tensor_gather(coup_vec_env* env, const uint32_t* d_env_ids, uint32_t count, int player, int dtype,
+                                       void* d_out, void* stream) {
+  if (!env || !d_out || !valid_player_sel(player) || !valid_dtype(dtype) || (count > 0 && !d_env_ids))
+    return fail(COUP_ERR_INVALID_ARG, "coup_vec_observation_tensor_gather: bad arguments");
+  DeviceGuard guard(env->opts.device);
+  const SlabSource src{env->A.state, env->A.history, d_env_ids, count};
+  return encode_obs_dispatch(env, src, count, player, dtype, d_out, nullptr, nullptr, S(stream));
+}
+
+int coup_vec_finished_observation_tensor(coup_vec_env* env, int player, int dtype, void* d_out, uint32_t max_episodes,
+                                         uint32_t* d_env_ids_out, uint32_t* d_count_out, void* stream) {
+  if (!env || !d_out || !valid_player_sel(player) || !valid_dtype(dtype))
+    return fail(COUP_ERR_INVALID_ARG, "coup_vec_finished_observation_tensor: bad arguments");
+  if (!env->A.ring) return fail(COUP_ERR_INVALID_ARG, "coup_vec_finished_observation_tensor: the ring is not enabled");
+  DeviceGuard guard(env->opts.device);
+  const RecordSource src{env->A.ring, nullptr, env->A.ring_ctrl, env->A.ring_mask, max_episodes};
+  return encode_obs_dispatch(env, src, max_episodes, player, dtype, d_out, d_env_ids_out, d_count_out, S(stream));
+}
+
+int coup_records_observation_tensor(coup_vec_env* env, const uint32_t* d_records, const uint32_t* d_indices, uint32_t count,
+                                    int player, int dtype, void* d_out, void* stream) {
+  if (!env || !d_records || !d_out || !(valid_player_sel(player) || player == COUP_PLAYER_FROM_RECORD) || !valid_dtype(dtype))
+    return fail(COUP_ERR_INVALID_ARG, "coup_records_observation_tensor: bad arguments");
+  DeviceGuard guard(env->opts.device);
+  const RecordSource src{d_records, d_indices, nullptr, 0xFFFFFFFFu, count};
+  return encode_obs_dispatch(env, src, count, player, dtype, d_out, nullptr, nullptr, S(stream));
 }
 
 int coup_vec_step_host(coup_vec_env* env, const uint8_t* h_actions, uint32_t* h_legal_mask, int8_t* h_current_player,
@@ -568,6 +734,10 @@ int coup_vec_check_errors(coup_vec_env* env, void* stream) {
 
 int coup_tensor_row_hash(const void* d_tensor, int dtype, uint32_t rows, uint32_t row_len, uint64_t* d_hash_out, void* stream) {
   if (!d_tensor || !d_hash_out || !valid_dtype(dtype)) return fail(COUP_ERR_INVALID_ARG, "coup_tensor_row_hash: bad arguments");
+  if (rows == 0) return COUP_OK;
+  const int dev = device_of(d_tensor);
+  if (dev < 0) return fail(COUP_ERR_INVALID_ARG, "coup_tensor_row_hash: d_tensor is not a device pointer");
+  DeviceGuard guard(dev);
   const unsigned grid = (rows + kWarpsPerBlock - 1) / kWarpsPerBlock;
   switch (dtype) {
     case COUP_DTYPE_F32:

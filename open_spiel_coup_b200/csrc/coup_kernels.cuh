@@ -31,7 +31,13 @@ struct EnvArrays {
   uint32_t flags;
   uint64_t seed;
   uint64_t global_env_offset;
+  // finished-episode ring (coup_vec_finished_ring_enable): [ring_mask + 1][COUP_RECORD_WORDS], or nullptr
+  uint32_t* ring;
+  unsigned long long* ring_ctrl;  // [0] records ever appended, [1] value of [0] when the last step/rollout call began
+  uint32_t ring_mask;
 };
+
+constexpr int kRecordWords = COUP_RECORD_WORDS;   // packed observation record: 16 history words, 4 state words, 4 meta words
 
 __device__ __forceinline__ Env load_env(const uint4* p) {
   uint4 v = *p;
@@ -95,6 +101,41 @@ __device__ __forceinline__ uint32_t deal_new_episode(Env& s, uint32_t* hist_row,
   return k;
 }
 
+// The episode of env `e` has just ended in terminal state `s` (its history row is flushed): append its trajectory log,
+// terminal state and outcome to the finished-episode ring BEFORE an auto-reset re-deals the env in place. This is what
+// SyncVectorEnv.step hands back as `unreset_time_steps` (python/vector_env.py:52-66) and what every agent is stepped with
+// at episode end (coup_experiments/scripts/nfsp.py:141-143): from the record, the terminal info-state rows of both players
+// are encoded on demand (k_encode_info* with a RecordSource) and the whole episode replays through the reference.
+// Slots come from ONE atomic cursor, bumped once per group of lanes that finish together (opportunistic aggregation).
+__device__ __forceinline__ void ring_append(const EnvArrays& A, uint32_t e, const Env& s, const uint32_t* hist_row,
+                                            uint64_t step, bool truncated) {
+  if (A.ring == nullptr) return;
+  const uint32_t peers = __activemask();
+  const uint32_t lane = threadIdx.x & 31u;
+  const int leader = __ffs(peers) - 1;
+  unsigned long long base = 0;
+  if (static_cast<int>(lane) == leader) base = atomicAdd(A.ring_ctrl, static_cast<unsigned long long>(__popc(peers)));
+  base = __shfl_sync(peers, base, leader);
+  const uint32_t slot = static_cast<uint32_t>(base + __popc(peers & ((1u << lane) - 1u))) & A.ring_mask;
+  uint4* dst = reinterpret_cast<uint4*>(A.ring + static_cast<size_t>(slot) * kRecordWords);
+  const uint4* h4 = reinterpret_cast<const uint4*>(hist_row);
+#pragma unroll
+  for (int k = 0; k < kHistoryWords / 4; ++k) dst[k] = h4[k];
+  dst[4] = make_uint4(s.p[0], s.p[1], s.g, s.c);
+  const uint32_t meta = c_moves(s.c) | (static_cast<uint32_t>(returns_p0(s) + 2) << 8) |
+                        (static_cast<uint32_t>(c_reward0(s.c) + 2) << 12) | (truncated ? 1u << 16 : 0u);
+  dst[5] = make_uint4(e, meta, static_cast<uint32_t>(step), static_cast<uint32_t>(step >> 32));
+}
+
+// Runs (one thread) in front of every step/rollout launch: remembers where the ring stood, so that "the episodes that
+// finished in the last call" is the range [ctrl[1], ctrl[0]), and re-arms the persistent kernel's batch counter.
+__global__ void k_step_prologue(unsigned long long* ring_ctrl, unsigned int* batch_counter) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    if (ring_ctrl != nullptr) ring_ctrl[1] = ring_ctrl[0];
+    if (batch_counter != nullptr) *batch_counter = 0u;
+  }
+}
+
 template <bool kSample>
 __device__ __forceinline__ StepResult step_env(Env& s, uint32_t* hist_row, uint32_t action_in,
                                                const uint8_t* forced, const EnvArrays& A, uint32_t e,
@@ -108,6 +149,15 @@ __device__ __forceinline__ StepResult step_env(Env& s, uint32_t* hist_row, uint3
   r.done = term;
   r.reward0 = c_reward0(s.c);
   r.return0 = returns_p0(s);
+  if (!term && g_chance(s.g)) {
+    // An env left at an explicit chance node (coup_vec_new_initial_state / coup_vec_apply_move) has no player to
+    // move: refuse instead of applying a player action to undealt hands.
+    s.g |= kBitError;
+    r.illegal = true;
+    r.legal = legal_mask_chance(s);
+    r.cur_player = COUP_CHANCE_PLAYER_ID;
+    return r;
+  }
   if (!term) {
     const uint32_t legal = legal_mask_decision(s);
     const uint4 rnd = env_random(A.seed, genv, step, 0);
@@ -128,8 +178,9 @@ __device__ __forceinline__ StepResult step_env(Env& s, uint32_t* hist_row, uint3
         r.done = true;
         r.reward0 = c_reward0(s.c);
         r.return0 = returns_p0(s);
+        hw.flush();
+        ring_append(A, e, s, hist_row, step, r.truncated);
         if (auto_reset) {
-          hw.flush();
           hw = HistoryWriter(hist_row);
           s = initial_state();
           cw = env_random(A.seed, genv, step, 1);
@@ -159,6 +210,7 @@ __device__ __forceinline__ StepResult step_env(Env& s, uint32_t* hist_row, uint3
           r.finished = true;
           r.final_moves = c_moves(s.c);
           r.truncated = true;
+          ring_append(A, e, s, hist_row, step, true);
           if (auto_reset) {
             const uint4 rr = env_random(A.seed, genv, step, 1);
             r.chance_moves += deal_new_episode(s, hist_row, rr, nullptr);
@@ -680,20 +732,67 @@ __device__ __forceinline__ void warp_encode_info(const uint32_t* recs, int nrec,
   }
 }
 
-template <typename T>
+// Where the encoders find the (state, history) pair behind output row group `e`:
+//   SlabSource   -- the env slab itself, optionally through a gather list of env ids;
+//   RecordSource -- an array (or ring) of packed observation records (COUP_RECORD_WORDS each: 16 history words, 4 state
+//                   words, 4 meta words), optionally through an index list, optionally limited to "the episodes that
+//                   finished in the last step call" = ring positions [ctrl[1], ctrl[0]). The row count is then only known
+//                   on the device: the grid is sized for the caller's capacity and surplus blocks exit.
+struct SlabSource {
+  const uint4* state;
+  const uint32_t* history;
+  const uint32_t* ids;
+  uint32_t n;
+  __device__ __forceinline__ uint32_t rows() const { return n; }
+  __device__ __forceinline__ void locate(uint32_t e, const uint4*& sp, const uint32_t*& hp, uint32_t& id, int& sel) const {
+    id = ids ? ids[e] : e;
+    sp = state + id;
+    hp = history + static_cast<size_t>(id) * kHistoryWords;
+  }
+};
+struct RecordSource {
+  const uint32_t* records;
+  const uint32_t* indices;           // optional
+  const unsigned long long* ctrl;    // optional ring control words
+  uint32_t index_mask;               // ring capacity - 1, or 0xFFFFFFFF for a plain array
+  uint32_t n;                        // rows wanted (an upper bound when ctrl is given)
+  __device__ __forceinline__ uint32_t rows() const {
+    if (ctrl == nullptr) return n;
+    const unsigned long long avail = ctrl[0] - ctrl[1];
+    return avail < n ? static_cast<uint32_t>(avail) : n;
+  }
+  __device__ __forceinline__ void locate(uint32_t e, const uint4*& sp, const uint32_t*& hp, uint32_t& id, int& sel) const {
+    const uint32_t idx = indices ? indices[e] : (ctrl ? static_cast<uint32_t>(ctrl[1]) + e : e);
+    const uint32_t* rec = records + static_cast<size_t>(idx & index_mask) * kRecordWords;
+    hp = rec;
+    sp = reinterpret_cast<const uint4*>(rec + kHistoryWords);
+    id = rec[20];
+    if (sel == COUP_PLAYER_FROM_RECORD) sel = static_cast<int>(rec[21] >> 31);   // the seat the record was taken for
+  }
+};
+
+// Loads the pair behind row group `e`, leaves its encoder record in `rec`, reports the env id the row describes.
+template <typename Src>
+__device__ __forceinline__ void load_and_fill(const Src& src, uint32_t e, int player_sel, uint32_t* rec, uint32_t* ids_out) {
+  const uint4* sp; const uint32_t* hp; uint32_t id; int sel = player_sel;
+  src.locate(e, sp, hp, id, sel);
+  const Env s = load_env(sp);
+  fill_record(rec, s, hp, sel);
+  if (ids_out != nullptr) ids_out[e] = id;
+}
+
+template <typename T, typename Src>
 __global__ void __launch_bounds__(kBlockThreads)
-k_encode_info(const uint4* __restrict__ state, const uint32_t* __restrict__ history, uint32_t n,
-              int player_sel, T* __restrict__ out, uint32_t stride, const uint32_t* __restrict__ ids) {
+k_encode_info(Src src, int player_sel, T* __restrict__ out, uint32_t stride, uint32_t* __restrict__ ids_out,
+              uint32_t* __restrict__ count_out) {
   __shared__ uint32_t s_rec[kWarpsPerBlock][32 * kRecWords];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t n = src.rows();
+  if (count_out != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *count_out = n;
   const uint32_t e0 = (blockIdx.x * kWarpsPerBlock + warp) * 32u;
   if (e0 >= n) return;
   const uint32_t e = e0 + lane;
-  if (e < n) {
-    const uint32_t src = ids ? ids[e] : e;  // gather: output row e describes env ids[e]
-    const Env s = load_env(state + src);
-    fill_record(&s_rec[warp][lane * kRecWords], s, history + static_cast<size_t>(src) * kHistoryWords, player_sel);
-  }
+  if (e < n) load_and_fill(src, e, player_sel, &s_rec[warp][lane * kRecWords], ids_out);
   __syncwarp();
   const int nrec = static_cast<int>(min(32u, n - e0));
   const bool both = player_sel == COUP_PLAYER_BOTH;
@@ -817,24 +916,23 @@ __device__ __forceinline__ void zero_stage(unsigned char* stage, int lane) {
   for (int q = lane; q < kStageBytes / 16; q += 32) p[q] = make_uint4(0, 0, 0, 0);
 }
 
-template <typename T>
+template <typename T, typename Src>
 __global__ void __launch_bounds__(kTmaBlockThreads, 2)
-k_encode_info_tma(const uint4* __restrict__ state, const uint32_t* __restrict__ history, uint32_t n,
-                  int player_sel, T* __restrict__ out, uint32_t stride, const uint32_t* __restrict__ ids) {
+k_encode_info_tma(Src src, int player_sel, T* __restrict__ out, uint32_t stride, uint32_t* __restrict__ ids_out,
+                  uint32_t* __restrict__ count_out) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   TmaSmem sm(smem_raw, warp);
+  const uint32_t n = src.rows();
+  if (count_out != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *count_out = n;
   const uint32_t b0 = blockIdx.x * (kTmaWarpsPerBlock * 32u);
+  if (b0 >= n) return;                                        // uniform over the block (device-side row counts)
   const uint32_t e0 = b0 + warp * 32u;
   const uint32_t e = e0 + lane;
   const bool block_full = b0 + kTmaWarpsPerBlock * 32u <= n;  // uniform over the block
   const bool both = player_sel == COUP_PLAYER_BOTH;
   if (block_full) zero_stage(sm.stage, lane);
-  if (e < n) {
-    const uint32_t src = ids ? ids[e] : e;
-    const Env s = load_env(state + src);
-    fill_record(sm.recs + lane * kRecWords, s, history + static_cast<size_t>(src) * kHistoryWords, player_sel);
-  }
+  if (e < n) load_and_fill(src, e, player_sel, sm.recs + lane * kRecWords, ids_out);
   if (block_full) {
     __syncthreads();
     block_encode_info_tma<T>(sm.block_recs, both, reinterpret_cast<T*>(sm.stage),
@@ -849,56 +947,90 @@ k_encode_info_tma(const uint4* __restrict__ state, const uint32_t* __restrict__ 
   }
 }
 
-// ---- observation encoder (98 elements per row): one element per thread step, rows of a warp contiguous --
-template <typename T> __device__ __forceinline__ T elem_from(uint32_t v);
-template <> __device__ __forceinline__ float elem_from<float>(uint32_t v) { return static_cast<float>(v); }
-template <> __device__ __forceinline__ uint8_t elem_from<uint8_t>(uint32_t v) { return static_cast<uint8_t>(v); }
-template <> __device__ __forceinline__ __nv_bfloat16 elem_from<__nv_bfloat16>(uint32_t v) { return __float2bfloat16(static_cast<float>(v)); }
+// ---- observation encoder (98 elements per row) ------------------------------------------------------------------------
+// Same staging idea as the info-state encoder, one warp per 32 consecutive envs: a row is 98 elements with ~14
+// non-zeros, and although one row is not a multiple of 16 bytes, the 32 (x2 views) rows of a warp are one contiguous,
+// 16-byte aligned span of the output (3 136 / 6 272 / 12 544 B per view for u8 / bf16 / f32). The warp keeps that span
+// zeroed in shared memory; each lane pokes the non-zeros of its own env's row(s), lane 0 hands the span to the TMA
+// engine with one bulk store, and the lanes erase what they poked. Persistent: warps stride over the 32-env groups.
+// A ragged last group, or an output that is not 16-byte aligned, is copied out of the staging span element by element.
+constexpr int kObsWarps = 4;
+constexpr int kObsThreads = kObsWarps * 32;
 
 template <typename T>
-__global__ void __launch_bounds__(kBlockThreads)
-k_encode_obs(const uint4* __restrict__ state, uint32_t n, int player_sel, T* __restrict__ out) {
-  // per record: head mask A (2 words), head mask B (2), last-action mask (2), coins (1)
-  __shared__ uint32_t s_rec[kWarpsPerBlock][32 * 7];
+__device__ __forceinline__ void poke_obs_row(T* row, uint64_t head, uint64_t last_action, uint32_t coins, bool set) {
+  const T one = Elem<T>::from(set ? 1u : 0u);
+  while (head) {                                                        // elements 0..59
+    const int b = __ffsll(static_cast<long long>(head)) - 1;
+    head &= head - 1;
+    row[b] = one;
+  }
+  row[60] = Elem<T>::from(set ? coins & 255u : 0u);                     // WriteCoins, 207-213
+  row[61] = Elem<T>::from(set ? coins >> 8 : 0u);
+  while (last_action) {                                                 // WriteLastAction, 217-225
+    const int b = __ffsll(static_cast<long long>(last_action)) - 1;
+    last_action &= last_action - 1;
+    row[62 + b] = one;
+  }
+}
+
+template <typename T, typename Src>
+__global__ void __launch_bounds__(kObsThreads)
+k_encode_obs(Src src, int player_sel, T* __restrict__ out, int use_bulk, uint32_t* __restrict__ ids_out,
+             uint32_t* __restrict__ count_out) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t e0 = (blockIdx.x * kWarpsPerBlock + warp) * 32u;
-  if (e0 >= n) return;
-  const uint32_t e = e0 + lane;
   const bool both = player_sel == COUP_PLAYER_BOTH;
-  if (e < n) {
-    const Env s = load_env(state + e);
-    const bool term = is_terminal(s);
-    const uint32_t obs_a = player_sel == COUP_PLAYER_1 ? 1u : player_sel == COUP_PLAYER_CURRENT ? g_mover(s.g) : 0u;
-    uint32_t* rec = &s_rec[warp][lane * 7];
-    const uint64_t ma = head_mask(s, obs_a, term);
-    const uint64_t mb = both ? head_mask(s, 1u, term) : 0ull;
-    const uint64_t la = last_action_mask(s);
-    rec[0] = static_cast<uint32_t>(ma); rec[1] = static_cast<uint32_t>(ma >> 32);
-    rec[2] = static_cast<uint32_t>(mb); rec[3] = static_cast<uint32_t>(mb >> 32);
-    rec[4] = static_cast<uint32_t>(la); rec[5] = static_cast<uint32_t>(la >> 32);
-    rec[6] = pw_coins(s.p[0]) | (pw_coins(s.p[1]) << 8);
-  }
+  const uint32_t views = both ? 2u : 1u;
+  const uint32_t n = src.rows();
+  if (count_out != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *count_out = n;
+  const uint32_t span_elems = 32u * views * kObservationSize;
+  T* stage = reinterpret_cast<T*>(smem_raw) + static_cast<size_t>(warp) * span_elems;
+  for (uint32_t q = lane; q < span_elems * sizeof(T) / 16u; q += 32u) reinterpret_cast<uint4*>(stage)[q] = make_uint4(0u, 0u, 0u, 0u);
   __syncwarp();
-  const int nrec = static_cast<int>(min(32u, n - e0));
-  const int nrows = both ? 2 * nrec : nrec;
-  T* base = out + static_cast<size_t>(e0) * (both ? 2 : 1) * kObservationSize;
-  const int total = nrows * kObservationSize;
-  for (int g = lane; g < total; g += 32) {
-    const int r = g / kObservationSize, p = g - r * kObservationSize;
-    const uint32_t* rec = &s_rec[warp][(both ? (r >> 1) : r) * 7];
-    const int view = both ? (r & 1) : 0;
-    uint32_t v;
-    if (p < 60) {
-      const uint64_t m = static_cast<uint64_t>(rec[2 * view]) | (static_cast<uint64_t>(rec[2 * view + 1]) << 32);
-      v = static_cast<uint32_t>(m >> p) & 1u;
-    } else if (p < 62) {
-      v = (rec[6] >> (8 * (p - 60))) & 255u;
-    } else {
-      const uint64_t m = static_cast<uint64_t>(rec[4]) | (static_cast<uint64_t>(rec[5]) << 32);
-      v = static_cast<uint32_t>(m >> (p - 62)) & 1u;
+  const uint32_t n_groups = (n + 31u) / 32u;
+  for (uint32_t g = blockIdx.x * kObsWarps + warp; g < n_groups; g += gridDim.x * kObsWarps) {
+    const uint32_t e0 = g * 32u, e = e0 + lane;
+    const uint32_t nrec = min(32u, n - e0);
+    uint64_t head_a = 0, head_b = 0, la = 0;
+    uint32_t coins = 0;
+    if (e < n) {
+      const uint4* sp; const uint32_t* hp; uint32_t id; int sel = player_sel;
+      src.locate(e, sp, hp, id, sel);
+      const Env s = load_env(sp);
+      const bool term = is_terminal(s);
+      const uint32_t obs_a = sel == COUP_PLAYER_1 ? 1u : sel == COUP_PLAYER_CURRENT ? g_mover(s.g) : 0u;
+      head_a = head_mask(s, obs_a, term);
+      if (both) head_b = head_mask(s, 1u, term);
+      la = last_action_mask(s);
+      coins = pw_coins(s.p[0]) | (pw_coins(s.p[1]) << 8);
+      if (ids_out != nullptr) ids_out[e] = id;
+      T* row = stage + static_cast<size_t>(lane) * views * kObservationSize;
+      poke_obs_row<T>(row, head_a, la, coins, true);
+      if (both) poke_obs_row<T>(row + kObservationSize, head_b, la, coins, true);
     }
-    base[g] = elem_from<T>(v);
+    T* dst = out + static_cast<size_t>(e0) * views * kObservationSize;
+    if (use_bulk && nrec == 32u) {
+      tma_store_fence();
+      __syncwarp();
+      if (lane == 0) {
+        tma_bulk_store(dst, stage, span_elems * static_cast<uint32_t>(sizeof(T)));
+        tma_wait_read_all();
+      }
+      __syncwarp();
+    } else {
+      __syncwarp();
+      const uint32_t total = nrec * views * kObservationSize;
+      for (uint32_t i = lane; i < total; i += 32u) dst[i] = stage[i];
+      __syncwarp();
+    }
+    if (e < n) {
+      T* row = stage + static_cast<size_t>(lane) * views * kObservationSize;
+      poke_obs_row<T>(row, head_a, la, coins, false);
+      if (both) poke_obs_row<T>(row + kObservationSize, head_b, la, coins, false);
+    }
   }
+  if (lane == 0) tma_wait_all();   // the engine must be done with this warp's shared memory before the CTA exits
 }
 
 // ---- fused random rollout step: sample -> step -> chance -> [auto-reset] -> outputs -> encode -------

@@ -14,7 +14,7 @@ import torch
 from . import _lib
 from ._lib import (DTYPE_BF16, DTYPE_F32, DTYPE_U8, FLAG_AUTO_RESET, HISTORY_WORDS, INFO_STATE_SIZE,
                    NUM_DISTINCT_ACTIONS, OBSERVATION_SIZE, PLAYER_0, PLAYER_1, PLAYER_BOTH, PLAYER_CURRENT,
-                   STATE_WORDS, STATS_LEN, CoupError, check)
+                   RECORD_WORDS, STATE_WORDS, STATS_LEN, TERMINAL_PLAYER_ID, CoupError, check)
 
 _TORCH_TO_DTYPE = {torch.float32: DTYPE_F32, torch.uint8: DTYPE_U8, torch.bfloat16: DTYPE_BF16}
 
@@ -46,7 +46,7 @@ class CoupVectorEnv:
     observation_size = OBSERVATION_SIZE
 
     def __init__(self, num_envs, seed=1234, device=0, global_env_offset=0, auto_reset=False,
-                 plain_store_encoder=False, warp_specialised=True, blocking_sync=False):
+                 plain_store_encoder=False, warp_specialised=True, blocking_sync=False, finished_ring=0):
         self._lib = _lib.load()
         if not torch.cuda.is_available():
             raise CoupError("CoupVectorEnv needs a CUDA device (there is no CPU fallback)")
@@ -72,6 +72,9 @@ class CoupVectorEnv:
         self.history = _view(L.coup_vec_history(self._h), (n, HISTORY_WORDS), "<i4", d, self)
         self.step_word = _view(L.coup_vec_step_word(self._h), (n,), "<i4", d, self)
         self.stats_device = _view(L.coup_vec_stats_device(self._h), (STATS_LEN,), "<i8", d, self)
+        self.finished_ring = self.finished_ctrl = None
+        if finished_ring:
+            self.enable_finished_ring(finished_ring)
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
@@ -107,6 +110,9 @@ class CoupVectorEnv:
         """Row stride in elements of a [rows, >=2492] output (2496 = padded, GEMM-aligned rows)."""
         if out.dim() != 2 or out.stride(1) != 1 or out.shape[1] < INFO_STATE_SIZE:
             raise ValueError("info-state output must be [rows, >=2492] with unit inner stride")
+        unit = 4 * out.element_size()          # the encoders store four elements at a time (coup_b200.h, "Alignment")
+        if out.data_ptr() % unit:
+            raise ValueError(f"info-state output must be {unit}-byte aligned (got a view at offset {out.data_ptr() % unit})")
         return int(out.stride(0))
 
     def _rows(self, player):
@@ -225,6 +231,18 @@ class CoupVectorEnv:
                                                     self._ptr(out), _stream_ptr(self.device)))
         return out
 
+    def observation_tensor_gather(self, env_ids, player=PLAYER_CURRENT, out=None, dtype=torch.float32):
+        """Observation rows of the envs listed in `env_ids` only."""
+        ids = env_ids.to(device=self.device, dtype=torch.int32).contiguous()
+        count = int(ids.numel())
+        rows = count * (2 if player == PLAYER_BOTH else 1)
+        if out is None:
+            out = torch.empty((rows, OBSERVATION_SIZE), dtype=dtype, device=self.device)
+        if count:
+            check(self._lib.coup_vec_observation_tensor_gather(self._h, self._ptr(ids), count, player,
+                                                               _TORCH_TO_DTYPE[out.dtype], self._ptr(out), _stream_ptr(self.device)))
+        return out[:rows]
+
     def legal_actions_mask(self, out=None):
         """State::LegalActionsMask (spiel.cc:371-377): uint8 [num_envs, 18]."""
         if out is None:
@@ -239,6 +257,98 @@ class CoupVectorEnv:
         check(self._lib.coup_tensor_row_hash(self._ptr(t), _TORCH_TO_DTYPE[t.dtype], rows, t.shape[1],
                                              self._ptr(out), _stream_ptr(self.device)))
         return out
+
+    # ---- finished episodes (auto-reset mode keeps them: include/coup_b200.h "finished episodes") ------
+    def enable_finished_ring(self, capacity):
+        """Device ring of `capacity` (power of two) packed records, one per episode that ends in any step/rollout
+        call, appended before the env is re-dealt. 0 disables."""
+        check(self._lib.coup_vec_finished_ring_enable(self._h, int(capacity)))
+        self.finished_ring = self.finished_ctrl = None
+        if capacity:
+            self.finished_ring = _view(self._lib.coup_vec_finished_ring(self._h), (int(capacity), RECORD_WORDS), "<i4",
+                                       self.device, self)
+            self.finished_ctrl = _view(self._lib.coup_vec_finished_ring_ctrl(self._h), (4,), "<i8", self.device, self)
+
+    def finished_drain(self, max_records=None):
+        """Records not handed out yet, oldest first: (uint32 numpy [k, 24], records dropped so far)."""
+        cap = int(self._lib.coup_vec_finished_ring_capacity(self._h))
+        k = cap if max_records is None else min(int(max_records), cap)
+        buf = np.empty((max(k, 1), RECORD_WORDS), np.uint32)
+        count, dropped = C.c_uint32(0), C.c_uint64(0)
+        check(self._lib.coup_vec_finished_drain(self._h, C.c_void_p(buf.ctypes.data), k, C.byref(count), C.byref(dropped),
+                                                _stream_ptr(self.device)))
+        return buf[: count.value], int(dropped.value)
+
+    def finished_information_state_tensor(self, player=PLAYER_BOTH, out=None, dtype=torch.float32, max_episodes=None,
+                                          env_ids_out=None, count_out=None):
+        """Terminal info-state rows of the episodes that ended in the most recent step/rollout call, in ring order.
+        Returns (rows, env_ids int32 [max_episodes], count int32 [1]); only the first `count` entries (x2 rows for
+        PLAYER_BOTH) are written. Nothing is read back to the host."""
+        views = 2 if player == PLAYER_BOTH else 1
+        if max_episodes is None:
+            max_episodes = self.num_envs if out is None else out.shape[0] // views
+        if out is None:
+            out = torch.empty((max_episodes * views, INFO_STATE_SIZE), dtype=dtype, device=self.device)
+        if out.shape[0] < max_episodes * views:
+            raise ValueError("output has too few rows")
+        if env_ids_out is None:
+            env_ids_out = torch.empty(max_episodes, dtype=torch.int32, device=self.device)
+        if count_out is None:
+            count_out = torch.zeros(1, dtype=torch.int32, device=self.device)
+        check(self._lib.coup_vec_finished_information_state_tensor(
+            self._h, player, _TORCH_TO_DTYPE[out.dtype], self._ptr(out), self._row_stride(out), int(max_episodes),
+            self._ptr(env_ids_out), self._ptr(count_out), _stream_ptr(self.device)))
+        return out, env_ids_out, count_out
+
+    def finished_observation_tensor(self, player=PLAYER_BOTH, out=None, dtype=torch.float32, max_episodes=None,
+                                    env_ids_out=None, count_out=None):
+        """Terminal observation rows ([.., 98]) of the episodes that ended in the most recent step/rollout call."""
+        views = 2 if player == PLAYER_BOTH else 1
+        if max_episodes is None:
+            max_episodes = self.num_envs if out is None else out.shape[0] // views
+        if out is None:
+            out = torch.empty((max_episodes * views, OBSERVATION_SIZE), dtype=dtype, device=self.device)
+        if out.shape[0] < max_episodes * views or not out.is_contiguous():
+            raise ValueError("output must be contiguous with max_episodes (x2) rows")
+        if env_ids_out is None:
+            env_ids_out = torch.empty(max_episodes, dtype=torch.int32, device=self.device)
+        if count_out is None:
+            count_out = torch.zeros(1, dtype=torch.int32, device=self.device)
+        check(self._lib.coup_vec_finished_observation_tensor(
+            self._h, player, _TORCH_TO_DTYPE[out.dtype], self._ptr(out), int(max_episodes), self._ptr(env_ids_out),
+            self._ptr(count_out), _stream_ptr(self.device)))
+        return out, env_ids_out, count_out
+
+    def records_observation_tensor(self, records, indices=None, player=PLAYER_BOTH, out=None, dtype=torch.float32):
+        """Decodes packed records into observation rows ([.., 98])."""
+        if indices is not None:
+            indices = indices.to(device=self.device, dtype=torch.int32).contiguous()
+        count = int(records.shape[0] if indices is None else indices.numel())
+        rows = count * (2 if player == PLAYER_BOTH else 1)
+        if out is None:
+            out = torch.empty((rows, OBSERVATION_SIZE), dtype=dtype, device=self.device)
+        if count:
+            check(self._lib.coup_records_observation_tensor(self._h, self._ptr(records), self._ptr(indices), count, player,
+                                                            _TORCH_TO_DTYPE[out.dtype], self._ptr(out), _stream_ptr(self.device)))
+        return out[:rows]
+
+    def records_information_state_tensor(self, records, indices=None, player=PLAYER_BOTH, out=None, dtype=torch.float32):
+        """Decodes packed records (int32 device tensor [m, 24]) into info-state rows; row i = record indices[i]."""
+        if records.dim() != 2 or records.shape[1] != RECORD_WORDS or not records.is_contiguous():
+            raise ValueError("records must be a contiguous [m, 24] int32 tensor")
+        if indices is not None:
+            indices = indices.to(device=self.device, dtype=torch.int32).contiguous()
+        count = int(records.shape[0] if indices is None else indices.numel())
+        rows = count * (2 if player == PLAYER_BOTH else 1)
+        if out is None:
+            out = torch.empty((rows, INFO_STATE_SIZE), dtype=dtype, device=self.device)
+        if out.shape[0] < rows:
+            raise ValueError("output has too few rows")
+        if count:
+            check(self._lib.coup_records_information_state_tensor(
+                self._h, self._ptr(records), self._ptr(indices), count, player, _TORCH_TO_DTYPE[out.dtype], self._ptr(out),
+                self._row_stride(out), _stream_ptr(self.device)))
+        return out[:rows]
 
     # ---- statistics -----------------------------------------------------------------------------
     def stats(self):
@@ -304,6 +414,21 @@ def decode_history(hist_words, lens):
     return out
 
 
+def decode_finished_records(records):
+    """uint32 [k, 24] ring records -> dict of numpy fields + per-episode (actions, deal_target) lists."""
+    r = np.asarray(records).view(np.uint32).reshape(-1, RECORD_WORDS)
+    meta = r[:, 21]
+    moves = (meta & 127).astype(np.int64)
+    return {
+        "env": r[:, 20].astype(np.int64), "moves": moves,
+        "return0": ((meta >> 8) & 7).astype(np.int64) - 2, "reward0": ((meta >> 12) & 7).astype(np.int64) - 2,
+        "truncated": ((meta >> 16) & 1).astype(bool),
+        "step": r[:, 22].astype(np.uint64) | (r[:, 23].astype(np.uint64) << np.uint64(32)),
+        "state": r[:, HISTORY_WORDS:HISTORY_WORDS + STATE_WORDS].copy(),
+        "trajectories": decode_history(r[:, :HISTORY_WORDS], moves),
+    }
+
+
 def stats_dict(buf):
     buf = [int(x) for x in buf]
     return {
@@ -343,3 +468,132 @@ def unpack_states(state_words):
     out["turn_number"] = ((c >> 7) & 127).astype(np.int64)
     out["reward0"] = ((c >> 14) & 7).astype(np.int64) - 2
     return out
+
+
+class BatchedTimeSteps:
+    """The list of `TimeStep`s that `SyncVectorEnv.step/reset` returns (python/vector_env.py:40-78), as device tensors:
+    observations["info_state"] [n, 2, 2492], observations["legal_actions_mask"] uint8 [n, 2, 18] (all zero for the
+    player who is not to move, rl_environment.py:243-249), observations["current_player"] int8 [n] (-4 = terminal),
+    rewards float [n, 2], discounts float [n, 2], step_type int8 [n] (0 FIRST, 1 MID, 2 LAST). `ts[i]` converts env i
+    into the reference's `rl_environment.TimeStep` with Python lists, for code written against the list form."""
+
+    def __init__(self, observations, rewards, discounts, step_type):
+        self.observations, self.rewards, self.discounts, self.step_type = observations, rewards, discounts, step_type
+
+    def __len__(self):
+        return int(self.step_type.shape[0])
+
+    def last(self):
+        return self.step_type == 2
+
+    def first(self):
+        return self.step_type == 0
+
+    def current_player(self):
+        return self.observations["current_player"]
+
+    def __getitem__(self, i):
+        from .rl_environment import StepType, TimeStep
+        st = StepType(int(self.step_type[i]))
+        mask = self.observations["legal_actions_mask"][i].cpu().numpy()
+        obs = {"info_state": [row.tolist() for row in self.observations["info_state"][i].float().cpu()],
+               "legal_actions": [np.nonzero(mask[p])[0].tolist() for p in range(2)],
+               "current_player": int(self.observations["current_player"][i]), "serialized_state": []}
+        first = st == StepType.FIRST
+        return TimeStep(observations=obs, rewards=None if first else self.rewards[i].tolist(),
+                        discounts=None if first else self.discounts[i].tolist(), step_type=st)
+
+
+class SyncVectorEnv:
+    """`vector_env.SyncVectorEnv` (python/vector_env.py:23-78) over ONE batched device environment instead of a list of
+    `rl_environment.Environment`s: same call shape -- `step(step_outputs, reset_if_done) -> (time_steps, reward, done,
+    unreset_time_steps)`, `reset(envs_to_reset)` -- with batched tensors (BatchedTimeSteps) where the reference has lists.
+
+    The slab runs in auto-reset mode with the finished-episode ring on: an env whose episode ends is re-dealt inside the
+    step kernel, and its terminal time step (what `unreset_time_steps` carries) is rebuilt from the ring record. With
+    `reset_if_done=False` the reference leaves a finished env alone and resets it on its NEXT step call, ignoring that
+    call's action (rl_environment.py:296-297); here the env already holds the new episode, so that next call lets it sit
+    the step out (action 0xFF) and reports its FIRST time step."""
+
+    def __init__(self, num_envs, seed=1234, device=0, discount=1.0, dtype=torch.float32, env=None):
+        self.env = env if env is not None else CoupVectorEnv(num_envs, seed=seed, device=device, auto_reset=True)
+        n = self.env.num_envs
+        ring = 1
+        while ring < 2 * n:
+            ring *= 2
+        self.env.enable_finished_ring(ring)
+        self._discount, self._dtype, dev = float(discount), dtype, self.env.device
+        self._pending_first = torch.zeros(n, dtype=torch.bool, device=dev)   # finished, not yet "reset" by the caller
+        self._term_rows = torch.empty((2 * n, INFO_STATE_SIZE), dtype=dtype, device=dev)
+        self._term_ids = torch.empty(n, dtype=torch.int32, device=dev)
+        self._term_count = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    def __len__(self):
+        return self.env.num_envs
+
+    @property
+    def num_players(self):
+        return 2
+
+    def observation_spec(self):
+        return dict(info_state=(INFO_STATE_SIZE,), legal_actions=(NUM_DISTINCT_ACTIONS,), current_player=(), serialized_state=())
+
+    def _current(self, first_mask):
+        """Time steps of the states the slab holds now; FIRST where `first_mask`, else MID."""
+        env, n = self.env, self.env.num_envs
+        info = env.information_state_tensor(PLAYER_BOTH, dtype=self._dtype).view(n, 2, INFO_STATE_SIZE)
+        mover = env.current_player.to(torch.int64).clamp(min=0)
+        legal = torch.zeros((n, 2, NUM_DISTINCT_ACTIONS), dtype=torch.uint8, device=env.device)
+        legal[torch.arange(n, device=env.device), mover] = env.legal_actions_mask()
+        rewards = env.rewards.to(torch.float32) * (~first_mask).unsqueeze(1)
+        discounts = torch.full((n, 2), self._discount, device=env.device)
+        step_type = torch.where(first_mask, 0, 1).to(torch.int8)
+        obs = {"info_state": info, "legal_actions_mask": legal, "current_player": env.current_player.clone()}
+        return BatchedTimeSteps(obs, rewards, discounts, step_type)
+
+    def step(self, step_outputs, reset_if_done=False):
+        env, n = self.env, self.env.num_envs
+        if torch.is_tensor(step_outputs):
+            actions = step_outputs.to(device=env.device, dtype=torch.uint8)
+        else:
+            actions = torch.as_tensor(np.asarray([getattr(o, "action", o) for o in step_outputs], dtype=np.uint8)).to(env.device)
+        sat_out = self._pending_first.clone()
+        actions = torch.where(sat_out, torch.full_like(actions, 0xFF), actions)
+        env.step(actions)
+        done = env.done.bool() & ~sat_out
+        time_steps = self._current(first_mask=sat_out | done)
+        reward = env.rewards.to(torch.float32) * (~sat_out).unsqueeze(1)
+        # unreset view: the finished envs' LAST time steps, rebuilt from this call's ring records
+        _, ids, count = env.finished_information_state_tensor(PLAYER_BOTH, out=self._term_rows, env_ids_out=self._term_ids,
+                                                              count_out=self._term_count)
+        k = int(count.item())
+        un_obs = {key: t.clone() for key, t in time_steps.observations.items()}
+        idx = ids[:k].long()
+        un_obs["info_state"][idx] = self._term_rows[: 2 * k].view(k, 2, INFO_STATE_SIZE)
+        un_obs["legal_actions_mask"][idx] = 0
+        un_obs["current_player"][idx] = TERMINAL_PLAYER_ID
+        un_discounts = time_steps.discounts.clone()
+        un_discounts[idx] = 0.0
+        un_type = torch.where(done, 2, torch.where(sat_out, 0, 1)).to(torch.int8)
+        unreset = BatchedTimeSteps(un_obs, reward, un_discounts, un_type)
+        if reset_if_done:
+            self._pending_first.zero_()
+            return time_steps, reward, done, unreset
+        self._pending_first = done
+        return unreset, reward, done, unreset
+
+    def reset(self, envs_to_reset=None):
+        """vector_env.py:68-78: reset the listed envs (all by default), `get_time_step()` for the others."""
+        env, n = self.env, self.env.num_envs
+        if envs_to_reset is None:
+            mask = torch.ones(n, dtype=torch.bool, device=env.device)
+        else:
+            mask = torch.as_tensor(envs_to_reset).to(device=env.device).bool()
+        redeal = mask & ~self._pending_first            # envs waiting for their reset already hold a fresh episode
+        env.reset(redeal.to(torch.uint8))
+        first = mask | self._pending_first
+        self._pending_first = self._pending_first & ~mask
+        ts = self._current(first_mask=first)
+        # an env that is finished-and-pending but not in the mask still shows its fresh episode: the terminal step was
+        # handed out by the step call that ended it
+        return ts

@@ -126,6 +126,102 @@ def check(envs, steered, seed, device, threads, use_reference=True):
     return out
 
 
+def check_autoreset(envs, episodes, seed, device, threads, use_reference=True, dtype=torch.float32):
+    """The same bit-exactness replay in the mode bench.py times: COUP_FLAG_AUTO_RESET, fused rollout kernel, finished
+    episodes harvested from the device ring (coup_vec_finished_*). Every state of every finished episode is folded into a
+    per-episode digest on the GPU side -- decision states from the slab, the terminal state (which the env no longer
+    holds: it was re-dealt inside the step kernel) from the ring record -- and compared with the checker's digest of the
+    ring's action + chance log."""
+    from oracle.bindings import Oracle, Reference
+    from open_spiel_coup_b200.vector_env import decode_finished_records
+    ref = use_reference and Reference.available()
+    checker = Reference() if ref else Oracle()
+    n = envs
+    cap = 1
+    while cap < episodes + 2 * n:
+        cap *= 2
+    env = CoupVectorEnv(n, seed=seed, device=device, auto_reset=True, finished_ring=cap)
+    dev = env.device
+    t0 = time.time()
+    buf = torch.empty((n, 2492), dtype=dtype, device=dev)
+    d = fold_state(env, torch.zeros(n, dtype=torch.int64, device=dev), torch.ones(n, dtype=torch.bool, device=dev))
+    reports = torch.ones(n, dtype=torch.int64, device=dev)
+    fin_digest, fin_reports, fin_env = [], [], []
+    term_info = torch.empty((2 * n, 2492), dtype=torch.float32, device=dev)
+    term_obs = torch.empty((2 * n, 98), dtype=torch.float32, device=dev)
+    fused_rows_checked = 0
+    steps = 0
+    while int(env.finished_ctrl[0]) < episodes:
+        env.rollout(1, _lib.PLAYER_CURRENT, out=buf)             # the benchmarked kernel, ring on
+        steps += 1
+        done = env.done.bool()
+        # the row the fused kernel wrote for the player to move == that player's row of the both-views encoder
+        info = env.information_state_tensor(_lib.PLAYER_BOTH)
+        hb = env.tensor_row_hash(info).view(n, 2)
+        hf = env.tensor_row_hash(buf)
+        assert bool((hf == hb.gather(1, env.current_player.long().clamp(min=0).view(n, 1)).view(n)).all())
+        fused_rows_checked += n
+        ho = env.tensor_row_hash(env.observation_tensor(_lib.PLAYER_BOTH)).view(n, 2)
+        del info
+        # terminal states of this step's finished episodes, from the ring
+        _, ids, cnt = env.finished_information_state_tensor(_lib.PLAYER_BOTH, out=term_info)
+        _, ids2, cnt2 = env.finished_observation_tensor(_lib.PLAYER_BOTH, out=term_obs)
+        k = int(cnt.item())
+        assert k == int(cnt2.item()) == int(done.sum().item()) and bool((ids[:k] == ids2[:k]).all())
+        ids = ids[:k].long()
+        assert bool(done[ids].all()) and ids.unique().numel() == k
+        hti = env.tensor_row_hash(term_info[: 2 * k]).view(k, 2)
+        hto = env.tensor_row_hash(term_obs[: 2 * k]).view(k, 2)
+        rew, ret = env.rewards.to(torch.int64)[ids], env.returns.to(torch.int64)[ids]
+        f = d[ids]
+        for v in (torch.zeros(k, dtype=torch.int64, device=dev), torch.full((k,), 252, dtype=torch.int64, device=dev),
+                  torch.ones(k, dtype=torch.int64, device=dev), rew[:, 0] + 2, rew[:, 1] + 2, ret[:, 0] + 2, ret[:, 1] + 2,
+                  hti[:, 0], hti[:, 1], hto[:, 0], hto[:, 1]):
+            f = fold(f, v)
+        fin_digest.append(f)
+        fin_reports.append(reports[ids] + 1)
+        fin_env.append(ids)
+        # every env now sits at a decision node: fold it (finished envs start a new digest at their re-dealt state)
+        base = torch.where(done, torch.zeros_like(d), d)
+        zero = torch.zeros(n, dtype=torch.int64, device=dev)
+        new = base
+        new = fold(new, env.legal_mask.to(torch.int64) & 0xFFFFFFFF)
+        new = fold(new, env.current_player.to(torch.int64) & 0xFF)
+        new = fold(new, zero)
+        rew, ret = env.rewards.to(torch.int64), env.returns.to(torch.int64)
+        for t in (rew[:, 0], rew[:, 1], ret[:, 0], ret[:, 1]):
+            new = fold(new, torch.where(done, zero, t) + 2)
+        new = fold(fold(new, hb[:, 0]), hb[:, 1])
+        d = fold(fold(new, ho[:, 0]), ho[:, 1])
+        reports = torch.where(done, torch.ones_like(reports), reports + 1)
+    torch.cuda.synchronize()
+    t_gpu = time.time() - t0
+    records, dropped = env.finished_drain()
+    stats = env.stats()
+    rec = decode_finished_records(records)
+    gd = torch.cat(fin_digest).cpu().numpy().view(np.uint64)
+    gr = torch.cat(fin_reports).cpu().numpy()
+    ge = torch.cat(fin_env).cpu().numpy()
+    assert dropped == 0 and len(records) == len(gd) == stats["episodes"], (dropped, len(records), len(gd), stats["episodes"])
+    assert (rec["env"] == ge).all()
+    trajs = rec["trajectories"]
+    flat = np.concatenate([a for a, _ in trajs])
+    off = np.concatenate([[0], np.cumsum([len(a) for a, _ in trajs])]).astype(np.int64)
+    t0 = time.time()
+    dig, rep, bad = checker.replay_digest_batch(flat, off, threads)
+    t_cpu = time.time() - t0
+    mism = int((gd != dig).sum() + (gr != rep).sum()) + int(bad)
+    lens = np.diff(off)
+    meta_bad = int((rec["moves"] != lens).sum())
+    return {"checker": "reference (oracle/_ref/libcoup_ref.so)" if ref else "oracle C port", "mode": "auto-reset, fused rollout kernel, finished-episode ring",
+            "envs": int(n), "steps": steps, "episodes": int(len(gd)), "moves": int(lens.sum()), "reported_states": int(gr.sum()),
+            "fused_rows_checked": int(fused_rows_checked), "mismatching_trajectories": mism, "rejected_by_checker": int(bad),
+            "ring_meta_mismatches": meta_bad, "truncated_91_move_games": int((lens > 90).sum()),
+            "ring_truncated_flags": int(rec["truncated"].sum()), "gpu_seconds": round(t_gpu, 2),
+            "checker_seconds": round(t_cpu, 2), "checker_threads": threads,
+            "total_mismatches": mism + meta_bad}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--envs", type=int, default=1 << 20)
@@ -134,8 +230,13 @@ def main():
     ap.add_argument("--device", type=int, default=0)
     ap.add_argument("--threads", type=int, default=os.cpu_count() or 1)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--autoreset-envs", type=int, default=1 << 17)
+    ap.add_argument("--autoreset-episodes", type=int, default=1 << 20)
     args = ap.parse_args()
     res = check(args.envs, args.steered, args.seed, args.device, args.threads)
+    if args.autoreset_episodes > 0:
+        res["autoreset"] = check_autoreset(args.autoreset_envs, args.autoreset_episodes, args.seed + 17, args.device, args.threads)
+        res["total_mismatches"] += res["autoreset"]["total_mismatches"]
     text = json.dumps(res, indent=1)
     print(text)
     if args.out:
