@@ -733,8 +733,8 @@ int coup_vec_check_errors(coup_vec_env* env, void* stream) {
 }
 
 int coup_tensor_row_hash(const void* d_tensor, int dtype, uint32_t rows, uint32_t row_len, uint64_t* d_hash_out, void* stream) {
-  if (!d_tensor || !d_hash_out || !valid_dtype(dtype)) return fail(COUP_ERR_INVALID_ARG, "coup_tensor_row_hash: bad arguments");
   if (rows == 0) return COUP_OK;
+  if (!d_tensor || !d_hash_out || !valid_dtype(dtype)) return fail(COUP_ERR_INVALID_ARG, "coup_tensor_row_hash: bad arguments");
   const int dev = device_of(d_tensor);
   if (dev < 0) return fail(COUP_ERR_INVALID_ARG, "coup_tensor_row_hash: d_tensor is not a device pointer");
   DeviceGuard guard(dev);

@@ -13,6 +13,9 @@
 namespace coup {
 
 constexpr int kBlockThreads = 256;
+#ifndef COUP_ENV_BLOCKS
+#define COUP_ENV_BLOCKS 3   // resident CTAs per SM the env-only rollout is compiled for (3 -> 80 registers, no spills)
+#endif
 constexpr int kWarpsPerBlock = kBlockThreads / 32;
 constexpr int kUnitsPerInfoRow = kInfoStateSize / 4;  // 623 four-element units (16 B in fp32)
 constexpr int kRecWords = 21;                         // per-env encoder record in shared memory
@@ -91,14 +94,21 @@ struct StepResult {
   uint32_t final_moves;
 };
 
-// Re-deal a fresh episode into `s` (CoupState ctor + the 4 initial chance nodes).
+// Re-deal a fresh episode into `s` (CoupState ctor + the 4 initial chance nodes). With forced outcomes (known-answer
+// replay) the deals run through the generic chance loop, else through the closed form; both give the same state for the
+// same Philox words. Writes history word 0 and returns the number of deals made.
 __device__ __forceinline__ uint32_t deal_new_episode(Env& s, uint32_t* hist_row, const uint4& rnd,
                                                      const uint8_t* forced) {
-  s = initial_state();
-  HistoryWriter hw(hist_row);
-  uint32_t k = resolve_chance(s, rnd, 0, forced, hw);
-  hw.flush();
-  return k;
+  uint32_t codes = 0, n_codes = 0;
+  if (forced != nullptr) {
+    s = initial_state();
+    resolve_chance(s, rnd, 0, forced, codes, n_codes);
+  } else {
+    s = dealt_initial_state(rnd, codes);
+    n_codes = 4;
+  }
+  hist_row[0] = codes;
+  return n_codes;
 }
 
 // The episode of env `e` has just ended in terminal state `s` (its history row is flushed): append its trajectory log,
@@ -136,95 +146,108 @@ __global__ void k_step_prologue(unsigned long long* ring_ctrl, unsigned int* bat
   }
 }
 
+// One decision step of one env per lane: sample or take the action, apply it, resolve the chance nodes that follow,
+// log, hand a finished episode to the ring and (auto-reset) re-deal it. CONVERGENT: all 32 lanes of the warp call this
+// together (`active` = this lane has an env to step), so that the step is one instruction stream under warp-uniform
+// guards -- "does any lane finish an episode", "does any lane still have a deal pending" -- with selects inside.
+// Per-lane branches remain only around memory side effects (the history / ring writes of the ~2 lanes in 32 that end
+// an episode) and the once-in-10^6-episodes move cap that falls in the middle of a deal sequence.
 template <bool kSample>
 __device__ __forceinline__ StepResult step_env(Env& s, uint32_t* hist_row, uint32_t action_in,
                                                const uint8_t* forced, const EnvArrays& A, uint32_t e,
-                                               uint64_t step) {
+                                               uint64_t step, bool active) {
+  constexpr uint32_t kFull = 0xffffffffu;
   StepResult r;
-  r.stepped = false; r.illegal = false; r.n_legal_before = 0; r.chance_moves = 0;
-  r.finished = false; r.truncated = false; r.final_moves = 0;
+  r.chance_moves = 0; r.truncated = false; r.final_moves = 0;
   const uint64_t genv = A.global_env_offset + e;
   const bool auto_reset = (A.flags & COUP_FLAG_AUTO_RESET) != 0;
-  bool term = is_terminal(s);
-  r.done = term;
+  const bool term0 = is_terminal(s);
+  const bool chance0 = g_chance(s.g) != 0;
+  const uint32_t legal0 = legal_mask_decision(s);
+  const uint4 rnd = env_random(A.seed, genv, step, 0);
+  const uint32_t a = kSample ? sample_action(legal0, rnd.x) : action_in;
+  // go: a player action is applied. An env left at an explicit chance node (coup_vec_new_initial_state /
+  // coup_vec_apply_move) has no player to move and is refused like an illegal action.
+  const bool go = active && !term0 && !chance0 && a < 18u && ((legal0 >> a) & 1u);
+  r.stepped = go;
+  r.illegal = active && !term0 && !go;
+  r.n_legal_before = go ? popc32(legal0) : 0u;
+  s.g |= r.illegal ? kBitError : 0u;        // sticky; the reference would SpielFatalError / raise (rl_environment.py:270-280)
+  const uint32_t m0 = c_moves(s.c);
+  bool fin = false;       // an episode ended in this call
+  bool term = term0;      // the state left in `s` is terminal
+  // Rewards() / Returns() of the stepped state: deals change neither, and an env that does not step keeps its own.
   r.reward0 = c_reward0(s.c);
   r.return0 = returns_p0(s);
-  if (!term && g_chance(s.g)) {
-    // An env left at an explicit chance node (coup_vec_new_initial_state / coup_vec_apply_move) has no player to
-    // move: refuse instead of applying a player action to undealt hands.
-    s.g |= kBitError;
-    r.illegal = true;
-    r.legal = legal_mask_chance(s);
-    r.cur_player = COUP_CHANCE_PLAYER_ID;
-    return r;
-  }
-  if (!term) {
-    const uint32_t legal = legal_mask_decision(s);
-    const uint4 rnd = env_random(A.seed, genv, step, 0);
-    uint32_t a = kSample ? sample_action(legal, rnd.x) : action_in;
-    r.n_legal_before = __popc(legal);
-    if (a < 18u && ((legal >> a) & 1u)) {
-      HistoryWriter hw(hist_row);
-      apply_player_action(s, a, hw);
-      r.stepped = true;
-      // Chance words of this step: y/z/w of the step block, or -- when the action ended the episode and the env
-      // re-deals in place -- the four words of the reset block. One shared deal loop serves both.
-      uint4 cw = make_uint4(rnd.y, rnd.z, rnd.w, 0u);
-      term = is_terminal(s);
-      if (term) {
-        r.finished = true;
+  if (__any_sync(kFull, go)) {
+    Env t = s;
+    apply_player_action(t, a);
+    s.p[0] = go ? t.p[0] : s.p[0]; s.p[1] = go ? t.p[1] : s.p[1]; s.g = go ? t.g : s.g; s.c = go ? t.c : s.c;
+    r.reward0 = c_reward0(s.c);
+    r.return0 = returns_p0(s);
+    fin = go && is_terminal(s);
+    term = go ? fin : term0;
+    // pending history codes of this step: `n_codes` codes that become moves first .. of the row
+    uint32_t codes = a, n_codes = go ? 1u : 0u, first = m0;
+    if (__any_sync(kFull, fin)) {
+      if (fin) {                                   // memory side effects of the lanes that end an episode
         r.final_moves = c_moves(s.c);
         r.truncated = r.final_moves > kMaxGameLength;
-        r.done = true;
-        r.reward0 = c_reward0(s.c);
-        r.return0 = returns_p0(s);
-        hw.flush();
+        history_commit(hist_row, m0, a, 1u);
         ring_append(A, e, s, hist_row, step, r.truncated);
-        if (auto_reset) {
-          hw = HistoryWriter(hist_row);
-          s = initial_state();
-          cw = env_random(A.seed, genv, step, 1);
-          forced = nullptr;
-          term = false;
-        }
       }
-      // Deals never change who is alive, so inside the loop only the move cap (coup.cc:990) can end the game.
+      // Re-deal in place: the four words of the reset block and the closed-form deal, computed by the whole warp.
+      const uint4 rr = env_random(A.seed, genv, step, 1);
+      uint32_t fresh_codes;
+      const Env fresh = dealt_initial_state(rr, fresh_codes);
+      const bool redeal = fin && auto_reset;
+      s.p[0] = redeal ? fresh.p[0] : s.p[0]; s.p[1] = redeal ? fresh.p[1] : s.p[1];
+      s.g = redeal ? fresh.g : s.g; s.c = redeal ? fresh.c : s.c;
+      codes = redeal ? fresh_codes : codes;
+      n_codes = redeal ? 4u : (fin ? 0u : n_codes);      // a finished episode's last move is already in the row
+      first = redeal ? 0u : first;
+      r.chance_moves = redeal ? 4u : 0u;
+      term = redeal ? false : term;
+    }
+    // The deals that follow the action (at most three: Exchange after a lost challenge). Deals never change who is
+    // alive, so inside the loop only the move cap (coup.cc:990) can end the game; a freshly dealt or finished env has
+    // nothing pending.
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (!g_chance(s.g) || c_moves(s.c) > kMaxGameLength) break;
-        uint32_t card = sample_card(s, k == 0 ? cw.x : k == 1 ? cw.y : k == 2 ? cw.z : cw.w);
-        if (forced != nullptr) {
-          const uint32_t f = forced[k];
-          if (f < 5u && g_deck(s.g, f) != 0) card = f;
-        }
-        apply_chance(s, card, hw);
-        r.chance_moves++;
+    for (int k = 0; k < 3; ++k) {
+      const bool pend = go && g_chance(s.g) && c_moves(s.c) <= kMaxGameLength;
+      if (!__any_sync(kFull, pend)) break;
+      uint32_t card = sample_card(s, k == 0 ? rnd.y : k == 1 ? rnd.z : rnd.w);
+      if (forced != nullptr) {
+        const uint32_t f = pend ? forced[k] : 0xFFu;   // lanes without an env must not touch the array
+        card = (f < 5u && g_deck(s.g, f) != 0) ? f : card;
       }
-      hw.flush();
-      if (!r.finished) {
-        term = is_terminal(s);
-        r.done = term;
-        r.reward0 = c_reward0(s.c);
-        r.return0 = returns_p0(s);
-        if (term) {  // only reachable through the move cap in the middle of a deal sequence: rare slow path
-          r.finished = true;
-          r.final_moves = c_moves(s.c);
-          r.truncated = true;
-          ring_append(A, e, s, hist_row, step, true);
-          if (auto_reset) {
-            const uint4 rr = env_random(A.seed, genv, step, 1);
-            r.chance_moves += deal_new_episode(s, hist_row, rr, nullptr);
-            term = false;
-          }
-        }
+      Env t2 = s;
+      const uint32_t code = apply_chance(t2, card);
+      s.p[0] = pend ? t2.p[0] : s.p[0]; s.p[1] = pend ? t2.p[1] : s.p[1]; s.g = pend ? t2.g : s.g; s.c = pend ? t2.c : s.c;
+      codes |= pend ? code << (5u * n_codes) : 0u;
+      n_codes += pend ? 1u : 0u;
+      r.chance_moves += pend ? 1u : 0u;
+    }
+    if (n_codes) history_commit(hist_row, first, codes, n_codes);
+    if (go && !fin && c_moves(s.c) > kMaxGameLength) {
+      // the move cap fell in the middle of a deal sequence: once in ~10^6 episodes, a slow path of its own
+      fin = true;
+      term = true;
+      r.final_moves = c_moves(s.c);
+      r.truncated = true;
+      ring_append(A, e, s, hist_row, step, true);
+      if (auto_reset) {
+        const uint4 rr = env_random(A.seed, genv, step, 1);
+        r.chance_moves += deal_new_episode(s, hist_row, rr, nullptr);
+        term = false;
       }
-    } else {
-      s.g |= kBitError;  // sticky; the reference would SpielFatalError / raise (rl_environment.py:270-280)
-      r.illegal = true;
     }
   }
-  r.legal = term ? 0u : legal_mask_decision(s);
-  r.cur_player = term ? COUP_TERMINAL_PLAYER_ID : static_cast<int>(g_mover(s.g));
+  r.done = fin || (!go && term0);
+  r.finished = fin;
+  const bool chance = !term && g_chance(s.g);   // only an env that was refused at an explicit chance node
+  r.legal = term ? 0u : (chance ? legal_mask_chance(s) : legal_mask_decision(s));
+  r.cur_player = term ? COUP_TERMINAL_PLAYER_ID : (chance ? COUP_CHANCE_PLAYER_ID : static_cast<int>(g_mover(s.g)));
   return r;
 }
 
@@ -297,18 +320,19 @@ k_reset(EnvArrays A, const uint8_t* __restrict__ mask, const uint8_t* __restrict
 }
 
 // ---- step with caller-provided actions --------------------------------------------------------------
-__global__ void __launch_bounds__(kBlockThreads, 5)
+__global__ void __launch_bounds__(kBlockThreads, 4)
 k_step(EnvArrays A, const uint8_t* __restrict__ actions, const uint8_t* __restrict__ forced, uint64_t step) {
   __shared__ uint32_t s_stats[COUP_STATS_LEN];
   BlockStats st;
   st.init(s_stats);
   const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool active = e < A.n && actions[e] != 0xFFu;   // 0xFF: this env sits the step out, outputs keep their values
-  StepResult r = {};
+  const uint32_t action = e < A.n ? actions[e] : 0xFFu;
+  const bool active = action != 0xFFu;   // 0xFF: this env sits the step out, outputs keep their values
+  Env s = {};
+  if (active) s = load_env(A.state + e);
+  const StepResult r = step_env<false>(s, A.history + static_cast<size_t>(e) * kHistoryWords, action,
+                                       forced ? forced + static_cast<size_t>(e) * 4 : nullptr, A, e, step, active);
   if (active) {
-    Env s = load_env(A.state + e);
-    r = step_env<false>(s, A.history + static_cast<size_t>(e) * kHistoryWords, actions[e],
-                        forced ? forced + static_cast<size_t>(e) * 4 : nullptr, A, e, step);
     store_env(A.state + e, s);
     write_outputs(A, e, r);
   }
@@ -356,9 +380,10 @@ k_single_move(EnvArrays A, const uint8_t* __restrict__ moves_or_mask, int mode) 
         const bool chance = !term && g_chance(s.g);
         const uint32_t legal = term ? 0u : chance ? legal_mask_chance(s) : legal_mask_decision(s);
         if (mv < 18u && ((legal >> mv) & 1u)) {
-          HistoryWriter hw(hist_row);
-          if (chance) apply_chance(s, mv, hw); else apply_player_action(s, mv, hw);
-          hw.flush();
+          const uint32_t at = c_moves(s.c);
+          uint32_t code = mv;
+          if (chance) code = apply_chance(s, mv); else apply_player_action(s, mv);
+          history_commit(hist_row, at, code, 1u);
         } else {
           s.g |= kBitError;
           illegal = true;
@@ -385,9 +410,10 @@ __global__ void k_single_move_one(EnvArrays A, uint32_t slot, uint32_t mv, int m
     const bool chance = !term && g_chance(s.g);
     const uint32_t legal = term ? 0u : chance ? legal_mask_chance(s) : legal_mask_decision(s);
     if (mv < 18u && ((legal >> mv) & 1u)) {
-      HistoryWriter hw(hist_row);
-      if (chance) apply_chance(s, mv, hw); else apply_player_action(s, mv, hw);
-      hw.flush();
+      const uint32_t at = c_moves(s.c);
+      uint32_t code = mv;
+      if (chance) code = apply_chance(s, mv); else apply_player_action(s, mv);
+      history_commit(hist_row, at, code, 1u);
       *illegal_out = 0;
     } else {
       *illegal_out = 1;  // nothing changes: the caller raises, as ApplyAction would (spiel_utils.cc:119-137)
@@ -425,22 +451,24 @@ k_fork(EnvArrays D, const uint4* __restrict__ src_state, const uint32_t* __restr
   st.init(s_stats);
   const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
   const bool active = e < count;
-  StepResult r = {};
-  if (active) {
-    const uint32_t p = parent[e];
-    uint32_t* hist_row = D.history + static_cast<size_t>(e) * kHistoryWords;
-    Env s;
-    if (p < src_n) {
-      const uint4* src_row = reinterpret_cast<const uint4*>(src_history + static_cast<size_t>(p) * kHistoryWords);
-      uint4* dst_row = reinterpret_cast<uint4*>(hist_row);
+  const uint32_t p = active ? parent[e] : 0xFFFFFFFFu;
+  const bool valid = active && p < src_n;                  // out-of-range parents set the child's error bit
+  uint32_t* hist_row = D.history + static_cast<size_t>(e) * kHistoryWords;
+  Env s = initial_state();
+  bool parent_terminal = false;
+  if (valid) {
+    const uint4* src_row = reinterpret_cast<const uint4*>(src_history + static_cast<size_t>(p) * kHistoryWords);
+    uint4* dst_row = reinterpret_cast<uint4*>(hist_row);
 #pragma unroll
-      for (int k = 0; k < kHistoryWords / 4; ++k) dst_row[k] = src_row[k];
-      s = load_env(src_state + p);
-      const bool parent_terminal = is_terminal(s);
-      r = step_env<false>(s, hist_row, actions[e], forced ? forced + static_cast<size_t>(e) * 4 : nullptr, D, e, step);
-      if (parent_terminal) { s.g |= kBitError; r.illegal = true; }   // a terminal state has no children
-    } else {
-      s = initial_state();
+    for (int k = 0; k < kHistoryWords / 4; ++k) dst_row[k] = src_row[k];
+    s = load_env(src_state + p);
+    parent_terminal = is_terminal(s);
+  }
+  StepResult r = step_env<false>(s, hist_row, valid ? actions[e] : 0xFFu, forced ? forced + static_cast<size_t>(e) * 4 : nullptr,
+                                 D, e, step, valid);
+  if (active) {
+    if (parent_terminal) { s.g |= kBitError; r.illegal = true; }   // a terminal state has no children
+    if (!valid) {
       s.g |= kBitError;
       r.illegal = true; r.done = false; r.legal = 0; r.cur_player = COUP_CHANCE_PLAYER_ID;
     }
@@ -1035,7 +1063,7 @@ k_encode_obs(Src src, int player_sel, T* __restrict__ out, int use_bulk, uint32_
 
 // ---- fused random rollout step: sample -> step -> chance -> [auto-reset] -> outputs -> encode -------
 template <typename T, bool kEncode>
-__global__ void __launch_bounds__(kBlockThreads, kEncode ? 4 : 5)   // rules only: cap registers for 5 blocks/SM
+__global__ void __launch_bounds__(kBlockThreads, 4)
 k_rollout(EnvArrays A, uint64_t step, int player_sel, T* __restrict__ out, uint32_t stride) {
   __shared__ uint32_t s_stats[COUP_STATS_LEN];
   __shared__ uint32_t s_rec[kEncode ? kWarpsPerBlock : 1][kEncode ? 32 * kRecWords : 1];
@@ -1045,11 +1073,11 @@ k_rollout(EnvArrays A, uint64_t step, int player_sel, T* __restrict__ out, uint3
   const uint32_t e0 = (blockIdx.x * kWarpsPerBlock + warp) * 32u;
   const uint32_t e = e0 + lane;
   const bool active = e < A.n;
-  StepResult r = {};
+  Env s = {};
+  uint32_t* hist_row = A.history + static_cast<size_t>(e) * kHistoryWords;
+  if (active) s = load_env(A.state + e);
+  const StepResult r = step_env<true>(s, hist_row, 0, nullptr, A, e, step, active);
   if (active) {
-    Env s = load_env(A.state + e);
-    uint32_t* hist_row = A.history + static_cast<size_t>(e) * kHistoryWords;
-    r = step_env<true>(s, hist_row, 0, nullptr, A, e, step);
     store_env(A.state + e, s);
     write_outputs(A, e, r);
     if (kEncode) fill_record(&s_rec[warp][lane * kRecWords], s, hist_row, player_sel);
@@ -1070,7 +1098,7 @@ k_rollout(EnvArrays A, uint64_t step, int player_sel, T* __restrict__ out, uint3
 // Env-only rollout of `n_steps` steps in ONE launch: envs are independent, so a thread keeps its env in registers across
 // steps (one 16-byte load and store, one set of outputs, one launch instead of n_steps of each); the history row and
 // the statistics are updated every step exactly as k_rollout<T, false> does, and step k uses Philox counter step + k.
-__global__ void __launch_bounds__(kBlockThreads, 5)
+__global__ void __launch_bounds__(kBlockThreads, COUP_ENV_BLOCKS)
 k_rollout_env_multi(EnvArrays A, uint64_t step, int n_steps) {
   __shared__ uint32_t s_stats[COUP_STATS_LEN];
   BlockStats st;
@@ -1082,7 +1110,7 @@ k_rollout_env_multi(EnvArrays A, uint64_t step, int n_steps) {
   if (active) s = load_env(A.state + e);
   StepResult r = {};
   for (int k = 0; k < n_steps; ++k) {
-    if (active) r = step_env<true>(s, hist_row, 0, nullptr, A, e, step + static_cast<uint64_t>(k));
+    r = step_env<true>(s, hist_row, 0, nullptr, A, e, step + static_cast<uint64_t>(k), active);
     account(st, r, active);
   }
   if (active) {
@@ -1108,11 +1136,11 @@ k_rollout_tma(EnvArrays A, uint64_t step, int player_sel, T* __restrict__ out, u
   const bool block_full = b0 + kTmaWarpsPerBlock * 32u <= A.n;  // uniform over the block
   const bool both = player_sel == COUP_PLAYER_BOTH;
   if (block_full) zero_stage(sm.stage, lane);
-  StepResult r = {};
+  Env s = {};
+  uint32_t* hist_row = A.history + static_cast<size_t>(e) * kHistoryWords;
+  if (active) s = load_env(A.state + e);
+  const StepResult r = step_env<true>(s, hist_row, 0, nullptr, A, e, step, active);
   if (active) {
-    Env s = load_env(A.state + e);
-    uint32_t* hist_row = A.history + static_cast<size_t>(e) * kHistoryWords;
-    r = step_env<true>(s, hist_row, 0, nullptr, A, e, step);
     store_env(A.state + e, s);
     write_outputs(A, e, r);
     fill_record(sm.recs + lane * kRecWords, s, hist_row, player_sel);
@@ -1202,7 +1230,7 @@ k_rollout_ws(EnvArrays A, uint64_t step, int player_sel, T* __restrict__ out, ui
           const uint32_t e = static_cast<uint32_t>(b) * kWsBatch + sub * 32 + lane;
           Env s = load_env(A.state + e);
           uint32_t* hist_row = A.history + static_cast<size_t>(e) * kHistoryWords;
-          const StepResult r = step_env<true>(s, hist_row, 0, nullptr, A, e, step);
+          const StepResult r = step_env<true>(s, hist_row, 0, nullptr, A, e, step, true);
           store_env(A.state + e, s);
           write_outputs(A, e, r);
           fill_record(recs + (sub * 32 + lane) * kRecWords, s, hist_row, player_sel);
@@ -1293,12 +1321,12 @@ k_rollout_incremental(EnvArrays A, uint64_t step, T* __restrict__ buf, uint32_t 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
   const bool active = e < A.n;
-  StepResult r = {};
+  Env s = {};
+  uint32_t* hist_row = A.history + static_cast<size_t>(e) * kHistoryWords;
+  if (active) s = load_env(A.state + e);
+  const uint32_t old_len = c_moves(s.c);
+  const StepResult r = step_env<true>(s, hist_row, 0, nullptr, A, e, step, active);
   if (active) {
-    Env s = load_env(A.state + e);
-    const uint32_t old_len = c_moves(s.c);
-    uint32_t* hist_row = A.history + static_cast<size_t>(e) * kHistoryWords;
-    r = step_env<true>(s, hist_row, 0, nullptr, A, e, step);
     store_env(A.state + e, s);
     write_outputs(A, e, r);
     if (r.stepped) {
