@@ -316,6 +316,60 @@ def main():
                                                "bytes_per_step": BYTES_PER_STEP_INCREMENTAL_F32}
         del inc
         torch.cuda.empty_cache()
+
+        # ---- every other kernel of SURVEY section 8(a), one at a time: algorithmic bytes per env and the fraction of
+        # the HBM peak it reaches. Rows = envs (x2 for both views). Kernels whose working set fits the 126 MB L2 say so.
+        peak_gbs, _ = measured_peak()
+        kern = {}
+
+        def add(name, kernel, fn, bytes_per_env, reps, note=None):
+            fn()
+            msk = timed(lambda k: [fn() for _ in range(k)], reps)
+            per_s = reps * n * world / (msk * 1e-3)
+            gbs = bytes_per_env * per_s / world / 1e9
+            kern[name] = {"kernel": kernel, "envs_per_s": per_s, "us_per_launch": 1e3 * msk / reps, "bytes_per_env": bytes_per_env,
+                          "hbm_gbs": gbs, "frac": gbs / peak_gbs}
+            if note:
+                kern[name]["note"] = note
+
+        for dt, tag, es in ((torch.float32, "f32", 4), (torch.uint8, "u8", 1)):
+            for sel2, views, vt in ((_lib.PLAYER_CURRENT, 1, "one_view"), (_lib.PLAYER_BOTH, 2, "both_views")):
+                o = torch.empty((views * n, 98), dtype=dt, device=dev)
+                add(f"obs98_{tag}_{vt}", "k_encode_obs", lambda: env.observation_tensor(sel2, out=o), 16 + views * 98 * es, 50,
+                    None if views * n * 98 * es > (1 << 28) else "output %d MB: partly L2-resident" % (views * n * 98 * es >> 20))
+                del o
+        for dt, tag, es in ((torch.float32, "f32", 4), (torch.uint8, "u8", 1)):
+            o = torch.empty((2 * n, 2492), dtype=dt, device=dev)
+            add(f"info_state_{tag}_both_views", "k_encode_info_tma", lambda: env.information_state_tensor(_lib.PLAYER_BOTH, out=o),
+                80 + 2 * 2492 * es, 20)
+            del o
+        o = torch.empty((n, 2492), dtype=torch.float32, device=dev)
+        acts = torch.empty(n, dtype=torch.uint8, device=dev)
+
+        def step_pair():
+            env.sample_uniform(out=acts)
+            env.step(acts)
+            env.information_state_tensor(_lib.PLAYER_CURRENT, out=o)
+        add("sample_uniform+step+encode_f32", "k_sample_uniform, k_step, k_encode_info_tma (the unfused form of the headline step, "
+            "what coup_vec_step_host_packed launches)", step_pair, 17 + 42 + 80 + 9968, 50)
+        del o
+
+        def step_only():
+            env.sample_uniform(out=acts)
+            env.step(acts)
+        add("sample_uniform+step", "k_sample_uniform, k_step", step_only, 17 + 42, 200,
+            "state + history + outputs = 100 MB: L2-resident; instruction bound")
+        logits = torch.randn((n, 18), device=dev)
+        probs = torch.empty((n, 18), device=dev)
+        add("sample_policy_f32", "k_sample_policy", lambda: env.sample_policy(logits, probs_out=probs, actions_out=acts), 72 + 4 + 1 + 72, 200,
+            "logits + probs = 151 MB: about L2 size")
+        add("sample_policy_f32_no_probs", "k_sample_policy", lambda: env.sample_policy(logits, actions_out=acts), 72 + 4 + 1, 200,
+            "L2-resident")
+        dense = torch.empty((n, 18), dtype=torch.uint8, device=dev)
+        add("legal_actions_mask", "k_legal_actions_mask", lambda: env.legal_actions_mask(out=dense), 4 + 18, 200, "23 MB: L2-resident")
+        del logits, probs, dense, acts
+        extra["kernels"] = kern
+        torch.cuda.empty_cache()
         out = None if torch_dtype is None else torch.empty((n, 2492), dtype=torch_dtype, device=dev)
 
     # ---- end to end through the host-buffer C-ABI call -------------------------------------------

@@ -313,6 +313,39 @@ int coup_records_information_state_tensor(coup_vec_env* env, const uint32_t* d_r
 int coup_records_observation_tensor(coup_vec_env* env, const uint32_t* d_records, const uint32_t* d_indices, uint32_t count,
                                     int player, int dtype, void* d_out, void* stream);
 
+/* ---- self-play recording fused into the step ------------------------------------------------------------------------
+ * coup_vec_step_record = coup_vec_step that also keeps what the reference's learning agents keep per decision, without a
+ * host round trip and without materialising tensors (the caller owns all buffers, device memory, zero-initialised):
+ *   NFSP supervised-learning reservoir (python/algorithms/nfsp.py:226-242,322-371): every env that is about to act offers
+ *     Transition(info_state, action_probs, legal_actions_mask). The element with running index t (= reservoir_offered +
+ *     env slot; the caller adds num_envs to reservoir_offered after every call) lands in slot t while the buffer fills,
+ *     afterwards in slot randint(0, t) if that is < capacity; of several elements drawing one slot in the same call the
+ *     later one wins, as it would sequentially. d_reservoir_records[slot] = packed record of the state (meta: env slot,
+ *     seat<<31 | legal mask, t lo, t hi), d_reservoir_probs[slot] = the 18 probabilities given in d_action_probs.
+ *   DQN replay (python/algorithms/dqn.py:30-32,223-246; the loop of coup_experiments/scripts/nfsp.py:134-144): per
+ *     (env, seat) the previous decision is kept in d_pending; when that seat acts again, and for BOTH seats when the
+ *     episode ends, Transition(info_state, action, reward, next_info_state, is_final_step, legal_actions_mask) is appended
+ *     at position (*d_replay_total)++ % replay_capacity of d_transitions as two packed records: [0] the earlier state
+ *     (meta: env slot, seat<<31 | action | (reward+2)<<5 | is_final<<8, ticket lo, ticket hi), [1] the later state (meta:
+ *     env slot, seat<<31 | legal mask of the later state). Rewards that fall between a seat's own turns are dropped, as
+ *     in the reference. Order of the transitions of one call is unspecified.
+ * Records turn into info-state rows with coup_records_information_state_tensor(..., COUP_PLAYER_FROM_RECORD, ...).
+ * Either half may be disabled with NULL pointers. Works with COUP_FLAG_AUTO_RESET (finished envs are re-dealt in place;
+ * their terminal observations go into the final transitions first). */
+typedef struct coup_recorder_buffers {
+  uint32_t* d_reservoir_records;  /* [reservoir_capacity][COUP_RECORD_WORDS] or NULL */
+  float* d_reservoir_probs;       /* [reservoir_capacity][18] */
+  uint64_t* d_reservoir_winner;   /* [reservoir_capacity] scratch, zero-initialised once */
+  uint64_t reservoir_capacity;
+  uint64_t reservoir_offered;     /* elements offered by earlier calls */
+  uint32_t* d_transitions;        /* [replay_capacity][2][COUP_RECORD_WORDS] or NULL */
+  uint64_t replay_capacity;
+  uint64_t* d_replay_total;       /* one device counter */
+  uint32_t* d_pending;            /* [num_envs][2][COUP_RECORD_WORDS], zero-initialised once */
+} coup_recorder_buffers;
+int coup_vec_step_record(coup_vec_env* env, const uint8_t* d_actions, const float* d_action_probs,
+                         const coup_recorder_buffers* buffers, void* stream);
+
 /* ---- host-buffer convenience path (what a host-driven caller such as rl_environment would use):
  * copies uint8[num_envs] actions from (pinned) host memory, steps, optionally encodes the current
  * player's info-state into d_tensor_out (device; may be NULL) and copies legal_mask / current_player /

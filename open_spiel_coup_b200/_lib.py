@@ -49,6 +49,7 @@ EXPORTED_SYMBOLS = [
     "coup_vec_finished_ring_enable", "coup_vec_finished_ring", "coup_vec_finished_ring_ctrl", "coup_vec_finished_ring_capacity",
     "coup_vec_finished_drain", "coup_vec_finished_information_state_tensor", "coup_records_information_state_tensor",
     "coup_vec_finished_observation_tensor", "coup_records_observation_tensor", "coup_vec_observation_tensor_gather",
+    "coup_vec_step_record",
     "coup_tensor_row_hash", "coup_vec_snapshot_size", "coup_vec_snapshot", "coup_vec_restore", "coup_vec_step_counter", "coup_vec_set_step_counter",
 ]
 
@@ -65,6 +66,16 @@ class VecOpts(C.Structure):
         ("global_env_offset", C.c_uint64),
         ("flags", C.c_uint32),
         ("reserved", C.c_uint32),
+    ]
+
+
+class RecorderBuffers(C.Structure):
+    """coup_recorder_buffers (include/coup_b200.h)."""
+    _fields_ = [
+        ("d_reservoir_records", C.c_void_p), ("d_reservoir_probs", C.c_void_p), ("d_reservoir_winner", C.c_void_p),
+        ("reservoir_capacity", C.c_uint64), ("reservoir_offered", C.c_uint64),
+        ("d_transitions", C.c_void_p), ("replay_capacity", C.c_uint64), ("d_replay_total", C.c_void_p),
+        ("d_pending", C.c_void_p),
     ]
 
 
@@ -121,6 +132,7 @@ def load():
     lib.coup_vec_finished_observation_tensor.argtypes = [vp, C.c_int, C.c_int, vp, C.c_uint32, vp, vp, vp]
     lib.coup_records_observation_tensor.argtypes = [vp, vp, vp, C.c_uint32, C.c_int, C.c_int, vp, vp]
     lib.coup_vec_observation_tensor_gather.argtypes = [vp, vp, C.c_uint32, C.c_int, C.c_int, vp, vp]
+    lib.coup_vec_step_record.argtypes = [vp, vp, vp, C.POINTER(RecorderBuffers), vp]
     lib.coup_records_information_state_tensor.argtypes = [vp, vp, vp, C.c_uint32, C.c_int, C.c_int, vp, C.c_uint32, vp]
     lib.coup_vec_information_state_tensor.argtypes = [vp, C.c_int, C.c_int, vp, vp]
     lib.coup_vec_information_state_tensor_strided.argtypes = [vp, C.c_int, C.c_int, vp, C.c_uint32, vp]

@@ -317,6 +317,33 @@ int coup_vec_step(coup_vec_env* env, const uint8_t* d_actions, const uint8_t* d_
   return launch_status("k_step");
 }
 
+int coup_vec_step_record(coup_vec_env* env, const uint8_t* d_actions, const float* d_action_probs,
+                         const coup_recorder_buffers* b, void* stream) {
+  if (!env || !d_actions || !b) return fail(COUP_ERR_INVALID_ARG, "coup_vec_step_record: null argument");
+  const bool reservoir = b->d_reservoir_records != nullptr, replay = b->d_transitions != nullptr;
+  if (reservoir && (!b->d_reservoir_probs || !b->d_reservoir_winner || !d_action_probs || b->reservoir_capacity == 0))
+    return fail(COUP_ERR_INVALID_ARG, "coup_vec_step_record: incomplete reservoir buffers");
+  if (replay && (!b->d_replay_total || !b->d_pending || b->replay_capacity == 0))
+    return fail(COUP_ERR_INVALID_ARG, "coup_vec_step_record: incomplete replay buffers");
+  DeviceGuard guard(env->opts.device);
+  RecorderArrays R{};
+  if (reservoir) {
+    R.res_records = b->d_reservoir_records; R.res_probs = b->d_reservoir_probs;
+    R.res_winner = reinterpret_cast<unsigned long long*>(b->d_reservoir_winner);
+    R.res_capacity = b->reservoir_capacity; R.res_base = b->reservoir_offered;
+  }
+  if (replay) {
+    R.transitions = b->d_transitions; R.rb_capacity = b->replay_capacity;
+    R.rb_total = reinterpret_cast<unsigned long long*>(b->d_replay_total); R.pending = b->d_pending;
+  }
+  step_prologue(env, false, S(stream));
+  if (reservoir)
+    k_reservoir_claim<<<blocks_for(env->A.n), kBlockThreads, 0, S(stream)>>>(env->A, R, d_actions, env->step_counter);
+  k_step_record<<<blocks_for(env->A.n), kBlockThreads, 0, S(stream)>>>(env->A, R, d_actions, d_action_probs, env->step_counter);
+  env->step_counter++;
+  return launch_status("k_step_record");
+}
+
 int coup_vec_new_initial_state(coup_vec_env* env, const uint8_t* d_mask, void* stream) {
   if (!env) return fail(COUP_ERR_INVALID_ARG, "null handle");
   DeviceGuard guard(env->opts.device);

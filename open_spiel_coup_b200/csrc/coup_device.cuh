@@ -110,13 +110,15 @@ COUP_FN uint32_t hand_down_mask(uint32_t h) { return ~h & 0x1111u; }  // empties
 COUP_FN uint32_t hand_face_up_count(uint32_t h) {
   return popc32(h & 0x1111u) - popc32(hand_empty_mask(h));
 }
-// Insert a card keeping the order. Requires a free slot.
+// Insert a card keeping the order. Requires a free slot. The position is the number of slots <= key, counted for all
+// four slots at once: the nibbles are spread to bytes, and (0x10 + key - slot) keeps bit 4 exactly when slot <= key.
 COUP_FN uint32_t hand_insert(uint32_t h, uint32_t key) {
-  uint32_t pos = (hand_slot(h, 0) <= key) + (hand_slot(h, 1) <= key) + (hand_slot(h, 2) <= key) +
-                 (hand_slot(h, 3) <= key);
-  uint32_t sh = 4 * pos;
-  uint32_t low = h & ((1u << sh) - 1u);
-  uint32_t high = (h >> sh) << (sh + 4);
+  uint32_t x = (h | (h << 8)) & 0x00FF00FFu;
+  x = (x | (x << 4)) & 0x0F0F0F0Fu;                                   // byte i = slot i
+  const uint32_t le = ((key * 0x01010101u + 0x10101010u) - x) & 0x10101010u;
+  const uint32_t sh = 4u * popc32(le);
+  const uint32_t low = h & ((1u << sh) - 1u);
+  const uint32_t high = (h >> sh) << (sh + 4u);
   return (low | (key << sh) | high) & 0xFFFFu;
 }
 // vector::erase(begin()+slot)
@@ -318,9 +320,11 @@ COUP_FN void apply_player_action(Env& s, uint32_t a) {
   // ---- cards ---------------------------------------------------------------------------------------
   const bool lose = (d >> 17) & 1u, give_back = (d >> 18) & 1u, replace = (d >> 13) & 1u;
   const uint32_t flip = (d >> 15) & 3u;
-  // LoseCard k: slot k turns FaceUp, then SortCards (608-613)
+  // LoseCard k: slot k turns FaceUp, then SortCards (608-613). A player who has to lose a card holds exactly two
+  // (a hand of four is always followed by ExchangeReturn first), so sorting is one min/max of the two slots.
   const uint32_t lk = (a - kLoseCard1) & 1u;
-  const uint32_t h_lose = hand_insert(hand_remove(ch, lk), hand_slot(ch, lk) | 1u);
+  const uint32_t s0 = (ch & 15u) | (lk ^ 1u), s1 = ((ch >> 4) & 15u) | lk;
+  const uint32_t h_lose = 0xFF00u | umin32(s0, s1) | (umax32(s0, s1) << 4);
   // ExchangeReturn: slot pairs (i<j) for 12..17: (0,1)(0,2)(0,3)(1,2)(1,3)(2,3), packed 2 bits each; erase j, then i.
   const uint32_t rk = umin32(a - kExchangeReturn12, 5u);
   const uint32_t ri = (0x940u >> (2u * rk)) & 3u;    // 0,0,0,1,1,2
@@ -436,17 +440,12 @@ COUP_FN uint32_t pick(const uint4& r, int k) {
   return k == 0 ? r.x : k == 1 ? r.y : k == 2 ? r.z : r.w;
 }
 
-// k-th (0-based) set bit of a mask with more than k bits set, by a branch-free binary search on popcounts.
+// k-th (0-based) set bit of a mask with more than k bits set, k <= 7 (a Coup state has at most 7 legal actions, a deck
+// 5 card types): clear the lowest set bit k times, without a loop-carried branch.
 COUP_FN uint32_t kth_set_bit(uint32_t mask, uint32_t k) {
-  uint32_t pos = 0;
 #pragma unroll
-  for (uint32_t width = 16; width > 0; width >>= 1) {
-    const uint32_t low = popc32((mask >> pos) & ((1u << width) - 1u));
-    const bool up = k >= low;
-    k -= up ? low : 0u;
-    pos += up ? width : 0u;
-  }
-  return pos;
+  for (uint32_t i = 0; i < 7; ++i) mask = i < k ? mask & (mask - 1u) : mask;
+  return ffs32(mask) - 1u;
 }
 
 // Uniform legal action (benchmark_game.cc:96-99) from one uniform 32-bit word.

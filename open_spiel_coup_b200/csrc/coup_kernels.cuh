@@ -92,6 +92,7 @@ struct StepResult {
   bool finished;      // an episode ended in this call
   bool truncated;
   uint32_t final_moves;
+  Env final_state;    // valid when `finished`: the terminal state, before any re-deal (unused fields are optimised away)
 };
 
 // Re-deal a fresh episode into `s` (CoupState ctor + the 4 initial chance nodes). With forced outcomes (known-answer
@@ -152,10 +153,10 @@ __global__ void k_step_prologue(unsigned long long* ring_ctrl, unsigned int* bat
 // guards -- "does any lane finish an episode", "does any lane still have a deal pending" -- with selects inside.
 // Per-lane branches remain only around memory side effects (the history / ring writes of the ~2 lanes in 32 that end
 // an episode) and the once-in-10^6-episodes move cap that falls in the middle of a deal sequence.
-template <bool kSample>
+template <bool kSample, bool kLegalKnown = false>
 __device__ __forceinline__ StepResult step_env(Env& s, uint32_t* hist_row, uint32_t action_in,
                                                const uint8_t* forced, const EnvArrays& A, uint32_t e,
-                                               uint64_t step, bool active) {
+                                               uint64_t step, bool active, uint32_t legal_known = 0u) {
   constexpr uint32_t kFull = 0xffffffffu;
   StepResult r;
   r.chance_moves = 0; r.truncated = false; r.final_moves = 0;
@@ -163,7 +164,8 @@ __device__ __forceinline__ StepResult step_env(Env& s, uint32_t* hist_row, uint3
   const bool auto_reset = (A.flags & COUP_FLAG_AUTO_RESET) != 0;
   const bool term0 = is_terminal(s);
   const bool chance0 = g_chance(s.g) != 0;
-  const uint32_t legal0 = legal_mask_decision(s);
+  // kLegalKnown: the caller still holds the mask the previous step returned for this very state
+  const uint32_t legal0 = kLegalKnown ? legal_known : legal_mask_decision(s);
   const uint4 rnd = env_random(A.seed, genv, step, 0);
   const uint32_t a = kSample ? sample_action(legal0, rnd.x) : action_in;
   // go: a player action is applied. An env left at an explicit chance node (coup_vec_new_initial_state /
@@ -191,6 +193,7 @@ __device__ __forceinline__ StepResult step_env(Env& s, uint32_t* hist_row, uint3
     uint32_t codes = a, n_codes = go ? 1u : 0u, first = m0;
     if (__any_sync(kFull, fin)) {
       if (fin) {                                   // memory side effects of the lanes that end an episode
+        r.final_state = s;
         r.final_moves = c_moves(s.c);
         r.truncated = r.final_moves > kMaxGameLength;
         history_commit(hist_row, m0, a, 1u);
@@ -233,6 +236,7 @@ __device__ __forceinline__ StepResult step_env(Env& s, uint32_t* hist_row, uint3
       // the move cap fell in the middle of a deal sequence: once in ~10^6 episodes, a slow path of its own
       fin = true;
       term = true;
+      r.final_state = s;
       r.final_moves = c_moves(s.c);
       r.truncated = true;
       ring_append(A, e, s, hist_row, step, true);
@@ -262,36 +266,74 @@ __device__ __forceinline__ void write_outputs(const EnvArrays& A, uint32_t e, co
                    (static_cast<uint32_t>(r.return0 + 2) << 24);
 }
 
-// All counters of one warp-step in four warp reductions: small fields are packed side by side (a count
-// over 32 lanes fits 6 bits), summed with REDUX, and lanes 0..18 each add one counter to shared memory.
+// Statistics of the steps one lane makes, kept in registers as packed 8-bit (16-bit) per-lane counters and turned into
+// warp sums only when flushed: the accounting of a step is ~20 ALU instructions, and the 11 warp reductions + shared-memory
+// atomics are paid once per launch (or every kMaxAdds steps), not once per step. A lane may add() at most kMaxAdds times
+// between flushes (8-bit fields: one count per add).
+struct StatAcc {
+  static constexpr int kMaxAdds = 64;
+  uint32_t misc;                 // stepped | finished << 8 | truncated << 16 | illegal << 24
+  uint32_t chance;               // chance moves (<= 7 per step)
+  uint32_t moves;                // sum of final move numbers (<= 91 per step)
+  unsigned long long returns;    // Returns()[0] histogram of finished episodes, 5 bins x 8 bits
+  unsigned long long legal;      // legal-count histogram of the steps made, 8 bins x 8 bits
+  __device__ __forceinline__ void clear() { misc = chance = moves = 0u; returns = legal = 0ull; }
+  __device__ __forceinline__ void add(const StepResult& r, bool active) {
+    const bool stepped = active && r.stepped, finished = active && r.finished;
+    misc += (stepped ? 1u : 0u) | (finished ? 1u << 8 : 0u) | ((active && r.truncated) ? 1u << 16 : 0u) |
+            ((active && r.illegal) ? 1u << 24 : 0u);
+    chance += active ? r.chance_moves : 0u;
+    moves += finished ? r.final_moves : 0u;
+    returns += finished ? 1ull << (8 * (r.return0 + 2)) : 0ull;
+    legal += stepped ? 1ull << (8u * min(r.n_legal_before, 7u)) : 0ull;
+  }
+  // All 32 lanes together. Even/odd fields are summed as 16-bit pairs (64 adds x 32 lanes < 2^16).
+  __device__ __forceinline__ void flush(BlockStats& st) {
+    constexpr uint32_t kFull = 0xffffffffu, kEven = 0x00FF00FFu;
+    const uint32_t m0 = __reduce_add_sync(kFull, misc & kEven), m1 = __reduce_add_sync(kFull, (misc >> 8) & kEven);
+    const uint32_t ch = __reduce_add_sync(kFull, chance), mv = __reduce_add_sync(kFull, moves);
+    const uint32_t rl = static_cast<uint32_t>(returns), rh = static_cast<uint32_t>(returns >> 32);
+    const uint32_t r0 = __reduce_add_sync(kFull, rl & kEven), r1 = __reduce_add_sync(kFull, (rl >> 8) & kEven);
+    const uint32_t r2 = __reduce_add_sync(kFull, rh & 0xFFu);
+    const uint32_t ll = static_cast<uint32_t>(legal), lh = static_cast<uint32_t>(legal >> 32);
+    const uint32_t l0 = __reduce_add_sync(kFull, ll & kEven), l1 = __reduce_add_sync(kFull, (ll >> 8) & kEven);
+    const uint32_t l2 = __reduce_add_sync(kFull, lh & kEven), l3 = __reduce_add_sync(kFull, (lh >> 8) & kEven);
+    const int lane = threadIdx.x & 31;
+    uint32_t val = 0;
+    int idx = 0;
+    switch (lane) {
+      case 0: val = m0 & 0xFFFFu; idx = COUP_STAT_DECISION_STEPS; break;
+      case 1: val = m1 & 0xFFFFu; idx = COUP_STAT_EPISODES; break;
+      case 2: val = m0 >> 16; idx = COUP_STAT_TRUNCATED; break;
+      case 3: val = m1 >> 16; idx = COUP_STAT_ILLEGAL; break;
+      case 4: val = ch; idx = COUP_STAT_CHANCE_MOVES; break;
+      case 5: val = mv; idx = COUP_STAT_EPISODE_MOVES; break;
+      case 6: val = r0 & 0xFFFFu; idx = COUP_STAT_RETURN_HIST + 0; break;
+      case 7: val = r1 & 0xFFFFu; idx = COUP_STAT_RETURN_HIST + 1; break;
+      case 8: val = r0 >> 16; idx = COUP_STAT_RETURN_HIST + 2; break;
+      case 9: val = r1 >> 16; idx = COUP_STAT_RETURN_HIST + 3; break;
+      case 10: val = r2; idx = COUP_STAT_RETURN_HIST + 4; break;
+      case 11: val = l0 & 0xFFFFu; idx = COUP_STAT_LEGAL_HIST + 0; break;
+      case 12: val = l1 & 0xFFFFu; idx = COUP_STAT_LEGAL_HIST + 1; break;
+      case 13: val = l0 >> 16; idx = COUP_STAT_LEGAL_HIST + 2; break;
+      case 14: val = l1 >> 16; idx = COUP_STAT_LEGAL_HIST + 3; break;
+      case 15: val = l2 & 0xFFFFu; idx = COUP_STAT_LEGAL_HIST + 4; break;
+      case 16: val = l3 & 0xFFFFu; idx = COUP_STAT_LEGAL_HIST + 5; break;
+      case 17: val = l2 >> 16; idx = COUP_STAT_LEGAL_HIST + 6; break;
+      case 18: val = l3 >> 16; idx = COUP_STAT_LEGAL_HIST + 7; break;
+      default: break;
+    }
+    if (val) atomicAdd(&st.sm[idx], val);
+    clear();
+  }
+};
+
+// One step of one warp, accounted at once (the single-step kernels).
 __device__ __forceinline__ void account(BlockStats& st, const StepResult& r, bool active) {
-  const uint32_t nl = min(r.n_legal_before, 7u);
-  const bool stepped = active && r.stepped, finished = active && r.finished;
-  // A: stepped | finished<<6 | truncated<<12 | illegal<<18 | chance moves<<24 (<= 7 per lane)
-  uint32_t a = !active ? 0u : (r.stepped ? 1u : 0u) | (r.finished ? 1u << 6 : 0u) | (r.truncated ? 1u << 12 : 0u) |
-                                  (r.illegal ? 1u << 18 : 0u) | (r.chance_moves << 24);
-  // B: Returns()[0] histogram of finished episodes, 5 bins x 6 bits
-  uint32_t b = finished ? 1u << (6 * (r.return0 + 2)) : 0u;
-  // C: sum of final move numbers (12 bits, <= 32 x 91) | legal-count bins 0..2 ; D: legal-count bins 3..7
-  uint32_t c = (finished ? r.final_moves : 0u) | ((stepped && nl < 3u) ? 1u << (12u + 6u * nl) : 0u);
-  uint32_t d = (stepped && nl >= 3u) ? 1u << (6u * (nl - 3u)) : 0u;
-  a = __reduce_add_sync(0xffffffffu, a);
-  b = __reduce_add_sync(0xffffffffu, b);
-  c = __reduce_add_sync(0xffffffffu, c);
-  d = __reduce_add_sync(0xffffffffu, d);
-  const int lane = threadIdx.x & 31;
-  uint32_t val = 0;
-  int idx = 0;
-  if (lane == 0) { val = a & 63u; idx = COUP_STAT_DECISION_STEPS; }
-  else if (lane == 1) { val = (a >> 6) & 63u; idx = COUP_STAT_EPISODES; }
-  else if (lane == 2) { val = (a >> 12) & 63u; idx = COUP_STAT_TRUNCATED; }
-  else if (lane == 3) { val = (a >> 18) & 63u; idx = COUP_STAT_ILLEGAL; }
-  else if (lane == 4) { val = a >> 24; idx = COUP_STAT_CHANCE_MOVES; }
-  else if (lane == 5) { val = c & 4095u; idx = COUP_STAT_EPISODE_MOVES; }
-  else if (lane < 11) { val = (b >> (6 * (lane - 6))) & 63u; idx = COUP_STAT_RETURN_HIST + lane - 6; }
-  else if (lane < 14) { val = (c >> (12 + 6 * (lane - 11))) & 63u; idx = COUP_STAT_LEGAL_HIST + lane - 11; }
-  else if (lane < 19) { val = (d >> (6 * (lane - 14))) & 63u; idx = COUP_STAT_LEGAL_HIST + 3 + lane - 14; }
-  if (val) atomicAdd(&st.sm[idx], val);
+  StatAcc acc;
+  acc.clear();
+  acc.add(r, active);
+  acc.flush(st);
 }
 
 // ---- reset -------------------------------------------------------------------------------------
@@ -586,6 +628,143 @@ k_cfr_children(const uint32_t* __restrict__ expand, const int64_t* __restrict__ 
     action_out[pos] = static_cast<uint8_t>(a);
     ++pos;
   }
+}
+
+// ---- self-play recording fused into the step (coup_vec_step_record) -----------------------------------------------------
+// What the reference's agents keep per decision (python/algorithms/nfsp.py:226-242 `Transition(info_state, action_probs,
+// legal_actions_mask)` into a reservoir, :322-371; python/algorithms/dqn.py:30-32,223-246 `Transition(info_state, action,
+// reward, next_info_state, is_final_step, legal_actions_mask)` into a circular replay buffer) is recorded by the thread
+// that steps the env, as PACKED observation records: 96 bytes (history + state + meta) instead of a 2492-element row. A
+// record decodes into exactly the row the dense encoder writes (k_encode_info* with a RecordSource), so a learner
+// materialises rows only for the batch it samples.
+struct RecorderArrays {
+  uint32_t* res_records;            // [res_capacity][24]  NFSP reservoir, or nullptr
+  float* res_probs;                 // [res_capacity][18]
+  unsigned long long* res_winner;   // [res_capacity] running index + 1 of the element that owns the slot
+  unsigned long long res_capacity;
+  unsigned long long res_base;      // elements offered before this step; env e of this step is element res_base + e
+  uint32_t* transitions;            // [rb_capacity][2][24]  DQN replay (record of s, record of s'), or nullptr
+  unsigned long long rb_capacity;
+  unsigned long long* rb_total;     // transitions ever written (device counter)
+  uint32_t* pending;                // [n][2][24] the previous decision of each seat; bit 30 of meta word 1 = valid
+};
+
+// Reservoir slot of the element with running index t (nfsp.py:340-356): t itself while the buffer fills, afterwards
+// randint(0, t) if that is below the capacity. ~0ull = not stored.
+__device__ __forceinline__ unsigned long long reservoir_slot(const EnvArrays& A, const RecorderArrays& R, uint32_t e, uint64_t step) {
+  const unsigned long long t = R.res_base + e;
+  if (t < R.res_capacity) return t;
+  const uint4 rnd = env_random(A.seed, A.global_env_offset + e, step, 5);
+  const unsigned long long u = (static_cast<unsigned long long>(rnd.x) << 32) | rnd.y;
+  const unsigned long long draw = __umul64hi(u, t + 1ull);
+  return draw < R.res_capacity ? draw : ~0ull;
+}
+
+// Pass 1: every env offers its decision; of the elements that draw the same slot in one step the LATER one must win, as it
+// would sequentially, so slots are claimed with an atomic max of the running index before anything is written.
+__global__ void __launch_bounds__(kBlockThreads)
+k_reservoir_claim(EnvArrays A, RecorderArrays R, const uint8_t* __restrict__ actions, uint64_t step) {
+  const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= A.n || actions[e] == 0xFFu) return;
+  const unsigned long long slot = reservoir_slot(A, R, e, step);
+  if (slot != ~0ull) atomicMax(&R.res_winner[slot], R.res_base + e + 1ull);
+}
+
+__device__ __forceinline__ void store_record(uint32_t* dst, const uint4 (&h)[4], const Env& s, uint32_t m0, uint32_t m1,
+                                             uint32_t m2, uint32_t m3) {
+  uint4* d = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) d[k] = h[k];
+  d[4] = make_uint4(s.p[0], s.p[1], s.g, s.c);
+  d[5] = make_uint4(m0, m1, m2, m3);
+}
+
+// One replay transition: the seat's pending record becomes `info_state` (its meta word 1 gains reward and is_final), the
+// given observation becomes `next_info_state`. Slots from one atomic cursor bumped once per group of emitting lanes.
+__device__ __forceinline__ void emit_transition(const RecorderArrays& R, uint32_t* pend, int reward, const uint4 (&h)[4],
+                                                const Env& next, uint32_t e, uint32_t seat, uint32_t is_final,
+                                                uint32_t legal_next) {
+  const uint32_t peers = __activemask();
+  const uint32_t lane = threadIdx.x & 31u;
+  const int leader = __ffs(peers) - 1;
+  unsigned long long base = 0;
+  if (static_cast<int>(lane) == leader) base = atomicAdd(R.rb_total, static_cast<unsigned long long>(__popc(peers)));
+  base = __shfl_sync(peers, base, leader);
+  const unsigned long long ticket = base + __popc(peers & ((1u << lane) - 1u));
+  uint32_t* dst = R.transitions + (ticket % R.rb_capacity) * (2 * kRecordWords);
+  const uint4* p4 = reinterpret_cast<const uint4*>(pend);
+  uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+  for (int k = 0; k < 5; ++k) d4[k] = p4[k];
+  const uint4 pm = p4[5];   // env | seat<<31, valid<<30, action | - | -
+  d4[5] = make_uint4(pm.x, (pm.y & 0x8000001Fu) | (static_cast<uint32_t>(reward + 2) << 5) | (is_final << 8),
+                     static_cast<uint32_t>(ticket), static_cast<uint32_t>(ticket >> 32));
+  store_record(dst + kRecordWords, h, next, e, (seat << 31) | legal_next, 0u, 0u);
+}
+
+// Pass 2: reservoir commit, replay bookkeeping, and the step itself (same semantics as k_step).
+__global__ void __launch_bounds__(kBlockThreads)
+k_step_record(EnvArrays A, RecorderArrays R, const uint8_t* __restrict__ actions, const float* __restrict__ probs,
+              uint64_t step) {
+  __shared__ uint32_t s_stats[COUP_STATS_LEN];
+  BlockStats st;
+  st.init(s_stats);
+  const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t action = e < A.n ? actions[e] : 0xFFu;
+  const bool active = action != 0xFFu;
+  Env s = {};
+  uint32_t* hist_row = A.history + static_cast<size_t>(e) * kHistoryWords;
+  uint4 h[4] = {};
+  if (active) {
+    s = load_env(A.state + e);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) h[k] = reinterpret_cast<const uint4*>(hist_row)[k];
+  }
+  const bool deciding = active && !is_terminal(s) && !g_chance(s.g);
+  const uint32_t seat = g_mover(s.g);
+  const uint32_t legal0 = legal_mask_decision(s);
+  const uint32_t m0 = c_moves(s.c);
+  if (deciding && R.res_records != nullptr) {                      // nfsp.py:226-242
+    const unsigned long long slot = reservoir_slot(A, R, e, step);
+    const unsigned long long t = R.res_base + e;
+    if (slot != ~0ull && R.res_winner[slot] == t + 1ull) {
+      store_record(R.res_records + slot * kRecordWords, h, s, e, (seat << 31) | legal0, static_cast<uint32_t>(t),
+                   static_cast<uint32_t>(t >> 32));
+      float* dst = R.res_probs + slot * kNumActions;
+      const float* src = probs + static_cast<size_t>(e) * kNumActions;
+#pragma unroll
+      for (int a = 0; a < kNumActions; ++a) dst[a] = src[a];
+    }
+  }
+  if (deciding && R.transitions != nullptr) {                      // dqn.py:223-246: the seat acts again
+    uint32_t* pend = R.pending + (static_cast<size_t>(e) * 2 + seat) * kRecordWords;
+    const int rew0 = c_reward0(s.c);
+    if ((pend[21] >> 30) & 1u) emit_transition(R, pend, seat == 0u ? rew0 : -rew0, h, s, e, seat, 0u, legal0);
+    store_record(pend, h, s, e, (seat << 31) | (1u << 30) | action, 0u, 0u);
+  }
+  const StepResult r = step_env<false>(s, hist_row, action, nullptr, A, e, step, active);
+  if (active) {
+    store_env(A.state + e, s);
+    write_outputs(A, e, r);
+  }
+  if (r.finished && R.transitions != nullptr) {
+    // Every agent is stepped with the final time step (coup_experiments/scripts/nfsp.py:141-143). The finished episode's
+    // row: word 0 from before the step (a re-deal rewrites only that word), patched if the last action landed in it.
+    uint4 ht[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) ht[k] = reinterpret_cast<const uint4*>(hist_row)[k];
+    ht[0].x = m0 < 6u ? h[0].x | (action << (5u * m0)) : h[0].x;
+#pragma unroll
+    for (uint32_t p = 0; p < 2; ++p) {
+      uint32_t* pend = R.pending + (static_cast<size_t>(e) * 2 + p) * kRecordWords;
+      if ((pend[21] >> 30) & 1u) {
+        emit_transition(R, pend, p == 0u ? r.reward0 : -r.reward0, ht, r.final_state, e, p, 1u, 0u);
+        pend[21] = 0u;
+      }
+    }
+  }
+  account(st, r, active);
+  st.flush(A.stats);
 }
 
 // ---- uniform-random legal action (same draw the fused rollout would use at this step counter) ------
@@ -1109,10 +1288,14 @@ k_rollout_env_multi(EnvArrays A, uint64_t step, int n_steps) {
   uint32_t* hist_row = A.history + static_cast<size_t>(active ? e : 0) * kHistoryWords;
   if (active) s = load_env(A.state + e);
   StepResult r = {};
-  for (int k = 0; k < n_steps; ++k) {
-    r = step_env<true>(s, hist_row, 0, nullptr, A, e, step + static_cast<uint64_t>(k), active);
-    account(st, r, active);
+  r.legal = is_terminal(s) ? 0u : legal_mask_decision(s);   // from then on every step hands the next one its mask
+  StatAcc acc;
+  acc.clear();
+  for (int k = 0; k < n_steps; ++k) {                       // n_steps <= StatAcc::kMaxAdds (the host launches in chunks of 64)
+    r = step_env<true, true>(s, hist_row, 0, nullptr, A, e, step + static_cast<uint64_t>(k), active, r.legal);
+    acc.add(r, active);
   }
+  acc.flush(st);
   if (active) {
     store_env(A.state + e, s);
     write_outputs(A, e, r);
@@ -1195,6 +1378,9 @@ k_rollout_ws(EnvArrays A, uint64_t step, int player_sel, T* __restrict__ out, ui
   st.init(reinterpret_cast<uint32_t*>(smem_raw + kWsEncWarps * kStageBytes + kWsBufs * kWsRecBytes));
   const bool both = player_sel == COUP_PLAYER_BOTH;
   const bool rules = warp < kWsRulesWarps;
+  StatAcc acc;
+  acc.clear();
+  int acc_adds = 0;
   unsigned char* stage = rules ? nullptr : stage_base + static_cast<size_t>(warp - kWsRulesWarps) * kStageBytes;
   if (!rules) zero_stage(stage, lane);
   // Batches are handed out dynamically (global counter): SMs differ by ~20 % in achieved store bandwidth, so a
@@ -1234,7 +1420,8 @@ k_rollout_ws(EnvArrays A, uint64_t step, int player_sel, T* __restrict__ out, ui
           store_env(A.state + e, s);
           write_outputs(A, e, r);
           fill_record(recs + (sub * 32 + lane) * kRecWords, s, hist_row, player_sel);
-          account(st, r, true);
+          acc.add(r, true);
+          if (++acc_adds == StatAcc::kMaxAdds) { acc.flush(st); acc_adds = 0; }
         }
       }
       __threadfence_block();
@@ -1265,6 +1452,7 @@ k_rollout_ws(EnvArrays A, uint64_t step, int player_sel, T* __restrict__ out, ui
     }
   }
   if (!rules && lane == 0) tma_wait_all();
+  if (rules) acc.flush(st);
   st.flush(A.stats);
 #ifdef COUP_WS_DEBUG
   if (lane == 0 && (warp == 0 || warp == kWsRulesWarps)) {

@@ -9,10 +9,13 @@ softmax, zero the illegal actions, renormalise, sample), and the supervised-lear
 reservoir buffer (`nfsp.py:322-371`). PyTorch is used for the network and buffers only; environment
 rules, encoding and sampling are the CUDA kernels behind the C ABI.
 """
+import ctypes as C
+
 import torch
 from torch import nn
 
-from ._lib import INFO_STATE_SIZE, NUM_DISTINCT_ACTIONS, PLAYER_CURRENT
+from . import _lib
+from ._lib import INFO_STATE_SIZE, NUM_DISTINCT_ACTIONS, PLAYER_CURRENT, PLAYER_FROM_RECORD, RECORD_WORDS
 
 # Row stride of the policy input: 2492 padded to a multiple of 32 elements. K = 2492 is not a multiple of 8, which
 # takes a bf16 cuBLAS GEMM off its fast path (5.2 ms vs 0.93 ms for [2^18, K] x [K, 1024] on B200); the encoder
@@ -111,6 +114,81 @@ class ReservoirBuffer:
         return self.info_state[j], self.action_probs[j], self.legal_actions_mask[j]
 
 
+class DeviceRecorder:
+    """The reference agents' two data stores, filled by the step kernel itself (coup_vec_step_record,
+    include/coup_b200.h): the NFSP reservoir of `Transition(info_state, action_probs, legal_actions_mask)`
+    (nfsp.py:36-37,226-242,322-371) and the DQN replay buffer of `Transition(info_state, action, reward,
+    next_info_state, is_final_step, legal_actions_mask)` (dqn.py:30-80,223-246), both as PACKED 96-byte observation
+    records. `sample_*` decodes only the sampled records into network inputs. No per-step torch op, no host read-back;
+    the only host state is the count of offered reservoir elements, which is `num_envs` per step."""
+
+    def __init__(self, env, reservoir_capacity=0, replay_capacity=0, seed=0):
+        self.env, dev, n = env, env.device, env.num_envs
+        self.reservoir_capacity, self.replay_capacity = int(reservoir_capacity), int(replay_capacity)
+        self.offered = 0
+        z = lambda *shape, dtype=torch.int32: torch.zeros(shape, dtype=dtype, device=dev)
+        self.res_records = z(max(self.reservoir_capacity, 1), RECORD_WORDS)
+        self.res_probs = z(max(self.reservoir_capacity, 1), NUM_DISTINCT_ACTIONS, dtype=torch.float32)
+        self.res_winner = z(max(self.reservoir_capacity, 1), dtype=torch.int64)
+        self.transitions = z(max(self.replay_capacity, 1), 2, RECORD_WORDS)
+        self.replay_total = z(1, dtype=torch.int64)
+        self.pending = z(n, 2, RECORD_WORDS)
+        self._gen = torch.Generator(device=dev)
+        self._gen.manual_seed(seed)
+
+    def _buffers(self):
+        p = lambda t: C.c_void_p(t.data_ptr())
+        b = _lib.RecorderBuffers()
+        if self.reservoir_capacity:
+            b.d_reservoir_records, b.d_reservoir_probs, b.d_reservoir_winner = p(self.res_records), p(self.res_probs), p(self.res_winner)
+            b.reservoir_capacity, b.reservoir_offered = self.reservoir_capacity, self.offered
+        if self.replay_capacity:
+            b.d_transitions, b.replay_capacity = p(self.transitions), self.replay_capacity
+            b.d_replay_total, b.d_pending = p(self.replay_total), p(self.pending)
+        return b
+
+    def step(self, actions, action_probs=None):
+        """env.step(actions) + recording. `action_probs` float32 [num_envs, 18] is needed for the reservoir."""
+        env = self.env
+        if self.reservoir_capacity and (action_probs is None or action_probs.dtype != torch.float32 or not action_probs.is_contiguous()):
+            raise ValueError("the reservoir needs contiguous float32 action probabilities")
+        b = self._buffers()
+        _lib.check(env._lib.coup_vec_step_record(env._h, C.c_void_p(actions.data_ptr()),
+                                                 C.c_void_p(action_probs.data_ptr()) if action_probs is not None else None,
+                                                 C.byref(b), C.c_void_p(torch.cuda.current_stream(env.device).cuda_stream)))
+        self.offered += env.num_envs
+
+    # ---- learner side --------------------------------------------------------------------------------
+    @property
+    def reservoir_size(self):
+        return min(self.reservoir_capacity, self.offered)
+
+    @property
+    def replay_size(self):
+        return min(self.replay_capacity, int(self.replay_total.item()))
+
+    def sample_reservoir(self, batch_size, dtype=torch.float32):
+        """(info_state [b, 2492], action_probs [b, 18], legal mask bits int32 [b]) of uniformly drawn records."""
+        j = torch.randint(0, self.reservoir_size, (batch_size,), device=self.env.device, generator=self._gen)
+        info = self.env.records_information_state_tensor(self.res_records, j, PLAYER_FROM_RECORD, dtype=dtype)
+        return info, self.res_probs[j], self.res_records[j, 21] & 0x3FFFF
+
+    def decode_transitions(self, idx, dtype=torch.float32):
+        """The transitions at buffer positions `idx`: (info_state, action, reward, next_info_state, is_final_step,
+        legal mask bits of the next state)."""
+        recs = self.transitions.view(-1, RECORD_WORDS)
+        idx = idx.to(torch.int64)
+        info = self.env.records_information_state_tensor(recs, 2 * idx, PLAYER_FROM_RECORD, dtype=dtype)
+        nxt = self.env.records_information_state_tensor(recs, 2 * idx + 1, PLAYER_FROM_RECORD, dtype=dtype)
+        meta = self.transitions[idx, 0, 21]
+        return (info, (meta & 31).to(torch.uint8), (((meta >> 5) & 7) - 2).to(torch.int8), nxt, ((meta >> 8) & 1).to(torch.uint8),
+                self.transitions[idx, 1, 21] & 0x3FFFF)
+
+    def sample_replay(self, batch_size, dtype=torch.float32):
+        j = torch.randint(0, self.replay_size, (batch_size,), device=self.env.device, generator=self._gen)
+        return self.decode_transitions(j, dtype=dtype)
+
+
 # Upper bounds of the move-number buckets of `bucketed_policy_forward` and the first-layer K each needs:
 # history row i is move i of the episode (coup.cc:230-256), so a state with move number m has no non-zero beyond
 # column 62 + 18 m; K is that bound rounded up to a multiple of 64 (the last bucket takes the whole row).
@@ -169,7 +247,8 @@ class SelfPlayDataGen:
     actions (chance nodes and auto-reset are resolved inside the step kernel)."""
 
     def __init__(self, num_envs=1 << 18, policy=None, seed=1234, device=0, tensor_dtype=torch.bfloat16,
-                 reservoir_capacity=0, global_env_offset=0, bucketed_first_layer=False):
+                 reservoir_capacity=0, global_env_offset=0, bucketed_first_layer=False, replay_capacity=0,
+                 torch_reservoir=False):
         self.env = CoupVectorEnv(num_envs, seed=seed, device=device, global_env_offset=global_env_offset,
                                  auto_reset=True)
         self.bucketed_first_layer = bucketed_first_layer and isinstance(policy, (MLPPolicy, type(None)))
@@ -183,7 +262,12 @@ class SelfPlayDataGen:
         self.actions = torch.empty(num_envs, dtype=torch.uint8, device=dev)
         self.acting_player = torch.empty(num_envs, dtype=torch.int8, device=dev)
         self.legal_before = torch.empty(num_envs, dtype=torch.int32, device=dev)
-        self.reservoir = (ReservoirBuffer(reservoir_capacity, dev, seed=seed) if reservoir_capacity else None)
+        # Records are kept by the step kernel (DeviceRecorder). torch_reservoir=True keeps the older torch-op reservoir
+        # of dense uint8 rows instead (used by tests as a cross-check of the reservoir rule).
+        self.reservoir = (ReservoirBuffer(reservoir_capacity, dev, seed=seed) if reservoir_capacity and torch_reservoir else None)
+        self.recorder = None
+        if (reservoir_capacity and not torch_reservoir) or replay_capacity:
+            self.recorder = DeviceRecorder(self.env, 0 if torch_reservoir else reservoir_capacity, replay_capacity, seed=seed)
         self.steps = 0
 
     @torch.no_grad()
@@ -203,7 +287,10 @@ class SelfPlayDataGen:
                 self.reservoir.add(self.info_state[:, :INFO_STATE_SIZE], self.action_probs, self.legal_before)
             else:           # rows are in move-number order: line the other columns up with them
                 self.reservoir.add(self.info_state[:, :INFO_STATE_SIZE], self.action_probs[perm], self.legal_before[perm])
-        env.step(self.actions)
+        if self.recorder is not None:
+            self.recorder.step(self.actions, self.action_probs)      # step + reservoir + replay in the step kernel
+        else:
+            env.step(self.actions)
         self.steps += 1
         # After the call: env.rewards / env.returns / env.done describe the transition just made
         # (done envs already hold a freshly dealt episode; env.returns is the finished episode's return).

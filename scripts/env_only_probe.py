@@ -48,12 +48,13 @@ def main():
             t = timed(loop)
             out["sample_uniform_plus_step"] = {"steps_per_s": n * 200 / t, "ms_per_step": 1e3 * t / 200}
             child = CoupVectorEnv(n, seed=5, auto_reset=False)
-            parents = torch.randint(0, n, (n,), device=env.device, dtype=torch.int32)
             env.sample_uniform(out=acts)
-            a = acts[parents.long()].contiguous()
-            child.fork_from(env, parents, a)
-            t = timed(lambda: [child.fork_from(env, parents, a) for _ in range(50)])
-            out["fork"] = {"children_per_s": n * 50 / t, "ms_per_call": 1e3 * t / 50}
+            for tag, parents in (("random_parents", torch.randint(0, n, (n,), device=env.device, dtype=torch.int32)),
+                                 ("two_children_per_parent", (torch.arange(n, device=env.device, dtype=torch.int32) // 2))):
+                a = acts[parents.long()].contiguous()
+                child.fork_from(env, parents, a)
+                t = timed(lambda: [child.fork_from(env, parents, a) for _ in range(50)])
+                out["fork_" + tag] = {"children_per_s": n * 50 / t, "ms_per_call": 1e3 * t / 50}
             child.close()
         env.close()
     print(json.dumps(out))

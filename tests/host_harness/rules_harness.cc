@@ -145,14 +145,30 @@ long hh_random_games(int n_games, uint64_t seed, int steer, uint8_t* actions_out
 long hh_check_kth_set_bit(int bits) {
   long bad = 0;
   for (uint32_t mask = 1; mask < (1u << bits); ++mask)
-    for (uint32_t k = 0; k < popc32(mask); ++k)
+    for (uint32_t k = 0; k < popc32(mask) && k <= 7; ++k)
       if (kth_set_bit(mask, k) != naive_kth(mask, k)) ++bad;
-  // and some wide masks
-  uint64_t st = 99;
-  for (int i = 0; i < 200000; ++i) {
-    const uint32_t mask = static_cast<uint32_t>(splitmix(st)) | 1u;
-    const uint32_t k = static_cast<uint32_t>(splitmix(st) % popc32(mask));
-    if (kth_set_bit(mask, k) != naive_kth(mask, k)) ++bad;
+  return bad;
+}
+
+// hand_insert (all four slots compared at once) against the plain definition, over every sorted hand with a free slot.
+long hh_check_hand_insert(void) {
+  long bad = 0;
+  for (uint32_t h = 0; h < 0x10000u; ++h) {
+    uint32_t n[4];
+    bool ok = true;
+    for (int i = 0; i < 4; ++i) { n[i] = (h >> (4 * i)) & 15u; if (n[i] != 15u && n[i] > 9u) ok = false; }
+    for (int i = 0; i < 3; ++i) if (n[i] > n[i + 1]) ok = false;
+    if (!ok || n[3] != 15u) continue;
+    for (uint32_t key = 0; key <= 9; ++key) {
+      uint32_t want[5], m = 0;
+      bool placed = false;
+      for (int i = 0; i < 4; ++i) {
+        if (!placed && n[i] > key) { want[m++] = key; placed = true; }
+        want[m++] = n[i];
+      }
+      const uint32_t w = want[0] | (want[1] << 4) | (want[2] << 8) | (want[3] << 12);
+      if (hand_insert(h, key) != w) ++bad;
+    }
   }
   return bad;
 }

@@ -61,9 +61,9 @@ def test_selfplay_datagen_runs_and_records():
         assert legal.all()
     s = gen.env.stats()
     assert s["illegal"] == 0 and s["decision_steps"] == 40 * 4096 and s["episodes"] > 4096
-    r = gen.reservoir
-    assert r.size == 10000 and r.add_calls == 40 * 4096
-    info, probs, mask = r.sample(256)
+    r = gen.recorder
+    assert r.reservoir_size == 10000 and r.offered == 40 * 4096
+    info, probs, mask = r.sample_reservoir(256, dtype=torch.uint8)
     assert torch.allclose(probs.sum(1), torch.ones(256, device="cuda"), atol=1e-4)
     # a stored record is a real info state: exactly one observer bit, and it equals the player to move
     f = info.float()
@@ -72,6 +72,110 @@ def test_selfplay_datagen_runs_and_records():
     # stored probabilities vanish outside the stored legal mask
     bits = ((mask.view(-1, 1) >> torch.arange(18, device="cuda", dtype=torch.int32)) & 1).bool()
     assert (probs[~bits] == 0).all()
+
+
+def test_selfplay_datagen_torch_reservoir_still_works():
+    gen = SelfPlayDataGen(num_envs=1024, policy=MLPPolicy(), seed=9, reservoir_capacity=3000, torch_reservoir=True)
+    gen.run(10)
+    assert gen.reservoir.size == 3000 and gen.recorder is None
+
+
+def test_device_recorder_reservoir(oracle):
+    """The reservoir kept by the step kernel: every stored record is the decision it claims to be (its running index
+    t = step * num_envs + env names the step and the env; row, probabilities and legal mask are compared with what
+    the env showed at that step), slot t holds element t while the buffer fills, and afterwards the stored indices
+    are a uniform sample of everything offered (nfsp.py:322-371)."""
+    from open_spiel_coup_b200.selfplay import DeviceRecorder
+    n, cap, steps = 512, 4096, 64
+    env = CoupVectorEnv(n, seed=21, auto_reset=True)
+    rec = DeviceRecorder(env, reservoir_capacity=cap, seed=1)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    rows, probs_log, legal_log = [], [], []
+    for t in range(steps):
+        info = env.information_state_tensor(_lib.PLAYER_CURRENT, dtype=torch.uint8)
+        logits = torch.randn(n, 18, device="cuda", generator=g)
+        probs = torch.empty(n, 18, device="cuda")
+        acts = env.sample_policy(logits, probs_out=probs)
+        rows.append(info.cpu().numpy()); probs_log.append(probs.cpu().numpy()); legal_log.append(env.legal_mask.cpu().numpy())
+        rec.step(acts, probs)
+        if (t + 1) * n == cap:                                   # just full: slot i holds element i
+            assert torch.equal(rec.res_records[:, 22].long(), torch.arange(cap, device="cuda"))
+    env.check_errors()
+    assert rec.reservoir_size == cap and rec.offered == steps * n
+    t_idx = (rec.res_records[:, 22].long() & 0xFFFFFFFF).cpu().numpy()
+    assert len(np.unique(t_idx)) == cap                                           # an element is stored at most once
+    dec = env.records_information_state_tensor(rec.res_records, None, _lib.PLAYER_FROM_RECORD, dtype=torch.uint8).cpu().numpy()
+    st, e = t_idx // n, t_idx % n
+    assert (rec.res_records[:, 20].cpu().numpy() == e).all()
+    assert (dec == np.stack(rows)[st, e]).all()
+    assert (rec.res_probs.cpu().numpy() == np.stack(probs_log)[st, e]).all()
+    assert ((rec.res_records[:, 21].cpu().numpy() & 0x3FFFF) == np.stack(legal_log)[st, e]).all()
+    # uniform over [0, offered): chi-square over 8 equal bins of the running index (7 d.o.f., p < 1e-4 at 29.9)
+    counts = np.bincount(t_idx * 8 // (steps * n), minlength=8)
+    chi2 = float(((counts - cap / 8) ** 2 / (cap / 8)).sum())
+    assert chi2 < 29.9, (chi2, counts)
+    info, p, mask = rec.sample_reservoir(64, dtype=torch.bfloat16)
+    assert info.shape == (64, 2492) and torch.allclose(p.sum(1), torch.ones(64, device="cuda"), atol=1e-4)
+
+
+def test_device_recorder_replay_matches_reference_bookkeeping(oracle):
+    """The replay transitions written by the step kernel (auto-reset mode, packed records) against a sequential
+    re-enactment of the reference loop (nfsp.py:134-144 driving DQN.step/add_transition, dqn.py:175-246) over the same
+    games, with time steps produced by the CPU oracle. Finished games come from the ring."""
+    from open_spiel_coup_b200.selfplay import DeviceRecorder
+    from open_spiel_coup_b200.vector_env import decode_finished_records
+    n, steps = 96, 70
+    env = CoupVectorEnv(n, seed=31, auto_reset=True, finished_ring=1 << 12)
+    rec = DeviceRecorder(env, replay_capacity=1 << 15)
+    for _ in range(steps):
+        rec.step(env.sample_uniform())
+    env.check_errors()
+    recs, dropped = env.finished_drain()
+    assert dropped == 0
+    fin = decode_finished_records(recs)
+    open_hist = env.trajectories()
+    expected = []
+
+    def time_step(s):
+        return {"info": [oracle.info_state(s, p).astype(np.uint8) for p in (0, 1)], "legal": oracle.legal_mask(s),
+                "rewards": oracle.rewards(s), "cur": oracle.current_player(s), "last": oracle.is_terminal(s)}
+
+    def play(actions):
+        s = oracle.new_state()
+        prev = [None, None]
+        i = 0
+        while True:
+            while oracle.current_player(s) == -1:                       # rl_environment resolves chance nodes
+                oracle.apply(s, actions[i]); i += 1
+            ts = time_step(s)
+            if ts["last"]:
+                for p in (0, 1):                                        # every agent sees the final time step
+                    if prev[p] is not None:
+                        expected.append((prev[p][0][p].tobytes(), prev[p][1], ts["rewards"][p], ts["info"][p].tobytes(), 1, 0))
+                return
+            p = ts["cur"]
+            if i >= len(actions):
+                return                                                  # game still running on the device
+            if prev[p] is not None:
+                expected.append((prev[p][0][p].tobytes(), prev[p][1], ts["rewards"][p], ts["info"][p].tobytes(), 0, ts["legal"]))
+            a = actions[i]; i += 1
+            prev[p] = (ts["info"], a)
+            oracle.apply(s, a)
+
+    for acts, _ in fin["trajectories"]:
+        play(list(acts))
+    for e in range(n):
+        play(list(open_hist[e][0]))
+    total = int(rec.replay_total.item())
+    assert total == len(expected) and total < rec.replay_capacity
+    info, action, reward, nxt, final, legal = rec.decode_transitions(torch.arange(total, device="cuda"), dtype=torch.uint8)
+    got = sorted(zip([bytes(x) for x in info.cpu().numpy()], action.cpu().tolist(), [float(x) for x in reward.cpu().tolist()],
+                     [bytes(x) for x in nxt.cpu().numpy()], final.cpu().tolist(), legal.cpu().tolist()))
+    assert got == sorted(expected)
+    assert len(fin["env"]) > n and int(final.sum()) > n
+    # tickets are a permutation of 0..total-1: one slot per transition
+    tickets = rec.transitions[:total, 0, 22].long() & 0xFFFFFFFF
+    assert torch.equal(torch.sort(tickets).values, torch.arange(total, device="cuda"))
 
 
 def test_batched_evaluation_random_vs_random():

@@ -31,6 +31,7 @@ def harness():
         getattr(lib, name).argtypes = [C.c_long, C.c_uint64]
     lib.hh_check_kth_set_bit.restype = C.c_long
     lib.hh_check_kth_set_bit.argtypes = [C.c_int]
+    lib.hh_check_hand_insert.restype = C.c_long
     return lib
 
 
@@ -62,6 +63,7 @@ def _compare(got, want):
 
 def test_building_blocks(harness):
     assert harness.hh_check_kth_set_bit(18) == 0
+    assert harness.hh_check_hand_insert() == 0
     assert harness.hh_check_sample_card(2_000_000, 7) == 0
     assert harness.hh_check_closed_form_deal(2_000_000, 11) == 0
     assert harness.hh_check_history_commit(1_000_000, 13) == 0
