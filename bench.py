@@ -462,15 +462,33 @@ def main():
         torch.cuda.empty_cache()
         torch.manual_seed(args.seed)
         n_sp = 1 << 18
-        gen = SelfPlayDataGen(num_envs=n_sp, policy=None, seed=args.seed, device=local,
-                              global_env_offset=rank * n_sp, reservoir_capacity=0)
+        # Data generation, i.e. WITH the records the reference's agents keep (NFSP reservoir + DQN replay, thesis capacities
+        # scaled to the batch: a step offers 2^18 decisions): kept by the step kernel as packed 96-byte records.
+        cap_res, cap_rb = 1 << 22, 1 << 22
+        gen = SelfPlayDataGen(num_envs=n_sp, policy=None, seed=args.seed, device=local, global_env_offset=rank * n_sp,
+                              reservoir_capacity=cap_res, replay_capacity=cap_rb)
         gen.env.rollout(100)
-        gen.run(5)
+        gen.run(20)                      # fills the reservoir (16 steps) and gets past its start-up phase
         k_sp = max(10, min(K, 60))
         ms_sp = timed(lambda k: gen.run(k), k_sp)
+        # the recording step alone (k_reservoir_claim + k_step_record) against a plain k_step on the same slab
+        acts, probs = gen.actions, gen.action_probs
+        ms_rec = timed(lambda k: [gen.recorder.step(acts, probs) for _ in range(k)], 50)
+        ms_plain = timed(lambda k: [gen.env.step(acts) for _ in range(k)], 50)
+        # algorithmic bytes per env of the recording step: step itself 42; replay: history row 64 R, pending record 96 R + 96 W,
+        # one transition per decision 192 W; reservoir (full, t >> capacity): ~0; claims 8
+        rec_bytes = 42 + 64 + 96 + 96 + 192 + 8
+        peak_gbs, _ = measured_peak()
         selfplay = {"steps_per_s": k_sp * n_sp * world / (ms_sp * 1e-3), "envs_per_gpu": n_sp, "ms_per_step": ms_sp / k_sp,
                     "policy": "MLP 2492(+4 zero pad)-1024-1024-18 (bf16, torch), masked softmax sampling fused on device (k_sample_policy)",
-                    "note": "per step: encode bf16 info-state of the player to move, policy forward, masked sampling, env step"}
+                    "recording": "NFSP reservoir (%d) + DQN replay (%d) kept by the step kernel as packed records (coup_vec_step_record)" % (cap_res, cap_rb),
+                    "recording_step": {"kernel": "k_reservoir_claim + k_step_record", "us_per_launch": 1e3 * ms_rec / 50,
+                                       "plain_k_step_us": 1e3 * ms_plain / 50, "bytes_per_env": rec_bytes,
+                                       "hbm_gbs": rec_bytes * n_sp / (ms_rec / 50 * 1e-3) / 1e9,
+                                       "frac": rec_bytes * n_sp / (ms_rec / 50 * 1e-3) / 1e9 / peak_gbs,
+                                       "note": "slab + records of 2^18 envs (~90 MB) are L2-resident"},
+                    "note": "per step: encode bf16 info-state of the player to move, policy forward, masked sampling, "
+                            "env step + reservoir + replay records"}
         del gen
         torch.cuda.empty_cache()
 
