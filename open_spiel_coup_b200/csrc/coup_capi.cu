@@ -542,8 +542,7 @@ uint32_t* coup_vec_history(coup_vec_env* env) { return env ? env->A.history : nu
 int coup_vec_legal_actions_mask(coup_vec_env* env, uint8_t* d_out, void* stream) {
   if (!env || !d_out) return fail(COUP_ERR_INVALID_ARG, "coup_vec_legal_actions_mask: null argument");
   DeviceGuard guard(env->opts.device);
-  k_legal_actions_mask<<<blocks_for(static_cast<size_t>(env->A.n) * kNumActions), kBlockThreads, 0, S(stream)>>>(
-      env->A.legal, d_out, env->A.n);
+  k_legal_actions_mask<<<blocks_for(env->A.n), kBlockThreads, 0, S(stream)>>>(env->A.legal, d_out, env->A.n);
   return launch_status("k_legal_actions_mask");
 }
 

@@ -427,7 +427,9 @@ COUP_FN uint4 philox4x32_10(uint4 ctr, uint2 key) {
 
 // Stream layout: key = (global env id lo, global env id hi ^ seed lo);
 // counter = (step lo, step hi, purpose, seed hi). purpose 0: x = action choice, y/z/w = the up to
-// three chance draws that can follow one player action; purpose 1: the four deals of a reset.
+// three chance draws that can follow one player action -- or, when the action ends the episode and the env is re-dealt in
+// place, the four initial deals (y, y * 15 mod 2^32, z, w); purpose 1: the four deals of an explicit reset (and of the
+// re-deal after a game cut by the move cap in the middle of a deal sequence); purpose 2-4: CFR expansion; 5: reservoir.
 COUP_FN uint4 env_random(uint64_t seed, uint64_t global_env, uint64_t step, uint32_t purpose) {
   uint2 key = make_uint2(static_cast<uint32_t>(global_env),
                          static_cast<uint32_t>(global_env >> 32) ^ static_cast<uint32_t>(seed));

@@ -199,8 +199,10 @@ __device__ __forceinline__ StepResult step_env(Env& s, uint32_t* hist_row, uint3
         history_commit(hist_row, m0, a, 1u);
         ring_append(A, e, s, hist_row, step, r.truncated);
       }
-      // Re-deal in place: the four words of the reset block and the closed-form deal, computed by the whole warp.
-      const uint4 rr = env_random(A.seed, genv, step, 1);
+      // Re-deal in place with the closed-form deal, computed by the whole warp. An episode that ends AT the action has
+      // used none of the three deal words of its step block, so the four cards come from them: y serves two draws
+      // (floor(y * 15 / 2^32), then its remainder y * 15 mod 2^32, again uniform), z and w one each.
+      const uint4 rr = make_uint4(rnd.y, rnd.y * 15u, rnd.z, rnd.w);
       uint32_t fresh_codes;
       const Env fresh = dealt_initial_state(rr, fresh_codes);
       const bool redeal = fin && auto_reset;
@@ -328,12 +330,36 @@ struct StatAcc {
   }
 };
 
-// One step of one warp, accounted at once (the single-step kernels).
+// One step of one warp, accounted at once (the single-step kernels): small fields packed side by side (a count over
+// 32 lanes fits 6 bits), four warp reductions, and lanes 0..18 each add one counter to shared memory.
 __device__ __forceinline__ void account(BlockStats& st, const StepResult& r, bool active) {
-  StatAcc acc;
-  acc.clear();
-  acc.add(r, active);
-  acc.flush(st);
+  const uint32_t nl = min(r.n_legal_before, 7u);
+  const bool stepped = active && r.stepped, finished = active && r.finished;
+  // A: stepped | finished<<6 | truncated<<12 | illegal<<18 | chance moves<<24 (<= 7 per lane)
+  uint32_t a = !active ? 0u : (r.stepped ? 1u : 0u) | (r.finished ? 1u << 6 : 0u) | (r.truncated ? 1u << 12 : 0u) |
+                                  (r.illegal ? 1u << 18 : 0u) | (r.chance_moves << 24);
+  // B: Returns()[0] histogram of finished episodes, 5 bins x 6 bits
+  uint32_t b = finished ? 1u << (6 * (r.return0 + 2)) : 0u;
+  // C: sum of final move numbers (12 bits, <= 32 x 91) | legal-count bins 0..2 ; D: legal-count bins 3..7
+  uint32_t c = (finished ? r.final_moves : 0u) | ((stepped && nl < 3u) ? 1u << (12u + 6u * nl) : 0u);
+  uint32_t d = (stepped && nl >= 3u) ? 1u << (6u * (nl - 3u)) : 0u;
+  a = __reduce_add_sync(0xffffffffu, a);
+  b = __reduce_add_sync(0xffffffffu, b);
+  c = __reduce_add_sync(0xffffffffu, c);
+  d = __reduce_add_sync(0xffffffffu, d);
+  const int lane = threadIdx.x & 31;
+  uint32_t val = 0;
+  int idx = 0;
+  if (lane == 0) { val = a & 63u; idx = COUP_STAT_DECISION_STEPS; }
+  else if (lane == 1) { val = (a >> 6) & 63u; idx = COUP_STAT_EPISODES; }
+  else if (lane == 2) { val = (a >> 12) & 63u; idx = COUP_STAT_TRUNCATED; }
+  else if (lane == 3) { val = (a >> 18) & 63u; idx = COUP_STAT_ILLEGAL; }
+  else if (lane == 4) { val = a >> 24; idx = COUP_STAT_CHANCE_MOVES; }
+  else if (lane == 5) { val = c & 4095u; idx = COUP_STAT_EPISODE_MOVES; }
+  else if (lane < 11) { val = (b >> (6 * (lane - 6))) & 63u; idx = COUP_STAT_RETURN_HIST + lane - 6; }
+  else if (lane < 14) { val = (c >> (12 + 6 * (lane - 11))) & 63u; idx = COUP_STAT_LEGAL_HIST + lane - 11; }
+  else if (lane < 19) { val = (d >> (6 * (lane - 14))) & 63u; idx = COUP_STAT_LEGAL_HIST + 3 + lane - 14; }
+  if (val) atomicAdd(&st.sm[idx], val);
 }
 
 // ---- reset -------------------------------------------------------------------------------------
@@ -788,19 +814,38 @@ template <typename T> __device__ __forceinline__ float logit_to_float(T v);
 template <> __device__ __forceinline__ float logit_to_float<float>(float v) { return v; }
 template <> __device__ __forceinline__ float logit_to_float<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
 
+// Rows of 18 elements are 72 (36) bytes apart: a lane reading its own row touches a different cache line than its
+// neighbour for every element. The warp therefore moves its 32 rows -- one contiguous 2 304-byte span -- with coalesced
+// loads/stores through shared memory (row pitch 19 words: conflict-free) and each lane works on its row there.
+constexpr int kRowPitch = kNumActions + 1;
+
 template <typename T>
 __global__ void __launch_bounds__(kBlockThreads)
 k_sample_policy(EnvArrays A, const T* __restrict__ logits, float* __restrict__ probs_out,
                 uint8_t* __restrict__ actions_out, uint64_t step) {
-  const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= A.n) return;
-  const uint32_t legal = A.legal[e];
-  const T* row = logits + static_cast<size_t>(e) * kNumActions;
+  __shared__ float s_rows[kWarpsPerBlock][32 * kRowPitch];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t e0 = (blockIdx.x * kWarpsPerBlock + warp) * 32u;
+  if (e0 >= A.n) return;
+  const uint32_t e = e0 + lane;
+  const uint32_t span = min(32u, A.n - e0) * kNumActions;
+  float* rows = s_rows[warp];
+  const T* src = logits + static_cast<size_t>(e0) * kNumActions;
+#pragma unroll
+  for (uint32_t i = 0; i < kNumActions; ++i) {
+    const uint32_t j = lane + 32u * i;
+    if (j < span) {
+      const uint32_t r = (j * 3641u) >> 16;                    // j / 18 for j < 576
+      rows[r * kRowPitch + (j - r * kNumActions)] = logit_to_float<T>(src[j]);
+    }
+  }
+  __syncwarp();
+  const uint32_t legal = e < A.n ? A.legal[e] : 0u;
   float p[kNumActions];
   float mx = -INFINITY;
 #pragma unroll
   for (int a = 0; a < kNumActions; ++a) {
-    p[a] = logit_to_float<T>(row[a]);
+    p[a] = rows[lane * kRowPitch + a];
     if ((legal >> a) & 1u) mx = fmaxf(mx, p[a]);
   }
   // softmax over all actions followed by masking and renormalising == softmax over the legal ones;
@@ -826,21 +871,56 @@ k_sample_policy(EnvArrays A, const T* __restrict__ logits, float* __restrict__ p
       if (!found && ((legal >> a) & 1u) && u < cdf) { action = a; found = true; }
     }
   }
+  if (e < A.n) actions_out[e] = static_cast<uint8_t>(action);
   if (probs_out != nullptr) {
-    float* o = probs_out + static_cast<size_t>(e) * kNumActions;
+    __syncwarp();
 #pragma unroll
-    for (int a = 0; a < kNumActions; ++a) o[a] = legal ? p[a] : 0.f;
+    for (int a = 0; a < kNumActions; ++a) rows[lane * kRowPitch + a] = legal ? p[a] : 0.f;
+    __syncwarp();
+    float* dst = probs_out + static_cast<size_t>(e0) * kNumActions;
+#pragma unroll
+    for (uint32_t i = 0; i < kNumActions; ++i) {
+      const uint32_t j = lane + 32u * i;
+      if (j < span) {
+        const uint32_t r = (j * 3641u) >> 16;
+        dst[j] = rows[r * kRowPitch + (j - r * kNumActions)];
+      }
+    }
   }
-  actions_out[e] = static_cast<uint8_t>(action);
 }
 
 // ---- dense legal mask: uint8[n][18] (State::LegalActionsMask, spiel.cc:371-377) ----------------------
+// A warp expands the masks of 32 envs into one contiguous 576-byte span: 36 sixteen-byte stores, each byte's mask fetched
+// from the lane that holds it.
 __global__ void __launch_bounds__(kBlockThreads)
 k_legal_actions_mask(const uint32_t* __restrict__ legal, uint8_t* __restrict__ out, uint32_t n) {
-  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= static_cast<size_t>(n) * kNumActions) return;
-  const uint32_t e = static_cast<uint32_t>(i / kNumActions), a = static_cast<uint32_t>(i - static_cast<size_t>(e) * kNumActions);
-  out[i] = (legal[e] >> a) & 1u;
+  const int lane = threadIdx.x & 31;
+  const uint32_t e0 = (blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5)) * 32u;
+  if (e0 >= n) return;
+  const uint32_t mine = e0 + lane < n ? legal[e0 + lane] : 0u;
+  const uint32_t span = min(32u, n - e0) * kNumActions;                 // bytes of this warp
+  uint8_t* dst = out + static_cast<size_t>(e0) * kNumActions;
+  const bool vector_ok = (reinterpret_cast<uintptr_t>(dst) & 15u) == 0 && span == 32u * kNumActions;
+#pragma unroll
+  for (uint32_t i = 0; i < 2; ++i) {
+    const uint32_t unit = lane + 32u * i;                               // 16-byte unit of the span (36 of them)
+    uint32_t w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (uint32_t b = 0; b < 16; ++b) {
+      const uint32_t j = min(unit * 16u + b, 32u * kNumActions - 1u);
+      const uint32_t r = (j * 3641u) >> 16;
+      const uint32_t bit = (__shfl_sync(0xffffffffu, mine, static_cast<int>(r)) >> (j - r * kNumActions)) & 1u;
+      w[b >> 2] |= bit << (8u * (b & 3u));
+    }
+    if (unit < 36u) {
+      if (vector_ok) {
+        reinterpret_cast<uint4*>(dst)[unit] = make_uint4(w[0], w[1], w[2], w[3]);
+      } else {
+        for (uint32_t b = 0; b < 16; ++b)
+          if (unit * 16u + b < span) dst[unit * 16u + b] = static_cast<uint8_t>((w[b >> 2] >> (8u * (b & 3u))) & 1u);
+      }
+    }
+  }
 }
 
 // ---- tensor element types ------------------------------------------------------------------------

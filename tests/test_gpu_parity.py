@@ -632,8 +632,15 @@ def test_device_trajectories_reproduced_from_philox_and_oracle(oracle):
             s = states[e]
             la = oracle.legal_actions(s)
             assert oracle.apply(s, la[(int(w0[e, 0]) * len(la)) >> 32]) == 0
-            deal(s, w0[e, 1:])
             if oracle.is_terminal(s):
+                # an episode that ends at the action has used none of the step block's deal words: the in-place re-deal
+                # draws its four cards from them -- y twice (floor(y * 15 / 2^32), then the remainder y * 15 mod 2^32), z, w
+                y = int(w0[e, 1])
+                s = states[e] = oracle.new_state()
+                deal(s, [y, (y * 15) & 0xFFFFFFFF, int(w0[e, 2]), int(w0[e, 3])])
+                continue
+            deal(s, w0[e, 1:])
+            if oracle.is_terminal(s):          # move cap in the middle of a deal sequence: a reset block of its own
                 s = states[e] = oracle.new_state()
                 deal(s, w1[e])
         got = env.trajectories()
