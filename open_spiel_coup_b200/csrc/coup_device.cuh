@@ -113,6 +113,11 @@ COUP_FN uint32_t hand_face_up_count(uint32_t h) {
 // Insert a card keeping the order. Requires a free slot. The position is the number of slots <= key, counted for all
 // four slots at once: the nibbles are spread to bytes, and (0x10 + key - slot) keeps bit 4 exactly when slot <= key.
 COUP_FN uint32_t hand_insert(uint32_t h, uint32_t key) {
+#ifdef COUP_AB_OLD_INSERT
+  uint32_t pos = (hand_slot(h, 0) <= key) + (hand_slot(h, 1) <= key) + (hand_slot(h, 2) <= key) + (hand_slot(h, 3) <= key);
+  uint32_t sh0 = 4 * pos;
+  return ((h & ((1u << sh0) - 1u)) | (key << sh0) | ((h >> sh0) << (sh0 + 4))) & 0xFFFFu;
+#endif
   uint32_t x = (h | (h << 8)) & 0x00FF00FFu;
   x = (x | (x << 4)) & 0x0F0F0F0Fu;                                   // byte i = slot i
   const uint32_t le = ((key * 0x01010101u + 0x10101010u) - x) & 0x10101010u;
@@ -207,13 +212,21 @@ COUP_FN int returns_p0(const Env& s) {
 // they are collected in a register and merged into the row with one read-modify-write of at most two words.
 // `codes` holds `n` codes, 5 bits each, the first in the low bits; they become moves first .. first+n-1 of the row.
 // Words past the last move are left alone ("entries at index >= move_number_ are unspecified").
-COUP_FN void history_commit(uint32_t* row, uint32_t first, uint32_t codes, uint32_t n) {
+COUP_FN void history_commit(uint32_t* row, uint32_t first, uint32_t codes, uint32_t n, uint32_t* mirror = nullptr) {
+  // `row` is read and updated; `mirror` (optional) receives the same words write-only -- the step kernels keep the row
+  // they work on in shared memory and write through to HBM, so that a step never waits for a second global load.
   const uint32_t w = first / 6u;
   const uint32_t sh = 5u * (first - 6u * w);
   const uint64_t bits = static_cast<uint64_t>(codes) << sh;
   const uint32_t keep = sh ? row[w] & ((1u << sh) - 1u) : 0u;          // a word is only ever (valid codes | zeros)
-  row[w] = keep | (static_cast<uint32_t>(bits) & 0x3FFFFFFFu);
-  if (sh + 5u * n > 30u) row[w + 1u] = static_cast<uint32_t>(bits >> 30);
+  const uint32_t v0 = keep | (static_cast<uint32_t>(bits) & 0x3FFFFFFFu);
+  row[w] = v0;
+  if (mirror != nullptr) mirror[w] = v0;
+  if (sh + 5u * n > 30u) {
+    const uint32_t v1 = static_cast<uint32_t>(bits >> 30);
+    row[w + 1u] = v1;
+    if (mirror != nullptr) mirror[w + 1u] = v1;
+  }
 }
 
 // ---- transitions --------------------------------------------------------------------------------
@@ -445,9 +458,21 @@ COUP_FN uint32_t pick(const uint4& r, int k) {
 // k-th (0-based) set bit of a mask with more than k bits set, k <= 7 (a Coup state has at most 7 legal actions, a deck
 // 5 card types): clear the lowest set bit k times, without a loop-carried branch.
 COUP_FN uint32_t kth_set_bit(uint32_t mask, uint32_t k) {
+#ifdef COUP_AB_KTH_BINARY
+  uint32_t pos = 0;
+#pragma unroll
+  for (uint32_t width = 16; width > 0; width >>= 1) {
+    const uint32_t low = popc32((mask >> pos) & ((1u << width) - 1u));
+    const bool up = k >= low;
+    k -= up ? low : 0u;
+    pos += up ? width : 0u;
+  }
+  return pos;
+#else
 #pragma unroll
   for (uint32_t i = 0; i < 7; ++i) mask = i < k ? mask & (mask - 1u) : mask;
   return ffs32(mask) - 1u;
+#endif
 }
 
 // Uniform legal action (benchmark_game.cc:96-99) from one uniform 32-bit word.

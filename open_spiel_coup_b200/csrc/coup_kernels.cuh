@@ -98,7 +98,15 @@ struct StepResult {
 // Re-deal a fresh episode into `s` (CoupState ctor + the 4 initial chance nodes). With forced outcomes (known-answer
 // replay) the deals run through the generic chance loop, else through the closed form; both give the same state for the
 // same Philox words. Writes history word 0 and returns the number of deals made.
-__device__ __forceinline__ uint32_t deal_new_episode(Env& s, uint32_t* hist_row, const uint4& rnd,
+// The history row a step works on: `work` is read and updated (the env's row in HBM itself, or a copy the kernel holds in
+// shared memory), `mirror` is the HBM row when `work` is a copy (written through, never read) and nullptr otherwise.
+struct HistRow {
+  uint32_t* work;
+  uint32_t* mirror;
+};
+__device__ __forceinline__ HistRow global_row(uint32_t* row) { return HistRow{row, nullptr}; }
+
+__device__ __forceinline__ uint32_t deal_new_episode(Env& s, HistRow row, const uint4& rnd,
                                                      const uint8_t* forced) {
   uint32_t codes = 0, n_codes = 0;
   if (forced != nullptr) {
@@ -108,30 +116,41 @@ __device__ __forceinline__ uint32_t deal_new_episode(Env& s, uint32_t* hist_row,
     s = dealt_initial_state(rnd, codes);
     n_codes = 4;
   }
-  hist_row[0] = codes;
+  row.work[0] = codes;
+  if (row.mirror != nullptr) row.mirror[0] = codes;
   return n_codes;
 }
 
-// The episode of env `e` has just ended in terminal state `s` (its history row is flushed): append its trajectory log,
-// terminal state and outcome to the finished-episode ring BEFORE an auto-reset re-deals the env in place. This is what
-// SyncVectorEnv.step hands back as `unreset_time_steps` (python/vector_env.py:52-66) and what every agent is stepped with
-// at episode end (coup_experiments/scripts/nfsp.py:141-143): from the record, the terminal info-state rows of both players
-// are encoded on demand (k_encode_info* with a RecordSource) and the whole episode replays through the reference.
+// The episode of env `e` has just ended in terminal state `s`: its trajectory log, terminal state and outcome go to the
+// finished-episode ring BEFORE an auto-reset re-deals the env in place. This is what SyncVectorEnv.step hands back as
+// `unreset_time_steps` (python/vector_env.py:52-66) and what every agent is stepped with at episode end
+// (coup_experiments/scripts/nfsp.py:141-143): from the record, the terminal info-state rows of both players are encoded on
+// demand (k_encode_info* with a RecordSource) and the whole episode replays through the reference.
 // Slots come from ONE atomic cursor, bumped once per group of lanes that finish together (opportunistic aggregation).
-__device__ __forceinline__ void ring_append(const EnvArrays& A, uint32_t e, const Env& s, const uint32_t* hist_row,
-                                            uint64_t step, bool truncated) {
-  if (A.ring == nullptr) return;
-  const uint32_t peers = __activemask();
+// Two halves, so that the round trip of the atomic hides behind the rest of the step: ring_reserve issues it where the
+// episode ends, ring_write -- called by the same lanes once the deals of the step are done -- consumes the slot.
+struct RingTicket {
+  unsigned long long base;   // the leader's atomic result
+  uint32_t peers;
+};
+__device__ __forceinline__ RingTicket ring_reserve(const EnvArrays& A) {
+  RingTicket t{0ull, 0u};
+  if (A.ring == nullptr) return t;
+  t.peers = __activemask();
   const uint32_t lane = threadIdx.x & 31u;
-  const int leader = __ffs(peers) - 1;
-  unsigned long long base = 0;
-  if (static_cast<int>(lane) == leader) base = atomicAdd(A.ring_ctrl, static_cast<unsigned long long>(__popc(peers)));
-  base = __shfl_sync(peers, base, leader);
-  const uint32_t slot = static_cast<uint32_t>(base + __popc(peers & ((1u << lane) - 1u))) & A.ring_mask;
+  if (static_cast<int>(lane) == __ffs(t.peers) - 1) t.base = atomicAdd(A.ring_ctrl, static_cast<unsigned long long>(__popc(t.peers)));
+  return t;
+}
+__device__ __forceinline__ void ring_write(const EnvArrays& A, const RingTicket& t, uint32_t e, const Env& s,
+                                           const uint32_t* hist_row, uint64_t step, bool truncated) {
+  if (A.ring == nullptr) return;       // hist_row: the working copy of the finished episode's row, any alignment
+  const uint32_t lane = threadIdx.x & 31u;
+  const unsigned long long base = __shfl_sync(t.peers, t.base, __ffs(t.peers) - 1);
+  const uint32_t slot = static_cast<uint32_t>(base + __popc(t.peers & ((1u << lane) - 1u))) & A.ring_mask;
   uint4* dst = reinterpret_cast<uint4*>(A.ring + static_cast<size_t>(slot) * kRecordWords);
-  const uint4* h4 = reinterpret_cast<const uint4*>(hist_row);
 #pragma unroll
-  for (int k = 0; k < kHistoryWords / 4; ++k) dst[k] = h4[k];
+  for (int k = 0; k < kHistoryWords / 4; ++k)
+    dst[k] = make_uint4(hist_row[4 * k], hist_row[4 * k + 1], hist_row[4 * k + 2], hist_row[4 * k + 3]);
   dst[4] = make_uint4(s.p[0], s.p[1], s.g, s.c);
   const uint32_t meta = c_moves(s.c) | (static_cast<uint32_t>(returns_p0(s) + 2) << 8) |
                         (static_cast<uint32_t>(c_reward0(s.c) + 2) << 12) | (truncated ? 1u << 16 : 0u);
@@ -154,7 +173,7 @@ __global__ void k_step_prologue(unsigned long long* ring_ctrl, unsigned int* bat
 // Per-lane branches remain only around memory side effects (the history / ring writes of the ~2 lanes in 32 that end
 // an episode) and the once-in-10^6-episodes move cap that falls in the middle of a deal sequence.
 template <bool kSample, bool kLegalKnown = false>
-__device__ __forceinline__ StepResult step_env(Env& s, uint32_t* hist_row, uint32_t action_in,
+__device__ __forceinline__ StepResult step_env(Env& s, HistRow row, uint32_t action_in,
                                                const uint8_t* forced, const EnvArrays& A, uint32_t e,
                                                uint64_t step, bool active, uint32_t legal_known = 0u) {
   constexpr uint32_t kFull = 0xffffffffu;
@@ -191,18 +210,24 @@ __device__ __forceinline__ StepResult step_env(Env& s, uint32_t* hist_row, uint3
     term = go ? fin : term0;
     // pending history codes of this step: `n_codes` codes that become moves first .. of the row
     uint32_t codes = a, n_codes = go ? 1u : 0u, first = m0;
-    if (__any_sync(kFull, fin)) {
+    RingTicket ticket{0ull, 0u};
+    const bool any_fin = __any_sync(kFull, fin);
+    if (any_fin) {
       if (fin) {                                   // memory side effects of the lanes that end an episode
         r.final_state = s;
         r.final_moves = c_moves(s.c);
         r.truncated = r.final_moves > kMaxGameLength;
-        history_commit(hist_row, m0, a, 1u);
-        ring_append(A, e, s, hist_row, step, r.truncated);
+        history_commit(row.work, m0, a, 1u, row.mirror);
+        ticket = ring_reserve(A);
       }
       // Re-deal in place with the closed-form deal, computed by the whole warp. An episode that ends AT the action has
       // used none of the three deal words of its step block, so the four cards come from them: y serves two draws
       // (floor(y * 15 / 2^32), then its remainder y * 15 mod 2^32, again uniform), z and w one each.
+#ifdef COUP_AB_RESET_BLOCK
+      const uint4 rr = env_random(A.seed, genv, step, 1);
+#else
       const uint4 rr = make_uint4(rnd.y, rnd.y * 15u, rnd.z, rnd.w);
+#endif
       uint32_t fresh_codes;
       const Env fresh = dealt_initial_state(rr, fresh_codes);
       const bool redeal = fin && auto_reset;
@@ -233,7 +258,8 @@ __device__ __forceinline__ StepResult step_env(Env& s, uint32_t* hist_row, uint3
       n_codes += pend ? 1u : 0u;
       r.chance_moves += pend ? 1u : 0u;
     }
-    if (n_codes) history_commit(hist_row, first, codes, n_codes);
+    if (any_fin && fin) ring_write(A, ticket, e, r.final_state, row.work, step, r.truncated);   // before word 0 is re-dealt
+    if (n_codes) history_commit(row.work, first, codes, n_codes, row.mirror);
     if (go && !fin && c_moves(s.c) > kMaxGameLength) {
       // the move cap fell in the middle of a deal sequence: once in ~10^6 episodes, a slow path of its own
       fin = true;
@@ -241,10 +267,10 @@ __device__ __forceinline__ StepResult step_env(Env& s, uint32_t* hist_row, uint3
       r.final_state = s;
       r.final_moves = c_moves(s.c);
       r.truncated = true;
-      ring_append(A, e, s, hist_row, step, true);
+      ring_write(A, ring_reserve(A), e, s, row.work, step, true);
       if (auto_reset) {
         const uint4 rr = env_random(A.seed, genv, step, 1);
-        r.chance_moves += deal_new_episode(s, hist_row, rr, nullptr);
+        r.chance_moves += deal_new_episode(s, row, rr, nullptr);
         term = false;
       }
     }
@@ -374,7 +400,7 @@ k_reset(EnvArrays A, const uint8_t* __restrict__ mask, const uint8_t* __restrict
   if (active) {
     Env s;
     const uint4 rnd = env_random(A.seed, A.global_env_offset + e, step, 1);
-    dealt = deal_new_episode(s, A.history + static_cast<size_t>(e) * kHistoryWords, rnd,
+    dealt = deal_new_episode(s, global_row(A.history + static_cast<size_t>(e) * kHistoryWords), rnd,
                              forced ? forced + static_cast<size_t>(e) * 4 : nullptr);
     store_env(A.state + e, s);
     StepResult r;
@@ -398,7 +424,7 @@ k_step(EnvArrays A, const uint8_t* __restrict__ actions, const uint8_t* __restri
   const bool active = action != 0xFFu;   // 0xFF: this env sits the step out, outputs keep their values
   Env s = {};
   if (active) s = load_env(A.state + e);
-  const StepResult r = step_env<false>(s, A.history + static_cast<size_t>(e) * kHistoryWords, action,
+  const StepResult r = step_env<false>(s, global_row(A.history + static_cast<size_t>(e) * kHistoryWords), action,
                                        forced ? forced + static_cast<size_t>(e) * 4 : nullptr, A, e, step, active);
   if (active) {
     store_env(A.state + e, s);
@@ -532,7 +558,7 @@ k_fork(EnvArrays D, const uint4* __restrict__ src_state, const uint32_t* __restr
     s = load_env(src_state + p);
     parent_terminal = is_terminal(s);
   }
-  StepResult r = step_env<false>(s, hist_row, valid ? actions[e] : 0xFFu, forced ? forced + static_cast<size_t>(e) * 4 : nullptr,
+  StepResult r = step_env<false>(s, global_row(hist_row), valid ? actions[e] : 0xFFu, forced ? forced + static_cast<size_t>(e) * 4 : nullptr,
                                  D, e, step, valid);
   if (active) {
     if (parent_terminal) { s.g |= kBitError; r.illegal = true; }   // a terminal state has no children
@@ -768,7 +794,7 @@ k_step_record(EnvArrays A, RecorderArrays R, const uint8_t* __restrict__ actions
     if ((pend[21] >> 30) & 1u) emit_transition(R, pend, seat == 0u ? rew0 : -rew0, h, s, e, seat, 0u, legal0);
     store_record(pend, h, s, e, (seat << 31) | (1u << 30) | action, 0u, 0u);
   }
-  const StepResult r = step_env<false>(s, hist_row, action, nullptr, A, e, step, active);
+  const StepResult r = step_env<false>(s, global_row(hist_row), action, nullptr, A, e, step, active);
   if (active) {
     store_env(A.state + e, s);
     write_outputs(A, e, r);
@@ -952,11 +978,13 @@ template <> struct Unit4<__nv_bfloat16> {
 //   [20] len | coins0<<8 | coins1<<16 | viewA_observer<<24 | viewB_observer<<25
 __device__ __forceinline__ void fill_record(uint32_t* rec, const Env& s, const uint32_t* hist_row,
                                             int player_sel) {
-  const uint4* h4 = reinterpret_cast<const uint4*>(hist_row);
+  if (hist_row != rec) {                      // the fused step kernels keep the row in the record all along
+    const uint4* h4 = reinterpret_cast<const uint4*>(hist_row);
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    uint4 v = h4[k];
-    rec[4 * k + 0] = v.x; rec[4 * k + 1] = v.y; rec[4 * k + 2] = v.z; rec[4 * k + 3] = v.w;
+    for (int k = 0; k < 4; ++k) {
+      uint4 v = h4[k];
+      rec[4 * k + 0] = v.x; rec[4 * k + 1] = v.y; rec[4 * k + 2] = v.z; rec[4 * k + 3] = v.w;
+    }
   }
   const bool term = is_terminal(s);
   const uint32_t obs_a = player_sel == COUP_PLAYER_1 ? 1u
@@ -969,6 +997,21 @@ __device__ __forceinline__ void fill_record(uint32_t* rec, const Env& s, const u
     rec[18] = static_cast<uint32_t>(mb); rec[19] = static_cast<uint32_t>(mb >> 32);
   }
   rec[20] = c_moves(s.c) | (pw_coins(s.p[0]) << 8) | (pw_coins(s.p[1]) << 16) | (obs_a << 24) | (obs_b << 25);
+}
+
+// The fused step kernels issue ALL the global loads of an env at once -- its state word and its 64-byte history row,
+// the row straight into the env's encoder record in shared memory -- and never load again: the step updates the row in
+// the record and writes the changed words through to HBM. Next to a saturated store stream every dependent global round
+// trip of the rules costs microseconds (scripts/ws_debug_probe.py), so the rules phase is ONE round trip, not four.
+__device__ __forceinline__ Env load_env_and_row(const EnvArrays& A, uint32_t e, uint32_t* rec) {
+  const uint4 sv = A.state[e];
+  const uint4* g4 = reinterpret_cast<const uint4*>(A.history + static_cast<size_t>(e) * kHistoryWords);
+  const uint4 h0 = g4[0], h1 = g4[1], h2 = g4[2], h3 = g4[3];
+  rec[0] = h0.x; rec[1] = h0.y; rec[2] = h0.z; rec[3] = h0.w; rec[4] = h1.x; rec[5] = h1.y; rec[6] = h1.z; rec[7] = h1.w;
+  rec[8] = h2.x; rec[9] = h2.y; rec[10] = h2.z; rec[11] = h2.w; rec[12] = h3.x; rec[13] = h3.y; rec[14] = h3.z; rec[15] = h3.w;
+  Env s;
+  s.p[0] = sv.x; s.p[1] = sv.y; s.g = sv.z; s.c = sv.w;
+  return s;
 }
 
 // Value of info-state element `p` (0..2491) of a record/view. Small non-negative integer.
@@ -1334,12 +1377,13 @@ k_rollout(EnvArrays A, uint64_t step, int player_sel, T* __restrict__ out, uint3
   const bool active = e < A.n;
   Env s = {};
   uint32_t* hist_row = A.history + static_cast<size_t>(e) * kHistoryWords;
-  if (active) s = load_env(A.state + e);
-  const StepResult r = step_env<true>(s, hist_row, 0, nullptr, A, e, step, active);
+  uint32_t* rec = kEncode ? &s_rec[warp][lane * kRecWords] : hist_row;
+  if (active) s = kEncode ? load_env_and_row(A, e, rec) : load_env(A.state + e);
+  const StepResult r = step_env<true>(s, kEncode ? HistRow{rec, hist_row} : global_row(hist_row), 0, nullptr, A, e, step, active);
   if (active) {
     store_env(A.state + e, s);
     write_outputs(A, e, r);
-    if (kEncode) fill_record(&s_rec[warp][lane * kRecWords], s, hist_row, player_sel);
+    if (kEncode) fill_record(rec, s, rec, player_sel);
   }
   account(st, r, active);
   if (kEncode && e0 < A.n) {
@@ -1372,7 +1416,7 @@ k_rollout_env_multi(EnvArrays A, uint64_t step, int n_steps) {
   StatAcc acc;
   acc.clear();
   for (int k = 0; k < n_steps; ++k) {                       // n_steps <= StatAcc::kMaxAdds (the host launches in chunks of 64)
-    r = step_env<true, true>(s, hist_row, 0, nullptr, A, e, step + static_cast<uint64_t>(k), active, r.legal);
+    r = step_env<true, true>(s, global_row(hist_row), 0, nullptr, A, e, step + static_cast<uint64_t>(k), active, r.legal);
     acc.add(r, active);
   }
   acc.flush(st);
@@ -1401,12 +1445,13 @@ k_rollout_tma(EnvArrays A, uint64_t step, int player_sel, T* __restrict__ out, u
   if (block_full) zero_stage(sm.stage, lane);
   Env s = {};
   uint32_t* hist_row = A.history + static_cast<size_t>(e) * kHistoryWords;
-  if (active) s = load_env(A.state + e);
-  const StepResult r = step_env<true>(s, hist_row, 0, nullptr, A, e, step, active);
+  uint32_t* rec = sm.recs + lane * kRecWords;
+  if (active) s = load_env_and_row(A, e, rec);
+  const StepResult r = step_env<true>(s, HistRow{rec, hist_row}, 0, nullptr, A, e, step, active);
   if (active) {
     store_env(A.state + e, s);
     write_outputs(A, e, r);
-    fill_record(sm.recs + lane * kRecWords, s, hist_row, player_sel);
+    fill_record(rec, s, rec, player_sel);
   }
   account(st, r, active);
   if (block_full) {
@@ -1458,9 +1503,6 @@ k_rollout_ws(EnvArrays A, uint64_t step, int player_sel, T* __restrict__ out, ui
   st.init(reinterpret_cast<uint32_t*>(smem_raw + kWsEncWarps * kStageBytes + kWsBufs * kWsRecBytes));
   const bool both = player_sel == COUP_PLAYER_BOTH;
   const bool rules = warp < kWsRulesWarps;
-  StatAcc acc;
-  acc.clear();
-  int acc_adds = 0;
   unsigned char* stage = rules ? nullptr : stage_base + static_cast<size_t>(warp - kWsRulesWarps) * kStageBytes;
   if (!rules) zero_stage(stage, lane);
   // Batches are handed out dynamically (global counter): SMs differ by ~20 % in achieved store bandwidth, so a
@@ -1494,14 +1536,18 @@ k_rollout_ws(EnvArrays A, uint64_t step, int player_sel, T* __restrict__ out, ui
       if (b >= 0) {
         for (int sub = warp; sub < kWsBatch / 32; sub += kWsRulesWarps) {
           const uint32_t e = static_cast<uint32_t>(b) * kWsBatch + sub * 32 + lane;
-          Env s = load_env(A.state + e);
+          uint32_t* rec = recs + (sub * 32 + lane) * kRecWords;
+          Env s = load_env_and_row(A, e, rec);
           uint32_t* hist_row = A.history + static_cast<size_t>(e) * kHistoryWords;
-          const StepResult r = step_env<true>(s, hist_row, 0, nullptr, A, e, step, true);
+          const StepResult r = step_env<true>(s, HistRow{rec, hist_row}, 0, nullptr, A, e, step, true);
           store_env(A.state + e, s);
           write_outputs(A, e, r);
-          fill_record(recs + (sub * 32 + lane) * kRecWords, s, hist_row, player_sel);
-          acc.add(r, true);
-          if (++acc_adds == StatAcc::kMaxAdds) { acc.flush(st); acc_adds = 0; }
+          fill_record(rec, s, rec, player_sel);
+#ifdef COUP_AB_WS_NOSTATS
+          (void)r;
+#else
+          account(st, r, true);
+#endif
         }
       }
       __threadfence_block();
@@ -1532,7 +1578,6 @@ k_rollout_ws(EnvArrays A, uint64_t step, int player_sel, T* __restrict__ out, ui
     }
   }
   if (!rules && lane == 0) tma_wait_all();
-  if (rules) acc.flush(st);
   st.flush(A.stats);
 #ifdef COUP_WS_DEBUG
   if (lane == 0 && (warp == 0 || warp == kWsRulesWarps)) {
@@ -1593,7 +1638,7 @@ k_rollout_incremental(EnvArrays A, uint64_t step, T* __restrict__ buf, uint32_t 
   uint32_t* hist_row = A.history + static_cast<size_t>(e) * kHistoryWords;
   if (active) s = load_env(A.state + e);
   const uint32_t old_len = c_moves(s.c);
-  const StepResult r = step_env<true>(s, hist_row, 0, nullptr, A, e, step, active);
+  const StepResult r = step_env<true>(s, global_row(hist_row), 0, nullptr, A, e, step, active);
   if (active) {
     store_env(A.state + e, s);
     write_outputs(A, e, r);
