@@ -1160,22 +1160,42 @@ __device__ __forceinline__ void tma_bulk_store(void* gptr, const void* smem, uin
 __device__ __forceinline__ void tma_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
-// Writes (set=true) or erases (set=false) the non-zeros of one row into its place in the staging buffer.
-template <typename T>
-__device__ __forceinline__ void poke_row(T* row, const uint32_t* rec, int view, bool set, int lane) {
+// What one lane pokes into one row, decided ahead of time (one word): bits 0-1 elements `lane` and `32 + lane` of the
+// head are 1; bits 2-9 the coin count this lane writes (lanes 28, 29 -> elements 60, 61, raw counts 207-213); bits 10-24
+// the columns of history rows lane, lane + 32, lane + 64 (5 bits each, 31 = nothing to write: a deal to the other
+// player, or past the end); bits 25-31 the number of moves. Planning reads the records and does all the arithmetic;
+// poking is then nothing but shared-memory stores, and the PLAN of the next group is computed while the TMA engine
+// reads the buffer of the current one.
+__device__ __forceinline__ uint32_t plan_row(const uint32_t* rec, int view, int lane) {
   const uint32_t meta = rec[20];
   const uint32_t observer = (meta >> (24 + view)) & 1u;
   const uint32_t lo = rec[16 + 2 * view], hi = rec[17 + 2 * view];
-  const T one = Elem<T>::from(set ? 1u : 0u);
-  if ((lo >> lane) & 1u) row[lane] = one;                                  // elements 0..31
-  if ((hi >> lane) & 1u) row[32 + lane] = one;                             // elements 32..59 (hi has 28 bits)
-  if (lane >= 28 && lane < 30)                                             // elements 60, 61: raw coin counts
-    row[32 + lane] = Elem<T>::from(set ? (meta >> (8u + 8u * (lane - 28))) & 255u : 0u);
-  const uint32_t len = meta & 255u;
-  for (uint32_t i = lane; i < len; i += 32) {                              // history rows
-    const uint32_t w = i / 6u;
-    const uint32_t col = history_column((rec[w] >> (5u * (i - 6u * w))) & 31u, observer);
-    if (col != 31u) row[62u + 18u * i + col] = one;
+  const uint32_t len = meta & 127u;
+  uint32_t plan = ((lo >> lane) & 1u) | (((hi >> lane) & 1u) << 1) | (len << 25);
+  if (lane >= 28 && lane < 30) plan |= ((meta >> (8u + 8u * (lane - 28))) & 255u) << 2;
+#pragma unroll
+  for (uint32_t j = 0; j < 3; ++j) {
+    const uint32_t i = lane + 32u * j;
+    uint32_t col = 31u;
+    if (i < len) {
+      const uint32_t w = i / 6u;
+      col = history_column((rec[w] >> (5u * (i - 6u * w))) & 31u, observer);   // WriteActionHistory, 230-245
+    }
+    plan |= col << (10u + 5u * j);
+  }
+  return plan;
+}
+
+template <typename T>
+__device__ __forceinline__ void poke_plan(T* row, uint32_t plan, int lane) {
+  const T one = Elem<T>::from(1u);
+  if (plan & 1u) row[lane] = one;                                          // elements 0..31
+  if (plan & 2u) row[32 + lane] = one;                                     // elements 32..59 (the mask has 60 bits)
+  if (lane >= 28 && lane < 30) row[32 + lane] = Elem<T>::from((plan >> 2) & 255u);
+#pragma unroll
+  for (uint32_t j = 0; j < 3; ++j) {
+    const uint32_t col = (plan >> (10u + 5u * j)) & 31u;
+    if (col != 31u) row[62u + 18u * (lane + 32u * j) + col] = one;
   }
 }
 
@@ -1184,10 +1204,10 @@ __device__ __forceinline__ void poke_row(T* row, const uint32_t* rec, int view, 
 // instructions per row for any element type). The widening can only touch the zero tail of the previous row of the
 // same staging buffer or later elements of this row, all of which are zero once the group has been erased.
 template <typename T>
-__device__ __forceinline__ void clear_row(T* row, const uint32_t* rec, int lane) {
+__device__ __forceinline__ void clear_row(T* row, uint32_t len, int lane) {
   const uint32_t saddr = static_cast<uint32_t>(__cvta_generic_to_shared(row));
   const uint32_t lo = saddr & ~15u;
-  const uint32_t hi = (saddr + (62u + 18u * (rec[20] & 255u)) * static_cast<uint32_t>(sizeof(T)) + 15u) & ~15u;
+  const uint32_t hi = (saddr + (62u + 18u * len) * static_cast<uint32_t>(sizeof(T)) + 15u) & ~15u;
   uint4* p = reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(row) - (saddr - lo));
   const int units = static_cast<int>((hi - lo) >> 4);
   for (int q = lane; q < units; q += 32) p[q] = make_uint4(0u, 0u, 0u, 0u);
@@ -1198,6 +1218,8 @@ __device__ __forceinline__ void clear_row(T* row, const uint32_t* rec, int lane)
 // ...), so at any moment the eight warps of a block are writing eight ADJACENT groups: that keeps the DRAM write
 // stream sequential over ~80 KB windows and is worth ~5 % of HBM write bandwidth over each warp streaming its own
 // 32 rows (scripts/store_bw_probe.cu: 7.26 vs 6.93 TB/s for pure bulk stores of this shape).
+// Per group: poke the planned non-zeros, hand the buffer to the TMA engine (cp.async.bulk shared -> global, SASS UBLKCP),
+// plan the NEXT group while the engine reads, wait for the read, erase.
 template <typename T>
 __device__ __forceinline__ void block_encode_info_tma(const uint32_t* block_recs, bool both, T* stage,
                                                       unsigned char* out_block_bytes, int warp, int lane, int stride,
@@ -1205,23 +1227,28 @@ __device__ __forceinline__ void block_encode_info_tma(const uint32_t* block_recs
   constexpr int G = 4 / static_cast<int>(sizeof(T));
   const uint32_t group_bytes = static_cast<uint32_t>(G * stride) * sizeof(T);  // 9968 (stride 2492) or 9984 (2496)
   const int ngroups = (both ? 2 : 1) * kTmaWarpsPerBlock * 32 / G;
+  uint32_t plan[G], next[G];
+  auto plan_group = [&](int g, uint32_t (&out)[G]) {
+#pragma unroll
+    for (int k = 0; k < G; ++k) {
+      const int r = g * G + k;
+      out[k] = plan_row(block_recs + (both ? (r >> 1) : r) * kRecWords, both ? (r & 1) : 0, lane);
+    }
+  };
+  if (warp < ngroups) plan_group(warp, plan);
   for (int g = warp; g < ngroups; g += nwarps) {
 #pragma unroll
-    for (int k = 0; k < G; ++k) {
-      const int r = g * G + k;
-      poke_row<T>(stage + k * stride, block_recs + (both ? (r >> 1) : r) * kRecWords, both ? (r & 1) : 0, true, lane);
-    }
+    for (int k = 0; k < G; ++k) poke_plan<T>(stage + k * stride, plan[k], lane);
     tma_store_fence();   // generic-proxy writes -> visible to the async proxy
     __syncwarp();
-    if (lane == 0) {
-      tma_bulk_store(out_block_bytes + static_cast<size_t>(g) * group_bytes, stage, group_bytes);
-      tma_wait_read_all();  // the engine has read the buffer (the global write itself is still in flight)
-    }
+    if (lane == 0) tma_bulk_store(out_block_bytes + static_cast<size_t>(g) * group_bytes, stage, group_bytes);
+    if (g + nwarps < ngroups) plan_group(g + nwarps, next);   // overlaps the engine's read of the buffer
+    if (lane == 0) tma_wait_read_all();  // the engine has read the buffer (the global write itself is still in flight)
     __syncwarp();
 #pragma unroll
     for (int k = 0; k < G; ++k) {
-      const int r = g * G + k;
-      clear_row<T>(stage + k * stride, block_recs + (both ? (r >> 1) : r) * kRecWords, lane);
+      clear_row<T>(stage + k * stride, plan[k] >> 25, lane);
+      plan[k] = next[k];
     }
   }
   // Before the CTA exits the engine must be done with this warp's shared memory (a persistent caller defers this).
@@ -1519,6 +1546,7 @@ k_rollout_ws(EnvArrays A, uint64_t step, int player_sel, T* __restrict__ out, ui
 #define WS_DBG_MARK()
 #define WS_DBG_ADD(var)
 #endif
+  unsigned int next_batch = 0;
   for (int it = 0;; ++it) {
     const int buf = it % kWsBufs;
     uint32_t* recs = rec0 + buf * (kWsRecBytes / 4);
@@ -1528,8 +1556,11 @@ k_rollout_ws(EnvArrays A, uint64_t step, int player_sel, T* __restrict__ out, ui
       WS_DBG_ADD(dbg_wait);
       WS_DBG_MARK();
       if (warp == 0 && lane == 0) {
-        const unsigned int b = atomicAdd(batch_counter, 1u);
+        // The batch number was requested one iteration ago (the first one here): next to the saturated store stream
+        // a global atomic takes microseconds to come back, and nothing of this batch can start before it does.
+        const unsigned int b = it == 0 ? atomicAdd(batch_counter, 1u) : next_batch;
         s_batch[buf] = b < n_batches ? static_cast<int>(b) : -1;
+        next_batch = atomicAdd(batch_counter, 1u);
       }
       named_bar_sync(kBarRules, kWsRulesWarps * 32);
       const int b = s_batch[buf];
@@ -1596,39 +1627,58 @@ k_rollout_ws(EnvArrays A, uint64_t step, int player_sel, T* __restrict__ out, ui
 // the history rows of the moves made in this step (1 player move + <= 3 deals, or the 4 deals of a re-dealt
 // episode) and, when an episode was re-dealt in place, zeros over the rows the finished episode had used.
 // ~0.9 KB of stores per env-step instead of 2 x 9 968 B; the buffer always equals what the dense encoder would write.
-// Mapping. The owner thread of an env steps it and leaves an 7-word update record in shared memory (both head masks,
-// coins, the codes of the <= 4 new history rows, the range to zero after an in-place re-deal). Then the warp walks
-// its touched envs; for each, the two half-warps take the two views and write, with one store instruction each:
-// the head as 16 four-element units (the last one also carries the first two elements of history row 0), and the
-// new rows as two-element units (9 per row). Two earlier mappings, measured on one B200 at 2^20 envs, fp32:
-// whole warp per (env, view) with one store per row and the dense encoder's 21-word records: 0.556 ms (246
-// warp-instructions per env-step, the serial walk was the bound: 43 % issue, DRAM at 29 %); every thread storing its
-// own env's units: 0.950 ms (32 different 32-byte sectors per store instruction).
-template <typename T> struct Unit2;  // two consecutive tensor elements
-template <> struct Unit2<float> {
-  using type = float2;
-  static __device__ __forceinline__ type make(uint32_t a, uint32_t b) { return make_float2(static_cast<float>(a), static_cast<float>(b)); }
-};
-template <> struct Unit2<uint8_t> {
-  using type = uint16_t;
-  static __device__ __forceinline__ type make(uint32_t a, uint32_t b) { return static_cast<uint16_t>(a | (b << 8)); }
-};
-template <> struct Unit2<__nv_bfloat16> {
-  using type = uint32_t;
-  static __device__ __forceinline__ type make(uint32_t a, uint32_t b) {
-    return Unit4<__nv_bfloat16>::bits(a) | (Unit4<__nv_bfloat16>::bits(b) << 16);
+//
+// Mapping. The owner thread of an env steps it (history row held in shared memory, as in the other fused kernels) and
+// leaves an 8-word update record. Then the warp walks its touched envs; for each, the two half-warps take the two views.
+// Every store is a 16-byte unit and every span of units starts and ends on a 32-BYTE SECTOR boundary of the buffer:
+// a span that changed ([0, 62) and [62 + 18 first, 62 + 18 len), or one span from 0 to the end of the finished episode
+// after a re-deal) is widened to whole sectors, and the elements the widening touches are recomputed, not read -- the
+// tail of the previous row (always zero: history rows >= 91 are never used), the row before the first new one, row 0,
+// zeros past the last move. Partial-sector writes make the L2 fetch the sector from DRAM before it can merge
+// (ncu: 0.25 GB of DRAM reads per step for a kernel that reads 0.08 GB, and the store path backs up behind those fills);
+// rows of the reference layout are 9 968 B apart, so every second row starts in the middle of a sector. Measured on one
+// B200, 2^20 envs, f32: 0.52 ms per step with 8/16-byte stores at their natural offsets, 0.40 ms with 32-byte aligned
+// rows (stride 2496) -- see profiles/README.md for the sector-exact numbers.
+// Two earlier mappings: whole warp per (env, view) with one store per row and the dense encoder's 21-word records:
+// 0.556 ms (246 warp-instructions per env-step, the serial walk was the bound); every thread storing its own env's
+// units: 0.950 ms (32 different 32-byte sectors per store instruction).
+constexpr int kIncRecWords = 8;
+constexpr int kIncRowPitch = kHistoryWords + 1;   // conflict-free per-lane rows in shared memory
+
+// Sixteen bytes of consecutive tensor elements from their small-integer values.
+template <typename T> struct Pack16;
+template <> struct Pack16<float> {
+  static constexpr int kElems = 4;
+  template <typename F> static __device__ __forceinline__ uint4 make(F value) {
+    return make_uint4(__float_as_uint(static_cast<float>(value(0))), __float_as_uint(static_cast<float>(value(1))),
+                      __float_as_uint(static_cast<float>(value(2))), __float_as_uint(static_cast<float>(value(3))));
   }
 };
-
-constexpr int kIncRecWords = 8;
+template <> struct Pack16<__nv_bfloat16> {
+  static constexpr int kElems = 8;
+  template <typename F> static __device__ __forceinline__ uint4 make(F value) {
+    uint32_t w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) w[k] = Unit4<__nv_bfloat16>::bits(value(2 * k)) | (Unit4<__nv_bfloat16>::bits(value(2 * k + 1)) << 16);
+    return make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+template <> struct Pack16<uint8_t> {
+  static constexpr int kElems = 16;
+  template <typename F> static __device__ __forceinline__ uint4 make(F value) {
+    uint32_t w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) w[k] = value(4 * k) | (value(4 * k + 1) << 8) | (value(4 * k + 2) << 16) | (value(4 * k + 3) << 24);
+    return make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
 
 template <typename T>
 __global__ void __launch_bounds__(kBlockThreads)
 k_rollout_incremental(EnvArrays A, uint64_t step, T* __restrict__ buf, uint32_t stride) {
-  using U4 = typename Unit4<T>::type;
-  using U2 = typename Unit2<T>::type;
   __shared__ uint32_t s_stats[COUP_STATS_LEN];
   __shared__ uint32_t s_rec[kWarpsPerBlock][32][kIncRecWords];
+  __shared__ uint32_t s_row[kWarpsPerBlock][32][kIncRowPitch];
   BlockStats st;
   st.init(s_stats);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1636,9 +1686,10 @@ k_rollout_incremental(EnvArrays A, uint64_t step, T* __restrict__ buf, uint32_t 
   const bool active = e < A.n;
   Env s = {};
   uint32_t* hist_row = A.history + static_cast<size_t>(e) * kHistoryWords;
-  if (active) s = load_env(A.state + e);
+  uint32_t* row_copy = s_row[warp][lane];
+  if (active) s = load_env_and_row(A, e, row_copy);
   const uint32_t old_len = c_moves(s.c);
-  const StepResult r = step_env<true>(s, global_row(hist_row), 0, nullptr, A, e, step, active);
+  const StepResult r = step_env<true>(s, HistRow{row_copy, hist_row}, 0, nullptr, A, e, step, active);
   if (active) {
     store_env(A.state + e, s);
     write_outputs(A, e, r);
@@ -1647,53 +1698,64 @@ k_rollout_incremental(EnvArrays A, uint64_t step, T* __restrict__ buf, uint32_t 
       const bool redealt = r.finished && new_len < r.final_moves + 1 && (A.flags & COUP_FLAG_AUTO_RESET);
       const uint32_t first = redealt ? 0u : old_len;   // rows [first, new_len) are (re)written, at most 4
       const bool term = is_terminal(s);
-      uint32_t codes = (new_len ? (hist_row[0] & 31u) : 31u) << 20;
-      for (uint32_t i = first, k = 0; i < new_len; ++i, ++k) {
-        const uint32_t w = i / 6u;
-        codes |= ((hist_row[w] >> (5u * (i - 6u * w))) & 31u) << (5u * k);
-      }
+      auto code_at = [&](uint32_t i) { const uint32_t w = i / 6u; return (row_copy[w] >> (5u * (i - 6u * w))) & 31u; };
+      // 5-bit codes: [0,20) the new rows, [20,25) row 0, [25,30) the row before the first new one
+      uint32_t codes = ((new_len ? code_at(0u) : 31u) << 20) | ((first ? code_at(first - 1u) : 31u) << 25);
+      for (uint32_t i = first, k = 0; i < new_len; ++i, ++k) codes |= code_at(i) << (5u * k);
       uint32_t* rec = s_rec[warp][lane];
       const uint64_t m0 = head_mask(s, 0u, term), m1 = head_mask(s, 1u, term);
       rec[0] = static_cast<uint32_t>(m0); rec[1] = static_cast<uint32_t>(m0 >> 32);
       rec[2] = static_cast<uint32_t>(m1); rec[3] = static_cast<uint32_t>(m1 >> 32);
       rec[4] = pw_coins(s.p[0]) | (pw_coins(s.p[1]) << 8) | (first << 16) | ((new_len - first) << 24);
       rec[5] = codes;
-      // elements both views must zero: the rows the finished episode had used beyond the new episode's deals
-      rec[6] = (redealt && r.final_moves > new_len) ? (62u + 18u * new_len) | ((62u + 18u * r.final_moves) << 16) : 0u;
+      // after a re-deal everything from element 0 to the end of the finished episode's rows is one span
+      rec[6] = redealt ? max(r.final_moves, new_len) : 0u;
     }
   }
   account(st, r, active);
   uint32_t touched = __ballot_sync(0xffffffffu, active && r.stepped);
   __syncwarp();
+  constexpr uint32_t kEl = Pack16<T>::kElems;            // elements per 16-byte unit
+  constexpr uint32_t kSector = 2u * kEl;                  // elements per 32-byte sector
   const uint32_t view = static_cast<uint32_t>(lane) >> 4, l = static_cast<uint32_t>(lane) & 15u;
   const uint32_t e0 = e - lane;
   while (touched) {
     const int j = __ffs(touched) - 1;
     touched &= touched - 1;
     const uint32_t* rec = s_rec[warp][j];
-    const uint32_t mlo = rec[2 * view], mhi = rec[2 * view + 1], meta = rec[4], codes = rec[5], clr = rec[6];
-    T* row = buf + (static_cast<size_t>(e0 + j) * 2 + view) * stride;
-    // head: unit l holds elements 4l .. 4l+3; unit 15 = coins (60, 61) and the first two elements of history row 0
-    uint32_t a, b, c, d;
-    if (l < 15u) {
-      const uint32_t bits = (l < 8u ? mlo >> (4u * l) : mhi >> (4u * l - 32u)) & 15u;
-      a = bits & 1u; b = (bits >> 1) & 1u; c = (bits >> 2) & 1u; d = bits >> 3;
-    } else {
-      const uint32_t col0 = history_column((codes >> 20) & 31u, view);
-      a = meta & 255u; b = (meta >> 8) & 255u; c = col0 == 0u ? 1u : 0u; d = col0 == 1u ? 1u : 0u;
-    }
-    reinterpret_cast<U4*>(row)[l] = Unit4<T>::make(a, b, c, d);
-    // new rows: 9 two-element units each, contiguous from element 62 + 18 * first (an even offset)
-    const uint32_t first = (meta >> 16) & 255u, npairs = 9u * (meta >> 24);
-    U2* row2 = reinterpret_cast<U2*>(row);
-    for (uint32_t p = l; p < npairs; p += 16u) {
-      const uint32_t k = p / 9u, u = p - 9u * k;
-      const uint32_t col = history_column((codes >> (5u * k)) & 31u, view);
-      row2[31u + 9u * first + p] = Unit2<T>::make(col == 2u * u ? 1u : 0u, col == 2u * u + 1u ? 1u : 0u);
-    }
-    if (clr) {
-      const U2 zero = Unit2<T>::make(0u, 0u);
-      for (uint32_t q = ((clr & 0xffffu) >> 1) + l; q < (clr >> 17); q += 16u) row2[q] = zero;
+    const uint32_t mlo = rec[2 * view], mhi = rec[2 * view + 1], meta = rec[4], codes = rec[5], span_end = rec[6];
+    const uint32_t first = (meta >> 16) & 255u, n_new = meta >> 24;
+    const size_t row_base = (static_cast<size_t>(e0 + j) * 2 + view) * stride;       // absolute element index of element 0
+    // value of element p of this row; p < 0 is the (zero) tail of the previous row
+    auto value = [&](int p) -> uint32_t {
+      if (p < 0) return 0u;
+      if (p < 32) return (mlo >> p) & 1u;
+      if (p < 60) return (mhi >> (p - 32)) & 1u;
+      if (p < 62) return (meta >> (8 * (p - 60))) & 255u;
+      const uint32_t q = static_cast<uint32_t>(p) - 62u;
+      const uint32_t i = q / 18u, a = q - 18u * i;
+      uint32_t code = 31u;                                                              // rows nobody set: zeros
+      if (i - first < n_new) code = (codes >> (5u * (i - first))) & 31u;
+      else if (i + 1u == first) code = (codes >> 25) & 31u;
+      else if (i == 0u) code = (codes >> 20) & 31u;
+      return history_column(code, view) == a ? 1u : 0u;
+    };
+    // spans in row elements: [0, 62) and the new rows -- or one span after a re-deal
+    uint32_t lo[2], hi[2];
+    lo[0] = 0u; hi[0] = span_end ? 62u + 18u * span_end : 62u;
+    lo[1] = 62u + 18u * first; hi[1] = span_end ? lo[1] : lo[1] + 18u * n_new;
+#pragma unroll
+    for (int sp = 0; sp < 2; ++sp) {
+      if (hi[sp] <= lo[sp]) continue;
+      const size_t abs_lo = (row_base + lo[sp]) / kSector * kSector;                    // widened to whole sectors
+      const size_t abs_hi = (row_base + hi[sp] + kSector - 1u) / kSector * kSector;
+      const uint32_t units = static_cast<uint32_t>((abs_hi - abs_lo) / kEl);
+      uint4* dst = reinterpret_cast<uint4*>(buf + abs_lo);
+      const int p0 = static_cast<int>(static_cast<long long>(abs_lo) - static_cast<long long>(row_base));
+      for (uint32_t u = l; u < units; u += 16u) {
+        const int p = p0 + static_cast<int>(u * kEl);
+        dst[u] = Pack16<T>::make([&](int k) { return value(p + k); });
+      }
     }
   }
   st.flush(A.stats);
