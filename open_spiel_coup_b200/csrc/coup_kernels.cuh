@@ -148,9 +148,14 @@ __device__ __forceinline__ void ring_write(const EnvArrays& A, const RingTicket&
   const unsigned long long base = __shfl_sync(t.peers, t.base, __ffs(t.peers) - 1);
   const uint32_t slot = static_cast<uint32_t>(base + __popc(t.peers & ((1u << lane) - 1u))) & A.ring_mask;
   uint4* dst = reinterpret_cast<uint4*>(A.ring + static_cast<size_t>(slot) * kRecordWords);
+  if ((reinterpret_cast<uintptr_t>(hist_row) & 15u) == 0) {      // the env's own row in HBM
 #pragma unroll
-  for (int k = 0; k < kHistoryWords / 4; ++k)
-    dst[k] = make_uint4(hist_row[4 * k], hist_row[4 * k + 1], hist_row[4 * k + 2], hist_row[4 * k + 3]);
+    for (int k = 0; k < kHistoryWords / 4; ++k) dst[k] = reinterpret_cast<const uint4*>(hist_row)[k];
+  } else {                                                        // a copy in a shared-memory record (odd pitch)
+#pragma unroll
+    for (int k = 0; k < kHistoryWords / 4; ++k)
+      dst[k] = make_uint4(hist_row[4 * k], hist_row[4 * k + 1], hist_row[4 * k + 2], hist_row[4 * k + 3]);
+  }
   dst[4] = make_uint4(s.p[0], s.p[1], s.g, s.c);
   const uint32_t meta = c_moves(s.c) | (static_cast<uint32_t>(returns_p0(s) + 2) << 8) |
                         (static_cast<uint32_t>(c_reward0(s.c) + 2) << 12) | (truncated ? 1u << 16 : 0u);
