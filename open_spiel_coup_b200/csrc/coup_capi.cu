@@ -2,6 +2,7 @@
 // the device slab of one GPU and launches the sm_100a kernels in coup_kernels.cuh. No game rule is
 // evaluated on the host anywhere in this file.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: ranges show up in Nsight Systems / Compute, cost nothing otherwise
 
 #include <cstdio>
 #include <cstring>
@@ -49,17 +50,20 @@ int fail(int code, const std::string& msg) {
       return fail(COUP_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(err__)); \
   } while (0)
 
-// Makes the handle's device current for the duration of a call and restores the caller's.
+// Makes the handle's device current for the duration of a call and restores the caller's; every entry point that
+// launches work holds one, so it also opens the call's NVTX range (named after the entry point).
 struct DeviceGuard {
   int prev = -1;
   bool ok = true;
-  explicit DeviceGuard(int dev) {
+  explicit DeviceGuard(int dev, const char* range = __builtin_FUNCTION()) {
+    nvtxRangePushA(range);
     if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
     if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
   }
   ~DeviceGuard() {
     int cur = -1;
     if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+    nvtxRangePop();
   }
 };
 

@@ -19,6 +19,7 @@ of one at every node (`deep_cfr.py:415-497,499-525`). Here `num_traversals` root
 Only the per-level bookkeeping (a few dozen small torch ops) runs from Python; states never leave HBM.
 """
 import collections
+import dataclasses
 import math
 import os
 
@@ -180,6 +181,43 @@ _STRAT_FIELDS = {"info_state": ((INFO_STATE_SIZE,), torch.uint8), "iteration": (
                  "strategy_action_probs": ((NUM_DISTINCT_ACTIONS,), torch.float32)}
 
 
+@dataclasses.dataclass
+class DeepCFRConfig:
+    """The keyword arguments of the reference's `DeepCFRSolver.__init__` (deep_cfr.py:118-188), same names and defaults
+    (the thesis runs set them from `coup_experiments/scripts/flags/thesis_runs/deep_cfr-*.cfg`)."""
+    policy_network_layers: tuple = (256, 256)
+    advantage_network_layers: tuple = (128, 128)
+    num_iterations: int = 100
+    num_traversals: int = 20
+    learning_rate: float = 1e-4
+    batch_size_advantage: int = None
+    batch_size_strategy: int = None
+    memory_capacity: int = int(1e6)
+    policy_network_train_steps: int = 1
+    advantage_network_train_steps: int = 1
+    reinitialize_advantage_networks: bool = True
+    sampling_method: str = "external"
+    outcome_samp_expl: float = 0.6
+    outcome_factor: int = 1
+    e_outcome: float = 0
+    iter_net_train: bool = False
+    adv_net_reinit_every: int = 1
+    eval_func: object = None
+    eval_every: int = 10
+    eval_train_episodes: int = 10000
+    eval_test_every: int = 5000
+    eval_test_episodes: int = 1000
+    use_checkpoints: bool = False
+    checkpoint_dir: str = None
+    save_every: int = None
+
+    def __post_init__(self):
+        if self.sampling_method not in ("external", "outcome", "e-outcome"):
+            raise ValueError(f"Unknown sampling method '{self.sampling_method}'.")           # deep_cfr.py:229-230
+        if self.outcome_factor <= 0:
+            raise ValueError("Outcome factor must be greater than 0.")                      # deep_cfr.py:233-234
+
+
 class DeepCFRSolver:
     """`deep_cfr.DeepCFRSolver` (deep_cfr.py:102-640) for game "coup". Arguments as in the reference (:118-188);
     additions: `device`, `seed`, `max_nodes` (size of each of the two scratch env slabs; a level with more nodes is
@@ -189,51 +227,20 @@ class DeepCFRSolver:
     trees grow past this many nodes raises instead of exhausting memory) and `record_tree` (keep the
     per-level bookkeeping of the last batch in `last_tree` for inspection and tests)."""
 
-    def __init__(self, game=None, policy_network_layers=(256, 256), advantage_network_layers=(128, 128),
-                 num_iterations=100, num_traversals=20, learning_rate=1e-4, batch_size_advantage=None,
-                 batch_size_strategy=None, memory_capacity=int(1e6), policy_network_train_steps=1,
-                 advantage_network_train_steps=1, reinitialize_advantage_networks=True, sampling_method="external",
-                 outcome_samp_expl=0.6, outcome_factor=1, e_outcome=0, iter_net_train=False, adv_net_reinit_every=1,
-                 eval_func=None, eval_every=10, eval_train_episodes=10000, eval_test_every=5000,
-                 eval_test_episodes=1000, use_checkpoints=False, checkpoint_dir=None, save_every=None,
-                 device=0, seed=0, max_nodes=1 << 18, roots_per_batch=None, max_tree_nodes=1 << 26, record_tree=False,
-                 fused_expand=True):
-        if sampling_method not in ("external", "outcome", "e-outcome"):
-            raise ValueError(f"Unknown sampling method '{sampling_method}'.")           # deep_cfr.py:229-230
-        if outcome_factor <= 0:
-            raise ValueError("Outcome factor must be greater than 0.")                 # deep_cfr.py:233-234
+    def __init__(self, game=None, device=0, seed=0, max_nodes=1 << 18, roots_per_batch=None, max_tree_nodes=1 << 26,
+                 record_tree=False, fused_expand=True, **reference_args):
+        self.cfg = cfg = DeepCFRConfig(**reference_args)          # the reference's keyword arguments, validated
         self._game = game
         self.device = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
-        self._num_players = 2
-        self._num_actions = NUM_DISTINCT_ACTIONS
-        self._embedding_size = INFO_STATE_SIZE
-        self._batch_size_advantage = batch_size_advantage
-        self._batch_size_strategy = batch_size_strategy
-        self._policy_network_train_steps = policy_network_train_steps
-        self._advantage_network_train_steps = advantage_network_train_steps
-        self._num_iterations = num_iterations
-        self._num_traversals = num_traversals
-        self._reinitialize_advantage_networks = reinitialize_advantage_networks
+        self._num_players, self._num_actions, self._embedding_size = 2, NUM_DISTINCT_ACTIONS, INFO_STATE_SIZE
         self._iteration = 1
         self._environment_steps = 0
-        self._sampling_method = sampling_method
-        self._expl = outcome_samp_expl
-        self._outcome_factor = outcome_factor
-        self._e_outcome = e_outcome
-        self._iter_net_train = iter_net_train
-        self._adv_net_reinit_every = adv_net_reinit_every
-        self._eval_func = eval_func
-        self._eval_every = eval_every
-        self._eval_train_episodes = eval_train_episodes
-        self._eval_test_every = eval_test_every
-        self._eval_test_episodes = eval_test_episodes
-        self._use_checkpoints = use_checkpoints
-        self._checkpoint_dir = checkpoint_dir
-        self._save_every = save_every
         self._record_tree = record_tree
         self._fused_expand = fused_expand       # regret matching + child selection in one CUDA kernel (coup_cfr_expand)
         self._expand_seed, self._expand_counter = seed * 2654435761 % (1 << 63) + 17, 0
         self.last_tree = None
+        policy_network_layers, advantage_network_layers = cfg.policy_network_layers, cfg.advantage_network_layers
+        learning_rate, memory_capacity, num_traversals = cfg.learning_rate, cfg.memory_capacity, cfg.num_traversals
 
         torch.manual_seed(seed)
         self._gen = torch.Generator(device=self.device)
@@ -308,36 +315,54 @@ class DeepCFRSolver:
         path = os.path.join(checkpoint_dir, "policy_network" + checkpoint_id + ".pt")
         self._policy_network.load_state_dict(torch.load(path, map_location=self.device))
 
-    # ---- solve (deep_cfr.py:360-410) -----------------------------------------------------------------
+    # ---- solve: the schedule of deep_cfr.py:360-410 ----------------------------------------------------
+    def _advantage_phase(self, losses):
+        """Traversals for both players, each followed by a (possibly re-initialised) fit of that player's network."""
+        cfg = self.cfg
+        for player in range(self._num_players):
+            self.traverse(player, cfg.num_traversals)
+            if cfg.reinitialize_advantage_networks and self._iteration % cfg.adv_net_reinit_every == 0:
+                self.reinitialize_advantage_network(player)
+            losses[player].append(self._learn_advantage_network(player))
+
+    def _evaluate(self):
+        cfg = self.cfg
+        cfg.eval_func(exploitee=self, num_train_episodes=cfg.eval_train_episodes, eval_every=cfg.eval_test_every,
+                      eval_episodes=cfg.eval_test_episodes)
+
+    def _checkpoint(self, iteration):
+        self.save_policy_network(self.cfg.checkpoint_dir, f"iter{iteration}")
+
     def solve(self):
-        advantage_losses = collections.defaultdict(list)
+        """Returns (policy network, advantage losses per player, last policy loss). Per iteration: the advantage phase;
+        a policy fit when `iter_net_train`; on evaluation iterations (every `eval_every`, never the last) the policy is
+        fitted if it was not, evaluated, checkpointed every `save_every`, and -- if it is only trained on demand --
+        discarded again. After the last iteration: final fit, evaluation, checkpoint."""
+        cfg = self.cfg
+        losses = collections.defaultdict(list)
         policy_loss = None
-        for _ in range(self._num_iterations):
-            for p in range(self._num_players):
-                self.traverse(p, self._num_traversals)
-                if self._reinitialize_advantage_networks and self._iteration % self._adv_net_reinit_every == 0:
-                    self.reinitialize_advantage_network(p)
-                advantage_losses[p].append(self._learn_advantage_network(p))
-            if self._iter_net_train:
+        for _ in range(cfg.num_iterations):
+            it = self._iteration
+            self._advantage_phase(losses)
+            trained_now = cfg.iter_net_train
+            if trained_now:
                 policy_loss = self._learn_strategy_network()
-            if (self._eval_func is not None and self._iteration % self._eval_every == 0
-                    and self._iteration != self._num_iterations):
-                if not self._iter_net_train:
+            evaluating = cfg.eval_func is not None and it % cfg.eval_every == 0 and it != cfg.num_iterations
+            if evaluating:
+                if not trained_now:
                     policy_loss = self._learn_strategy_network()
-                self._eval_func(exploitee=self, num_train_episodes=self._eval_train_episodes,
-                                eval_every=self._eval_test_every, eval_episodes=self._eval_test_episodes)
-                if self._use_checkpoints and self._save_every and self._iteration % self._save_every == 0:
-                    self.save_policy_network(self._checkpoint_dir, f"iter{self._iteration}")
-                if not self._iter_net_train:
+                self._evaluate()
+                if cfg.use_checkpoints and cfg.save_every and it % cfg.save_every == 0:
+                    self._checkpoint(it)
+                if not trained_now:
                     self._reinitialize_policy_network()
-            self._iteration += 1
+            self._iteration = it + 1
         policy_loss = self._learn_strategy_network()
-        if self._eval_func is not None:
-            self._eval_func(exploitee=self, num_train_episodes=self._eval_train_episodes,
-                            eval_every=self._eval_test_every, eval_episodes=self._eval_test_episodes)
-        if self._use_checkpoints:
-            self.save_policy_network(self._checkpoint_dir, f"iter{self._iteration - 1}")
-        return self._policy_network, advantage_losses, policy_loss
+        if cfg.eval_func is not None:
+            self._evaluate()
+        if cfg.use_checkpoints:
+            self._checkpoint(self._iteration - 1)
+        return self._policy_network, losses, policy_loss
 
     # ---- traversal -----------------------------------------------------------------------------------
     def traverse(self, player, num_traversals):
@@ -381,18 +406,18 @@ class DeepCFRSolver:
 
     def _children_of_traverser(self, strategy, legal):
         """bool [m, 18]: which actions of each traverser node are expanded (deep_cfr.py:438-466)."""
-        if self._sampling_method == "external":
+        if self.cfg.sampling_method == "external":
             return legal
         m = legal.shape[0]
         n_legal = legal.sum(-1)
-        if self._sampling_method == "e-outcome":
-            multi = torch.rand(m, device=self.device, generator=self._gen) < self._e_outcome
-            factor = torch.where(multi, self._outcome_factor, 1)
+        if self.cfg.sampling_method == "e-outcome":
+            multi = torch.rand(m, device=self.device, generator=self._gen) < self.cfg.e_outcome
+            factor = torch.where(multi, self.cfg.outcome_factor, 1)
         else:
-            factor = torch.full((m,), self._outcome_factor, device=self.device)
+            factor = torch.full((m,), self.cfg.outcome_factor, device=self.device)
         num_to_sample = torch.minimum(n_legal, factor)
         uniform = legal / n_legal.clamp_min(1).view(-1, 1)
-        probs = self._expl * uniform + (1.0 - self._expl) * strategy
+        probs = self.cfg.outcome_samp_expl * uniform + (1.0 - self.cfg.outcome_samp_expl) * strategy
         probs = probs / probs.sum(-1, keepdim=True)
         # np.random.choice(size=k, replace=False, p=probs) draws sequentially without replacement, which is the
         # Plackett-Luce order of the Gumbel-perturbed log-probabilities: take the k largest keys
@@ -412,9 +437,9 @@ class DeepCFRSolver:
         strategy = torch.empty((k, NUM_DISTINCT_ACTIONS), dtype=torch.float32, device=dev)
         expand = torch.empty(k, dtype=torch.int32, device=dev)
         counts = torch.empty(k, dtype=torch.int32, device=dev)
-        e_outcome = float(self._e_outcome) if self._sampling_method == "e-outcome" else -1.0
-        check(lib.coup_cfr_expand(ptr(adv), ptr(word), k, player, int(self._sampling_method == "external"),
-                                  int(self._outcome_factor), e_outcome, float(self._expl), self._expand_seed,
+        e_outcome = float(self.cfg.e_outcome) if self.cfg.sampling_method == "e-outcome" else -1.0
+        check(lib.coup_cfr_expand(ptr(adv), ptr(word), k, player, int(self.cfg.sampling_method == "external"),
+                                  int(self.cfg.outcome_factor), e_outcome, float(self.cfg.outcome_samp_expl), self._expand_seed,
                                   self._expand_counter, ptr(strategy), ptr(expand), ptr(counts), stream))
         self._expand_counter += 1
         ends = torch.cumsum(counts, 0, dtype=torch.int64)
@@ -530,11 +555,11 @@ class DeepCFRSolver:
     def _learn_advantage_network(self, player):
         memory, net, opt = self._advantage_memories[player], self._advantage_networks[player], self._optimizer_advantages[player]
         loss = None
-        for _ in range(self._advantage_network_train_steps):
-            if self._batch_size_advantage:
-                if self._batch_size_advantage > len(memory):
+        for _ in range(self.cfg.advantage_network_train_steps):
+            if self.cfg.batch_size_advantage:
+                if self.cfg.batch_size_advantage > len(memory):
                     return None                                                     # not enough samples (:562-564)
-                batch = memory.sample(self._batch_size_advantage)
+                batch = memory.sample(self.cfg.batch_size_advantage)
             else:
                 batch = memory.all()
             if batch["info_state"].shape[0] == 0:
@@ -550,11 +575,11 @@ class DeepCFRSolver:
     def _learn_strategy_network(self):
         memory = self._strategy_memories
         loss = None
-        for _ in range(self._policy_network_train_steps):
-            if self._batch_size_strategy:
-                if self._batch_size_strategy > len(memory):
+        for _ in range(self.cfg.policy_network_train_steps):
+            if self.cfg.batch_size_strategy:
+                if self.cfg.batch_size_strategy > len(memory):
                     return None
-                batch = memory.sample(self._batch_size_strategy)
+                batch = memory.sample(self.cfg.batch_size_strategy)
             else:
                 batch = memory.all()
             if batch["info_state"].shape[0] == 0:
