@@ -258,6 +258,13 @@ int coup_vec_legal_actions_mask(coup_vec_env* env, uint8_t* d_out, void* stream)
  * that are also 16-byte aligned (any fresh allocation) get the bulk-store encoder; others the plain-store one. */
 int coup_vec_information_state_tensor(coup_vec_env* env, int player, int dtype, void* d_out, void* stream);
 int coup_vec_observation_tensor(coup_vec_env* env, int player, int dtype, void* d_out, void* stream);
+/* The general observer, CoupGame::MakeObserver(IIGObservationType{public_info, perfect_recall, private_info})
+ * (coup.cc:1132-1141, 248-287; observer.h:270-315), for every env: private_info 0 kNone / 1 kSinglePlayer / 2 kAllPlayers
+ * decides whose face-down cards show, public_info adds face-up cards, cur_move_player, cards_state, coins and then the
+ * history (perfect_recall) or the last actions. Rows are contiguous: 2492 elements with public_info and perfect_recall,
+ * 98 with public_info only, 42 without public_info. (1, 1, 1) is the info-state tensor, (1, 0, 1) the observation tensor. */
+int coup_vec_observer_tensor(coup_vec_env* env, int player, int public_info, int perfect_recall, int private_info, int dtype,
+                             void* d_out, void* stream);
 /* Observation rows of a SUBSET of envs (row i, or rows 2i, 2i+1, describe env d_env_ids[i]). */
 int coup_vec_observation_tensor_gather(coup_vec_env* env, const uint32_t* d_env_ids, uint32_t count, int player, int dtype,
                                        void* d_out, void* stream);

@@ -49,7 +49,7 @@ EXPORTED_SYMBOLS = [
     "coup_vec_finished_ring_enable", "coup_vec_finished_ring", "coup_vec_finished_ring_ctrl", "coup_vec_finished_ring_capacity",
     "coup_vec_finished_drain", "coup_vec_finished_information_state_tensor", "coup_records_information_state_tensor",
     "coup_vec_finished_observation_tensor", "coup_records_observation_tensor", "coup_vec_observation_tensor_gather",
-    "coup_vec_step_record",
+    "coup_vec_step_record", "coup_vec_observer_tensor",
     "coup_tensor_row_hash", "coup_vec_snapshot_size", "coup_vec_snapshot", "coup_vec_restore", "coup_vec_step_counter", "coup_vec_set_step_counter",
 ]
 
@@ -132,6 +132,7 @@ def load():
     lib.coup_vec_finished_observation_tensor.argtypes = [vp, C.c_int, C.c_int, vp, C.c_uint32, vp, vp, vp]
     lib.coup_records_observation_tensor.argtypes = [vp, vp, vp, C.c_uint32, C.c_int, C.c_int, vp, vp]
     lib.coup_vec_observation_tensor_gather.argtypes = [vp, vp, C.c_uint32, C.c_int, C.c_int, vp, vp]
+    lib.coup_vec_observer_tensor.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
     lib.coup_vec_step_record.argtypes = [vp, vp, vp, C.POINTER(RecorderBuffers), vp]
     lib.coup_records_information_state_tensor.argtypes = [vp, vp, vp, C.c_uint32, C.c_int, C.c_int, vp, C.c_uint32, vp]
     lib.coup_vec_information_state_tensor.argtypes = [vp, C.c_int, C.c_int, vp, vp]

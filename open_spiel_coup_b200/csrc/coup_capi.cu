@@ -184,7 +184,8 @@ template <typename T, typename Src>
 int encode_obs_typed(coup_vec_env* env, const Src& src, uint32_t max_groups, int player, void* d_out, uint32_t* d_ids_out,
                      uint32_t* d_count_out, cudaStream_t st) {
   if (max_groups == 0) return COUP_OK;
-  const size_t smem = static_cast<size_t>(kObsWarps) * 32 * (player == COUP_PLAYER_BOTH ? 2 : 1) * COUP_OBSERVATION_SIZE * sizeof(T);
+  const uint32_t row_len = ((player >> 8) & kVisNoPublic) ? 42u : COUP_OBSERVATION_SIZE;
+  const size_t smem = static_cast<size_t>(kObsWarps) * 32 * ((player & 7) == COUP_PLAYER_BOTH ? 2 : 1) * row_len * sizeof(T);
   int sms = 0;
   cudaError_t err = cudaFuncSetAttribute(k_encode_obs<T, Src>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (err == cudaSuccess) err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, env->opts.device);
@@ -194,7 +195,7 @@ int encode_obs_typed(coup_vec_env* env, const Src& src, uint32_t max_groups, int
   const unsigned groups = (max_groups + 31) / 32;
   const unsigned grid = std::max(1u, std::min(static_cast<unsigned>(sms) * per_sm, (groups + kObsWarps - 1) / kObsWarps));
   const int use_bulk = reinterpret_cast<uintptr_t>(d_out) % 16u == 0 && (env->opts.flags & COUP_FLAG_PLAIN_STORE_ENCODER) == 0;
-  k_encode_obs<T, Src><<<grid, kObsThreads, smem, st>>>(src, player, static_cast<T*>(d_out), use_bulk, d_ids_out, d_count_out);
+  k_encode_obs<T, Src><<<grid, kObsThreads, smem, st>>>(src, player, static_cast<T*>(d_out), use_bulk, row_len, d_ids_out, d_count_out);
   return launch_status("k_encode_obs");
 }
 
@@ -657,6 +658,19 @@ int coup_vec_observation_tensor(coup_vec_env* env, int player, int dtype, void* 
   DeviceGuard guard(env->opts.device);
   const SlabSource src{env->A.state, env->A.history, nullptr, env->A.n};
   return encode_obs_dispatch(env, src, env->A.n, player, dtype, d_out, nullptr, nullptr, S(stream));
+}
+
+int coup_vec_observer_tensor(coup_vec_env* env, int player, int public_info, int perfect_recall, int private_info, int dtype,
+                             void* d_out, void* stream) {
+  if (!env || !d_out || !valid_player_sel(player) || !valid_dtype(dtype) || private_info < 0 || private_info > 2)
+    return fail(COUP_ERR_INVALID_ARG, "coup_vec_observer_tensor: bad arguments");
+  DeviceGuard guard(env->opts.device);
+  const uint32_t vis = (private_info == 0 ? kVisPrivateNone : private_info == 2 ? kVisPrivateAll : 0u) | (public_info ? 0u : kVisNoPublic);
+  const int sel = player | static_cast<int>(vis << 8);
+  const SlabSource src{env->A.state, env->A.history, nullptr, env->A.n};
+  if (public_info && perfect_recall)    // the info-state layout (2492), other visibility
+    return encode_info_dispatch(env, src, env->A.n, sel, dtype, d_out, COUP_INFO_STATE_SIZE, nullptr, nullptr, S(stream));
+  return encode_obs_dispatch(env, src, env->A.n, sel, dtype, d_out, nullptr, nullptr, S(stream));   // 98, or 42 without public info
 }
 
 int coup_vec_observation_tensor_gather(coup_vec_env* env, const uint32_t* d_env_ids, uint32_t count, int player, int dtype,

@@ -533,24 +533,31 @@ COUP_FN uint32_t resolve_chance(Env& s, const uint4& rnd, int first, const uint8
 // is 1 where float q is 1; floats 60/61 are the raw coin counts (207-213), returned separately.
 //   [0,2) observer  [2,22) p1_cards[4][5]  [22,42) p2_cards[4][5]  [42,44) cur_move_player
 //   [44,60) cards_state[2][4][2]  [60,62) coins
-COUP_FN uint64_t head_mask(const Env& s, uint32_t observer, bool terminal) {
+// `vis` selects the IIGObservationType (observer.h:270-315) of the general observer, CoupGame::MakeObserver
+// (1132-1141): 0 = private_info kSinglePlayer + public_info, the type of both built-in tensors; kVisPrivateNone /
+// kVisPrivateAll change whose face-down cards show (185-188, 258-265); kVisNoPublic drops everything public: face-up
+// cards, cur_move_player, cards_state (267-279) -- the tensor then ends after element 41.
+enum : uint32_t { kVisPrivateNone = 1u, kVisPrivateAll = 2u, kVisNoPublic = 4u };
+COUP_FN uint64_t head_mask(const Env& s, uint32_t observer, bool terminal, uint32_t vis = 0u) {
   uint64_t mask = 1ull << observer;                                    // WritePlayer, 160-165
+  const bool pub = (vis & kVisNoPublic) == 0;
 #pragma unroll
   for (uint32_t pl = 0; pl < 2; ++pl) {
     const uint32_t h = pw_hand(s.p[pl]);
+    const bool priv = (vis & kVisPrivateAll) != 0 || ((vis & kVisPrivateNone) == 0 && pl == observer);
 #pragma unroll
     for (uint32_t i = 0; i < 4; ++i) {
       const uint32_t key = hand_slot(h, i);
       if (key != 15u) {
         const uint32_t up = key & 1u, value = key >> 1;
-        // WritePlayerCardsValue 178-191 with kSinglePlayer private info (258-265): own face-down
-        // cards and every face-up card are visible.
-        if (up || pl == observer) mask |= 1ull << (2u + 20u * pl + 5u * i + value);
-        mask |= 1ull << (44u + (pl * 4u + i) * 2u + up);               // WriteCardsState, 194-204
+        // WritePlayerCardsValue 178-191: a face-down card shows to whom private info is granted, a face-up one to
+        // whoever sees public info
+        if (up ? pub : priv) mask |= 1ull << (2u + 20u * pl + 5u * i + value);
+        if (pub) mask |= 1ull << (44u + (pl * 4u + i) * 2u + up);     // WriteCardsState, 194-204
       }
     }
   }
-  if (!terminal) mask |= 1ull << (42u + g_mover(s.g));                 // 268-276
+  if (!terminal && pub) mask |= 1ull << (42u + g_mover(s.g));         // 268-276
   return mask;
 }
 

@@ -992,13 +992,14 @@ __device__ __forceinline__ void fill_record(uint32_t* rec, const Env& s, const u
     }
   }
   const bool term = is_terminal(s);
-  const uint32_t obs_a = player_sel == COUP_PLAYER_1 ? 1u
-                        : player_sel == COUP_PLAYER_CURRENT ? g_mover(s.g) : 0u;
+  const int who = player_sel & 7;                                   // COUP_PLAYER_*; bits 8.. = kVis* of the observer type
+  const uint32_t vis = static_cast<uint32_t>(player_sel) >> 8;
+  const uint32_t obs_a = who == COUP_PLAYER_1 ? 1u : who == COUP_PLAYER_CURRENT ? g_mover(s.g) : 0u;
   const uint32_t obs_b = 1u;
-  const uint64_t ma = head_mask(s, obs_a, term);
+  const uint64_t ma = head_mask(s, obs_a, term, vis);
   rec[16] = static_cast<uint32_t>(ma); rec[17] = static_cast<uint32_t>(ma >> 32);
-  if (player_sel == COUP_PLAYER_BOTH) {
-    const uint64_t mb = head_mask(s, obs_b, term);
+  if (who == COUP_PLAYER_BOTH) {
+    const uint64_t mb = head_mask(s, obs_b, term, vis);
     rec[18] = static_cast<uint32_t>(mb); rec[19] = static_cast<uint32_t>(mb >> 32);
   }
   rec[20] = c_moves(s.c) | (pw_coins(s.p[0]) << 8) | (pw_coins(s.p[1]) << 16) | (obs_a << 24) | (obs_b << 25);
@@ -1102,7 +1103,7 @@ struct RecordSource {
     hp = rec;
     sp = reinterpret_cast<const uint4*>(rec + kHistoryWords);
     id = rec[20];
-    if (sel == COUP_PLAYER_FROM_RECORD) sel = static_cast<int>(rec[21] >> 31);   // the seat the record was taken for
+    if ((sel & 7) == COUP_PLAYER_FROM_RECORD) sel = (sel & ~7) | static_cast<int>(rec[21] >> 31);   // the record's seat
   }
 };
 
@@ -1130,7 +1131,7 @@ k_encode_info(Src src, int player_sel, T* __restrict__ out, uint32_t stride, uin
   if (e < n) load_and_fill(src, e, player_sel, &s_rec[warp][lane * kRecWords], ids_out);
   __syncwarp();
   const int nrec = static_cast<int>(min(32u, n - e0));
-  const bool both = player_sel == COUP_PLAYER_BOTH;
+  const bool both = (player_sel & 7) == COUP_PLAYER_BOTH;
   using U = typename Unit4<T>::type;
   const int row_units = static_cast<int>(stride / 4);
   U* out_units = reinterpret_cast<U*>(out) + static_cast<size_t>(e0) * (both ? 2 : 1) * row_units;
@@ -1292,7 +1293,7 @@ k_encode_info_tma(Src src, int player_sel, T* __restrict__ out, uint32_t stride,
   const uint32_t e0 = b0 + warp * 32u;
   const uint32_t e = e0 + lane;
   const bool block_full = b0 + kTmaWarpsPerBlock * 32u <= n;  // uniform over the block
-  const bool both = player_sel == COUP_PLAYER_BOTH;
+  const bool both = (player_sel & 7) == COUP_PLAYER_BOTH;
   if (block_full) zero_stage(sm.stage, lane);
   if (e < n) load_and_fill(src, e, player_sel, sm.recs + lane * kRecWords, ids_out);
   if (block_full) {
@@ -1320,13 +1321,14 @@ constexpr int kObsWarps = 4;
 constexpr int kObsThreads = kObsWarps * 32;
 
 template <typename T>
-__device__ __forceinline__ void poke_obs_row(T* row, uint64_t head, uint64_t last_action, uint32_t coins, bool set) {
+__device__ __forceinline__ void poke_obs_row(T* row, uint64_t head, uint64_t last_action, uint32_t coins, bool set, bool pub) {
   const T one = Elem<T>::from(set ? 1u : 0u);
   while (head) {                                                        // elements 0..59
     const int b = __ffsll(static_cast<long long>(head)) - 1;
     head &= head - 1;
     row[b] = one;
   }
+  if (!pub) return;                                                     // no public info: the row ends after element 41
   row[60] = Elem<T>::from(set ? coins & 255u : 0u);                     // WriteCoins, 207-213
   row[61] = Elem<T>::from(set ? coins >> 8 : 0u);
   while (last_action) {                                                 // WriteLastAction, 217-225
@@ -1336,17 +1338,20 @@ __device__ __forceinline__ void poke_obs_row(T* row, uint64_t head, uint64_t las
   }
 }
 
+// player_sel: bits 0-2 COUP_PLAYER_*, bits 8.. kVis* (the observer type); row_len = 98, or 42 without public info.
 template <typename T, typename Src>
 __global__ void __launch_bounds__(kObsThreads)
-k_encode_obs(Src src, int player_sel, T* __restrict__ out, int use_bulk, uint32_t* __restrict__ ids_out,
+k_encode_obs(Src src, int player_sel, T* __restrict__ out, int use_bulk, uint32_t row_len, uint32_t* __restrict__ ids_out,
              uint32_t* __restrict__ count_out) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool both = player_sel == COUP_PLAYER_BOTH;
+  const uint32_t vis = static_cast<uint32_t>(player_sel) >> 8;
+  const bool pub = (vis & kVisNoPublic) == 0;
+  const bool both = (player_sel & 7) == COUP_PLAYER_BOTH;
   const uint32_t views = both ? 2u : 1u;
   const uint32_t n = src.rows();
   if (count_out != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *count_out = n;
-  const uint32_t span_elems = 32u * views * kObservationSize;
+  const uint32_t span_elems = 32u * views * row_len;
   T* stage = reinterpret_cast<T*>(smem_raw) + static_cast<size_t>(warp) * span_elems;
   for (uint32_t q = lane; q < span_elems * sizeof(T) / 16u; q += 32u) reinterpret_cast<uint4*>(stage)[q] = make_uint4(0u, 0u, 0u, 0u);
   __syncwarp();
@@ -1361,17 +1366,18 @@ k_encode_obs(Src src, int player_sel, T* __restrict__ out, int use_bulk, uint32_
       src.locate(e, sp, hp, id, sel);
       const Env s = load_env(sp);
       const bool term = is_terminal(s);
-      const uint32_t obs_a = sel == COUP_PLAYER_1 ? 1u : sel == COUP_PLAYER_CURRENT ? g_mover(s.g) : 0u;
-      head_a = head_mask(s, obs_a, term);
-      if (both) head_b = head_mask(s, 1u, term);
+      const int who = sel & 7;
+      const uint32_t obs_a = who == COUP_PLAYER_1 ? 1u : who == COUP_PLAYER_CURRENT ? g_mover(s.g) : 0u;
+      head_a = head_mask(s, obs_a, term, vis);
+      if (both) head_b = head_mask(s, 1u, term, vis);
       la = last_action_mask(s);
       coins = pw_coins(s.p[0]) | (pw_coins(s.p[1]) << 8);
       if (ids_out != nullptr) ids_out[e] = id;
-      T* row = stage + static_cast<size_t>(lane) * views * kObservationSize;
-      poke_obs_row<T>(row, head_a, la, coins, true);
-      if (both) poke_obs_row<T>(row + kObservationSize, head_b, la, coins, true);
+      T* row = stage + static_cast<size_t>(lane) * views * row_len;
+      poke_obs_row<T>(row, head_a, la, coins, true, pub);
+      if (both) poke_obs_row<T>(row + row_len, head_b, la, coins, true, pub);
     }
-    T* dst = out + static_cast<size_t>(e0) * views * kObservationSize;
+    T* dst = out + static_cast<size_t>(e0) * views * row_len;
     if (use_bulk && nrec == 32u) {
       tma_store_fence();
       __syncwarp();
@@ -1382,14 +1388,14 @@ k_encode_obs(Src src, int player_sel, T* __restrict__ out, int use_bulk, uint32_
       __syncwarp();
     } else {
       __syncwarp();
-      const uint32_t total = nrec * views * kObservationSize;
+      const uint32_t total = nrec * views * row_len;
       for (uint32_t i = lane; i < total; i += 32u) dst[i] = stage[i];
       __syncwarp();
     }
     if (e < n) {
-      T* row = stage + static_cast<size_t>(lane) * views * kObservationSize;
-      poke_obs_row<T>(row, head_a, la, coins, false);
-      if (both) poke_obs_row<T>(row + kObservationSize, head_b, la, coins, false);
+      T* row = stage + static_cast<size_t>(lane) * views * row_len;
+      poke_obs_row<T>(row, head_a, la, coins, false, pub);
+      if (both) poke_obs_row<T>(row + row_len, head_b, la, coins, false, pub);
     }
   }
   if (lane == 0) tma_wait_all();   // the engine must be done with this warp's shared memory before the CTA exits

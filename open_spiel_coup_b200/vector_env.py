@@ -231,6 +231,20 @@ class CoupVectorEnv:
                                                     self._ptr(out), _stream_ptr(self.device)))
         return out
 
+    def observer_tensor(self, player=PLAYER_CURRENT, public_info=True, perfect_recall=False, private_info=1, out=None,
+                        dtype=torch.float32):
+        """`game.make_observer(IIGObservationType(public_info, perfect_recall, private_info))` tensors (coup.cc:1132-1141)
+        for every env; private_info 0 none / 1 single player / 2 all players. [rows, 2492 | 98 | 42]."""
+        width = (INFO_STATE_SIZE if perfect_recall else OBSERVATION_SIZE) if public_info else 42
+        if out is None:
+            out = torch.empty((self._rows(player), width), dtype=dtype, device=self.device)
+        if tuple(out.shape) != (self._rows(player), width) or not out.is_contiguous():
+            raise ValueError(f"observer output must be a contiguous [{self._rows(player)}, {width}] tensor")
+        check(self._lib.coup_vec_observer_tensor(self._h, player, int(bool(public_info)), int(bool(perfect_recall)),
+                                                 int(private_info), _TORCH_TO_DTYPE[out.dtype], self._ptr(out),
+                                                 _stream_ptr(self.device)))
+        return out
+
     def observation_tensor_gather(self, env_ids, player=PLAYER_CURRENT, out=None, dtype=torch.float32):
         """Observation rows of the envs listed in `env_ids` only."""
         ids = env_ids.to(device=self.device, dtype=torch.int32).contiguous()
