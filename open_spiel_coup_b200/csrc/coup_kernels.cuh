@@ -587,6 +587,9 @@ k_fork(EnvArrays D, const uint4* __restrict__ src_state, const uint32_t* __restr
 // opponent's nodes one action drawn from the strategy (:482-487). Sampling without replacement is the Gumbel-top-k
 // order of the log-probabilities, i.e. the sequential renormalised draw of np.random.choice(replace=False).
 __device__ __forceinline__ float u01(uint32_t r) { return (static_cast<float>(r >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+__device__ __forceinline__ uint32_t cfr_expand_node(const float* __restrict__ adv_row, uint32_t word, uint32_t i, int traverser,
+                                                    int external, uint32_t outcome_factor, float e_outcome, float expl,
+                                                    uint64_t seed, uint64_t counter, float* __restrict__ strategy_row);
 
 __global__ void __launch_bounds__(kBlockThreads)
 k_cfr_expand(const float* __restrict__ advantages, const uint32_t* __restrict__ step_words, uint32_t count,
@@ -595,76 +598,8 @@ k_cfr_expand(const float* __restrict__ advantages, const uint32_t* __restrict__ 
              uint32_t* __restrict__ count_out) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
-  const uint32_t word = step_words[i];
-  const uint32_t legal = word & 0x3FFFFu;
-  const int player = (word >> 18) & 1u;
-  const int n_legal = __popc(legal);
-  float adv[18];
-#pragma unroll
-  for (int a = 0; a < 18; ++a) adv[a] = advantages[static_cast<size_t>(i) * 18 + a];
-  float total = 0.f, best = -INFINITY;
-  int best_a = 0;
-#pragma unroll
-  for (int a = 0; a < 18; ++a) {
-    if ((legal >> a) & 1u) {
-      total += fmaxf(adv[a], 0.f);
-      if (adv[a] > best) { best = adv[a]; best_a = a; }
-    }
-  }
-  float strat[18];
-#pragma unroll
-  for (int a = 0; a < 18; ++a) {
-    const bool ok = (legal >> a) & 1u;
-    strat[a] = !ok ? 0.f : total > 0.f ? fmaxf(adv[a], 0.f) / total : (a == best_a ? 1.f : 0.f);
-    strategy_out[static_cast<size_t>(i) * 18 + a] = strat[a];
-  }
-  uint32_t expand = 0;
-  if (n_legal > 0) {
-    const uint4 r0 = env_random(seed, i, counter, 2), r1 = env_random(seed, i, counter, 3), r2 = env_random(seed, i, counter, 4);
-    if (player != traverser) {
-      float sum = 0.f;
-#pragma unroll
-      for (int a = 0; a < 18; ++a) sum += strat[a];
-      const float target = u01(r0.x) * sum;
-      float acc = 0.f;
-      int pick = best_a;
-#pragma unroll
-      for (int a = 17; a >= 0; --a) if (strat[a] > 0.f) pick = a;           // fall-back: first action with mass
-      bool done = false;
-#pragma unroll
-      for (int a = 0; a < 18; ++a) {
-        if (!done && strat[a] > 0.f) { acc += strat[a]; pick = a; if (target < acc) done = true; }
-      }
-      expand = 1u << pick;
-    } else if (external) {
-      expand = legal;
-    } else {
-      uint32_t k = outcome_factor;
-      if (e_outcome >= 0.f) k = u01(r0.y) < e_outcome ? outcome_factor : 1u;
-      k = min(k, static_cast<uint32_t>(n_legal));
-      float key[18];
-      int slot = 0;                                                          // legal actions draw r0.z, r0.w, r1.*, r2.* in order
-#pragma unroll
-      for (int a = 0; a < 18; ++a) {
-        key[a] = -INFINITY;
-        if ((legal >> a) & 1u) {
-          const uint32_t r = slot == 0 ? r0.z : slot == 1 ? r0.w : slot == 2 ? r1.x : slot == 3 ? r1.y : slot == 4 ? r1.z
-                           : slot == 5 ? r1.w : slot == 6 ? r2.x : slot == 7 ? r2.y : slot == 8 ? r2.z : r2.w;
-          ++slot;
-          const float p = expl / n_legal + (1.f - expl) * strat[a];
-          if (p > 0.f) key[a] = logf(p) - logf(-logf(u01(r)));
-        }
-      }
-      for (uint32_t t = 0; t < k; ++t) {
-        int arg = -1;
-        float m = -INFINITY;
-#pragma unroll
-        for (int a = 0; a < 18; ++a) if (!((expand >> a) & 1u) && key[a] > m) { m = key[a]; arg = a; }
-        if (arg < 0) break;
-        expand |= 1u << arg;
-      }
-    }
-  }
+  const uint32_t expand = cfr_expand_node(advantages + static_cast<size_t>(i) * 18, step_words[i], i, traverser, external,
+                                          outcome_factor, e_outcome, expl, seed, counter, strategy_out + static_cast<size_t>(i) * 18);
   expand_out[i] = expand;
   count_out[i] = __popc(expand);
 }
@@ -822,6 +757,215 @@ k_step_record(EnvArrays A, RecorderArrays R, const uint8_t* __restrict__ actions
   }
   account(st, r, active);
   st.flush(A.stats);
+}
+
+// ---- a whole level of a sampled CFR traversal with DEVICE-side node counts ------------------------------------------------
+// The level-by-level expansion above, without the host in the loop: the number of nodes of a level lives in device memory
+// (levels shrink and grow with the sampling), every kernel is launched for the capacity of the level buffers and works on
+// the first *count nodes, and one single-CTA kernel per level does regret matching, child selection, the prefix sum of the
+// child counts and the (parent, action) lists, and leaves the next level's count. The host only checks "is the frontier
+// empty" every few levels.
+constexpr int kCfrLevelThreads = 1024;
+
+// Regret matching + child selection of ONE node (the body of k_cfr_expand as a function).
+__device__ __forceinline__ uint32_t cfr_expand_node(const float* __restrict__ adv_row, uint32_t word, uint32_t i, int traverser,
+                                                    int external, uint32_t outcome_factor, float e_outcome, float expl,
+                                                    uint64_t seed, uint64_t counter, float* __restrict__ strategy_row) {
+  const uint32_t legal = word & 0x3FFFFu;
+  const int player = (word >> 18) & 1u;
+  const int n_legal = __popc(legal);
+  float adv[18];
+#pragma unroll
+  for (int a = 0; a < 18; ++a) adv[a] = adv_row[a];
+  float total = 0.f, best = -INFINITY;
+  int best_a = 0;
+#pragma unroll
+  for (int a = 0; a < 18; ++a) {
+    if ((legal >> a) & 1u) {
+      total += fmaxf(adv[a], 0.f);
+      if (adv[a] > best) { best = adv[a]; best_a = a; }
+    }
+  }
+  float strat[18];
+#pragma unroll
+  for (int a = 0; a < 18; ++a) {
+    const bool ok = (legal >> a) & 1u;
+    strat[a] = !ok ? 0.f : total > 0.f ? fmaxf(adv[a], 0.f) / total : (a == best_a ? 1.f : 0.f);
+    strategy_row[a] = strat[a];
+  }
+  uint32_t expand = 0;
+  if (n_legal > 0) {
+    const uint4 r0 = env_random(seed, i, counter, 2), r1 = env_random(seed, i, counter, 3), r2 = env_random(seed, i, counter, 4);
+    if (player != traverser) {
+      float sum = 0.f;
+#pragma unroll
+      for (int a = 0; a < 18; ++a) sum += strat[a];
+      const float target = u01(r0.x) * sum;
+      float acc = 0.f;
+      int pick = best_a;
+#pragma unroll
+      for (int a = 17; a >= 0; --a) if (strat[a] > 0.f) pick = a;           // fall-back: first action with mass
+      bool done = false;
+#pragma unroll
+      for (int a = 0; a < 18; ++a) {
+        if (!done && strat[a] > 0.f) { acc += strat[a]; pick = a; if (target < acc) done = true; }
+      }
+      expand = 1u << pick;
+    } else if (external) {
+      expand = legal;
+    } else {
+      uint32_t k = outcome_factor;
+      if (e_outcome >= 0.f) k = u01(r0.y) < e_outcome ? outcome_factor : 1u;
+      k = min(k, static_cast<uint32_t>(n_legal));
+      float key[18];
+      int slot = 0;                                                          // legal actions draw r0.z, r0.w, r1.*, r2.* in order
+#pragma unroll
+      for (int a = 0; a < 18; ++a) {
+        key[a] = -INFINITY;
+        if ((legal >> a) & 1u) {
+          const uint32_t r = slot == 0 ? r0.z : slot == 1 ? r0.w : slot == 2 ? r1.x : slot == 3 ? r1.y : slot == 4 ? r1.z
+                           : slot == 5 ? r1.w : slot == 6 ? r2.x : slot == 7 ? r2.y : slot == 8 ? r2.z : r2.w;
+          ++slot;
+          const float p = expl / n_legal + (1.f - expl) * strat[a];
+          if (p > 0.f) key[a] = logf(p) - logf(-logf(u01(r)));
+        }
+      }
+      for (uint32_t t = 0; t < k; ++t) {
+        int arg = -1;
+        float m = -INFINITY;
+#pragma unroll
+        for (int a = 0; a < 18; ++a) if (!((expand >> a) & 1u) && key[a] > m) { m = key[a]; arg = a; }
+        if (arg < 0) break;
+        expand |= 1u << arg;
+      }
+    }
+  }
+  return expand;
+}
+
+// One CTA. Nodes [0, *count) of the level: terminal nodes (bit 19 of the step word) expand nothing. Writes, per node,
+// strategy [18], expand mask and the exclusive prefix `offset` of its children; per child (parent order, ascending action)
+// parent index and action; *next_count = number of children, clipped to `capacity` (then *overflow is set: the level is
+// truncated -- the caller sized the buffers too small).
+__global__ void __launch_bounds__(kCfrLevelThreads)
+k_cfr_level(const float* __restrict__ advantages, const uint32_t* __restrict__ step_words, const uint32_t* __restrict__ count_ptr,
+            uint32_t capacity, int traverser, int external, uint32_t outcome_factor, float e_outcome, float expl, uint64_t seed,
+            uint64_t counter, float* __restrict__ strategy_out, uint32_t* __restrict__ expand_out, uint32_t* __restrict__ offset_out,
+            uint32_t* __restrict__ parent_out, uint8_t* __restrict__ action_out, uint32_t* __restrict__ next_count,
+            uint32_t* __restrict__ overflow) {
+  __shared__ uint32_t s_warp[kCfrLevelThreads / 32];
+  __shared__ uint32_t s_base;
+  const uint32_t count = min(*count_ptr, capacity);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_base = 0;
+  __syncthreads();
+  for (uint32_t start = 0; start < count; start += kCfrLevelThreads) {     // uniform trip count
+    const uint32_t i = start + threadIdx.x;
+    uint32_t expand = 0;
+    if (i < count) {
+      const uint32_t word = step_words[i];
+      if (((word >> 19) & 1u) == 0)
+        expand = cfr_expand_node(advantages + static_cast<size_t>(i) * 18, word, i, traverser, external, outcome_factor,
+                                 e_outcome, expl, seed, counter, strategy_out + static_cast<size_t>(i) * 18);
+      expand_out[i] = expand;
+    }
+    // block-wide exclusive scan of the child counts of this chunk
+    const uint32_t c = __popc(expand);
+    uint32_t incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t w = s_warp[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += v;
+      }
+      s_warp[lane] = w;                      // inclusive over warps
+    }
+    __syncthreads();
+    const uint32_t base = s_base + (warp ? s_warp[warp - 1] : 0u) + incl - c;
+    const uint32_t chunk_total = s_warp[kCfrLevelThreads / 32 - 1];
+    if (i < count) {
+      offset_out[i] = base;
+      uint32_t bits = expand, pos = base;
+      while (bits) {
+        const int a = __ffs(bits) - 1;
+        bits &= bits - 1;
+        if (pos < capacity) { parent_out[pos] = i; action_out[pos] = static_cast<uint8_t>(a); }
+        ++pos;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_base += chunk_total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const uint32_t total = s_base;
+    *next_count = min(total, capacity);
+    if (total > capacity) *overflow = 1u;
+  }
+}
+
+// Backward pass of one level (deep_cfr.py:468-480, 492-497), thread per node: a terminal node's value is the traverser's
+// return; an opponent node's value is its sampled child's; a traverser node's is cfv = sum_a strategy[a] * payoff[a] over
+// its expanded children (unsampled actions count as payoff 0, as in the reference), and its sampled regrets are
+// payoff[a] - cfv on the legal actions. `child_value` are the values of the next level (node offset[i] + j = j-th child).
+__global__ void __launch_bounds__(kBlockThreads)
+k_cfr_backward(const uint32_t* __restrict__ step_words, const uint32_t* __restrict__ count_ptr, uint32_t capacity, int traverser,
+               const float* __restrict__ strategy, const uint32_t* __restrict__ expand, const uint32_t* __restrict__ offset,
+               const double* __restrict__ child_value, double* __restrict__ value_out, float* __restrict__ regret_out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= min(*count_ptr, capacity)) return;
+  const uint32_t word = step_words[i];
+  const double sign = traverser == 0 ? 1.0 : -1.0;
+  if ((word >> 19) & 1u) {                                     // terminal: Returns()[traverser]
+    value_out[i] = sign * (static_cast<int>((word >> 24) & 7u) - 2);
+    return;
+  }
+  const uint32_t legal = word & 0x3FFFFu;
+  const bool is_trav = static_cast<int>((word >> 18) & 1u) == traverser;
+  double payoff[18];
+#pragma unroll
+  for (int a = 0; a < 18; ++a) payoff[a] = 0.0;
+  uint32_t bits = expand[i], pos = offset[i];
+  double sum = 0.0;
+  while (bits) {
+    const int a = __ffs(bits) - 1;
+    bits &= bits - 1;
+    const double v = pos < capacity ? child_value[pos] : 0.0;
+#pragma unroll
+    for (int b = 0; b < 18; ++b) if (b == a) payoff[b] = v;
+    sum += v;
+    ++pos;
+  }
+  if (!is_trav) { value_out[i] = sum; return; }
+  double cfv = 0.0;
+#pragma unroll
+  for (int a = 0; a < 18; ++a) if ((legal >> a) & 1u) cfv += static_cast<double>(strategy[static_cast<size_t>(i) * 18 + a]) * payoff[a];
+  value_out[i] = cfv;
+#pragma unroll
+  for (int a = 0; a < 18; ++a)
+    regret_out[static_cast<size_t>(i) * 18 + a] = ((legal >> a) & 1u) ? static_cast<float>(payoff[a] - cfv) : 0.f;
+}
+
+// The nodes [0, *count) of a slab as packed records (history, state, meta: node index, seat<<31 | step word bits 0-26).
+__global__ void __launch_bounds__(kBlockThreads)
+k_pack_records(EnvArrays A, const uint32_t* __restrict__ count_ptr, uint32_t* __restrict__ records) {
+  const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= min(*count_ptr, A.n)) return;
+  uint4* dst = reinterpret_cast<uint4*>(records + static_cast<size_t>(e) * kRecordWords);
+  const uint4* h4 = reinterpret_cast<const uint4*>(A.history + static_cast<size_t>(e) * kHistoryWords);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) dst[k] = h4[k];
+  dst[4] = A.state[e];
+  const uint32_t word = A.step_word[e];
+  dst[5] = make_uint4(e, (((word >> 18) & 1u) << 31) | (word & 0x7FFFFFFu), 0u, 0u);
 }
 
 // ---- uniform-random legal action (same draw the fused rollout would use at this step counter) ------
@@ -1656,10 +1800,34 @@ k_rollout_ws(EnvArrays A, uint64_t step, int player_sel, T* __restrict__ out, ui
 constexpr int kIncRecWords = 8;
 constexpr int kIncRowPitch = kHistoryWords + 1;   // conflict-free per-lane rows in shared memory
 
-// Sixteen bytes of consecutive tensor elements from their small-integer values.
+// 192 one-bit elements: the 0/1 content of a span of a row, bit t = element (span start + t).
+struct Bits192 {
+  unsigned long long w0, w1, w2;
+  __device__ __forceinline__ void set(int t) {                        // ignores t outside [0, 192)
+    const unsigned long long m = 1ull << (t & 63);
+    w0 |= (t >= 0 && t < 64) ? m : 0ull;
+    w1 |= (t >= 64 && t < 128) ? m : 0ull;
+    w2 |= (t >= 128 && t < 192) ? m : 0ull;
+  }
+  __device__ __forceinline__ void or64(unsigned long long v, int t) {  // v at offset t, 0 <= t < 64
+    w0 |= v << t;
+    w1 |= t ? v >> (64 - t) : 0ull;
+  }
+  __device__ __forceinline__ uint32_t get16(uint32_t o) const {        // bits o .. o+15, zeros past the end
+    const uint32_t w = o >> 6, sh = o & 63u;
+    const unsigned long long a = w == 0 ? w0 : w == 1 ? w1 : w == 2 ? w2 : 0ull;
+    const unsigned long long b = w == 0 ? w1 : w == 1 ? w2 : 0ull;
+    return static_cast<uint32_t>((a >> sh) | (sh ? b << (64u - sh) : 0ull)) & 0xFFFFu;
+  }
+};
+
+// Sixteen bytes of consecutive tensor elements: from 0/1 bits, or from small-integer values.
 template <typename T> struct Pack16;
 template <> struct Pack16<float> {
   static constexpr int kElems = 4;
+  static __device__ __forceinline__ uint4 from_bits(uint32_t b) {
+    return make_uint4((b & 1u) * 0x3F800000u, ((b >> 1) & 1u) * 0x3F800000u, ((b >> 2) & 1u) * 0x3F800000u, ((b >> 3) & 1u) * 0x3F800000u);
+  }
   template <typename F> static __device__ __forceinline__ uint4 make(F value) {
     return make_uint4(__float_as_uint(static_cast<float>(value(0))), __float_as_uint(static_cast<float>(value(1))),
                       __float_as_uint(static_cast<float>(value(2))), __float_as_uint(static_cast<float>(value(3))));
@@ -1667,6 +1835,12 @@ template <> struct Pack16<float> {
 };
 template <> struct Pack16<__nv_bfloat16> {
   static constexpr int kElems = 8;
+  static __device__ __forceinline__ uint4 from_bits(uint32_t b) {
+    uint32_t w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) w[k] = ((b >> (2 * k)) & 1u) * 0x3F80u + ((b >> (2 * k + 1)) & 1u) * 0x3F800000u;
+    return make_uint4(w[0], w[1], w[2], w[3]);
+  }
   template <typename F> static __device__ __forceinline__ uint4 make(F value) {
     uint32_t w[4];
 #pragma unroll
@@ -1676,6 +1850,12 @@ template <> struct Pack16<__nv_bfloat16> {
 };
 template <> struct Pack16<uint8_t> {
   static constexpr int kElems = 16;
+  static __device__ __forceinline__ uint4 from_bits(uint32_t b) {
+    uint32_t w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) w[k] = (((b >> (4 * k)) & 15u) * 0x00204081u) & 0x01010101u;   // four bits -> four bytes
+    return make_uint4(w[0], w[1], w[2], w[3]);
+  }
   template <typename F> static __device__ __forceinline__ uint4 make(F value) {
     uint32_t w[4];
 #pragma unroll
@@ -1709,18 +1889,25 @@ k_rollout_incremental(EnvArrays A, uint64_t step, T* __restrict__ buf, uint32_t 
       const bool redealt = r.finished && new_len < r.final_moves + 1 && (A.flags & COUP_FLAG_AUTO_RESET);
       const uint32_t first = redealt ? 0u : old_len;   // rows [first, new_len) are (re)written, at most 4
       const bool term = is_terminal(s);
-      auto code_at = [&](uint32_t i) { const uint32_t w = i / 6u; return (row_copy[w] >> (5u * (i - 6u * w))) & 31u; };
-      // 5-bit codes: [0,20) the new rows, [20,25) row 0, [25,30) the row before the first new one
-      uint32_t codes = ((new_len ? code_at(0u) : 31u) << 20) | ((first ? code_at(first - 1u) : 31u) << 25);
-      for (uint32_t i = first, k = 0; i < new_len; ++i, ++k) codes |= code_at(i) << (5u * k);
+      auto code_at = [&](uint32_t i) {                  // 31 = no such row
+        const uint32_t w = min(i, 95u) / 6u;
+        return i < new_len ? (row_copy[w] >> (5u * (i - 6u * w))) & 31u : 31u;
+      };
+      // 5-bit codes of rows 0..3 (next to the head) and of rows first-2 .. first+3 (around the new rows)
+      uint32_t lead = 0, tail = 0;
+#pragma unroll
+      for (uint32_t k = 0; k < 4; ++k) lead |= code_at(k) << (5u * k);
+#pragma unroll
+      for (uint32_t k = 0; k < 6; ++k) tail |= (first + k >= 2u ? code_at(first + k - 2u) : 31u) << (5u * k);
       uint32_t* rec = s_rec[warp][lane];
       const uint64_t m0 = head_mask(s, 0u, term), m1 = head_mask(s, 1u, term);
       rec[0] = static_cast<uint32_t>(m0); rec[1] = static_cast<uint32_t>(m0 >> 32);
       rec[2] = static_cast<uint32_t>(m1); rec[3] = static_cast<uint32_t>(m1 >> 32);
       rec[4] = pw_coins(s.p[0]) | (pw_coins(s.p[1]) << 8) | (first << 16) | ((new_len - first) << 24);
-      rec[5] = codes;
+      rec[5] = lead;
+      rec[6] = tail;
       // after a re-deal everything from element 0 to the end of the finished episode's rows is one span
-      rec[6] = redealt ? max(r.final_moves, new_len) : 0u;
+      rec[7] = redealt ? max(r.final_moves, new_len) : 0u;
     }
   }
   account(st, r, active);
@@ -1734,38 +1921,46 @@ k_rollout_incremental(EnvArrays A, uint64_t step, T* __restrict__ buf, uint32_t 
     const int j = __ffs(touched) - 1;
     touched &= touched - 1;
     const uint32_t* rec = s_rec[warp][j];
-    const uint32_t mlo = rec[2 * view], mhi = rec[2 * view + 1], meta = rec[4], codes = rec[5], span_end = rec[6];
+    const uint32_t mlo = rec[2 * view], mhi = rec[2 * view + 1], meta = rec[4], lead = rec[5], tail = rec[6], span_end = rec[7];
     const uint32_t first = (meta >> 16) & 255u, n_new = meta >> 24;
-    const size_t row_base = (static_cast<size_t>(e0 + j) * 2 + view) * stride;       // absolute element index of element 0
-    // value of element p of this row; p < 0 is the (zero) tail of the previous row
-    auto value = [&](int p) -> uint32_t {
-      if (p < 0) return 0u;
-      if (p < 32) return (mlo >> p) & 1u;
-      if (p < 60) return (mhi >> (p - 32)) & 1u;
-      if (p < 62) return (meta >> (8 * (p - 60))) & 255u;
-      const uint32_t q = static_cast<uint32_t>(p) - 62u;
-      const uint32_t i = q / 18u, a = q - 18u * i;
-      uint32_t code = 31u;                                                              // rows nobody set: zeros
-      if (i - first < n_new) code = (codes >> (5u * (i - first))) & 31u;
-      else if (i + 1u == first) code = (codes >> 25) & 31u;
-      else if (i == 0u) code = (codes >> 20) & 31u;
-      return history_column(code, view) == a ? 1u : 0u;
-    };
-    // spans in row elements: [0, 62) and the new rows -- or one span after a re-deal
-    uint32_t lo[2], hi[2];
-    lo[0] = 0u; hi[0] = span_end ? 62u + 18u * span_end : 62u;
-    lo[1] = 62u + 18u * first; hi[1] = span_end ? lo[1] : lo[1] + 18u * n_new;
+    const uint32_t coin0 = meta & 255u, coin1 = (meta >> 8) & 255u;
+    const size_t row_base = (static_cast<size_t>(e0 + j) * 2 + view) * stride;       // absolute index of element 0 of the row
+    // two spans in row elements: [0, 62) and the new rows -- or one span after a re-deal
 #pragma unroll
     for (int sp = 0; sp < 2; ++sp) {
-      if (hi[sp] <= lo[sp]) continue;
-      const size_t abs_lo = (row_base + lo[sp]) / kSector * kSector;                    // widened to whole sectors
-      const size_t abs_hi = (row_base + hi[sp] + kSector - 1u) / kSector * kSector;
+      const uint32_t lo = sp == 0 ? 0u : 62u + 18u * first;
+      const uint32_t hi = sp == 0 ? (span_end ? 62u + 18u * span_end : 62u) : (span_end ? lo : lo + 18u * n_new);
+      if (hi <= lo) continue;
+      const size_t abs_lo = (row_base + lo) / kSector * kSector;                      // widened to whole sectors
+      const size_t abs_hi = (row_base + hi + kSector - 1u) / kSector * kSector;
       const uint32_t units = static_cast<uint32_t>((abs_hi - abs_lo) / kEl);
+      const int p_start = static_cast<int>(static_cast<long long>(abs_lo) - static_cast<long long>(row_base));   // >= -31
+      // the 0/1 content of the span and of what the widening touches: the previous row's tail and everything past the
+      // last move are zeros; next to the head, rows 0..3; around the new rows, rows first-2 .. first+3
+      Bits192 bm{0ull, 0ull, 0ull};
+      if (sp == 0) {
+        bm.or64((static_cast<unsigned long long>(mhi) << 32) | mlo, -p_start);        // -p_start in [0, 31]
+#pragma unroll
+        for (uint32_t k = 0; k < 4; ++k) {
+          const uint32_t col = history_column((lead >> (5u * k)) & 31u, view);
+          if (col != 31u) bm.set(62 + 18 * static_cast<int>(k) + static_cast<int>(col) - p_start);
+        }
+      } else {
+#pragma unroll
+        for (uint32_t k = 0; k < 6; ++k) {
+          const uint32_t col = history_column((tail >> (5u * k)) & 31u, view);
+          if (col != 31u) bm.set(62 + 18 * (static_cast<int>(first + k) - 2) + static_cast<int>(col) - p_start);
+        }
+      }
       uint4* dst = reinterpret_cast<uint4*>(buf + abs_lo);
-      const int p0 = static_cast<int>(static_cast<long long>(abs_lo) - static_cast<long long>(row_base));
       for (uint32_t u = l; u < units; u += 16u) {
-        const int p = p0 + static_cast<int>(u * kEl);
-        dst[u] = Pack16<T>::make([&](int k) { return value(p + k); });
+        const uint32_t o = u * kEl;
+        const uint32_t bits = bm.get16(o);
+        const int p = p_start + static_cast<int>(o);            // row element of the unit's first element
+        uint4 v = Pack16<T>::from_bits(bits);
+        if (sp == 0 && p <= 61 && p + static_cast<int>(kEl) > 60)   // the unit that holds the raw coin counts (207-213)
+          v = Pack16<T>::make([&](int k) { return p + k == 60 ? coin0 : p + k == 61 ? coin1 : (bits >> k) & 1u; });
+        dst[u] = v;
       }
     }
   }
