@@ -191,6 +191,30 @@ int coup_cfr_expand(const float* d_advantages, const uint32_t* d_step_words, uin
 int coup_cfr_children(const uint32_t* d_expand, const int64_t* d_offsets, uint32_t count, uint32_t* d_parent_out,
                       uint8_t* d_action_out, void* stream);
 
+/* The same traversal level WITHOUT the host in the loop: the number of nodes of a level lives in device memory (*d_count),
+ * every call is launched for a capacity and works on the first min(*d_count, capacity) nodes.
+ *   coup_vec_information_state_tensor_prefix: info-state rows of envs [0, *d_count) of a slab.
+ *   coup_cfr_level: coup_cfr_expand + the prefix sum of the child counts + coup_cfr_children in one single-CTA kernel:
+ *     strategy [capacity][18], expand masks, d_offset_out[i] = index of node i's first child in the next level, the
+ *     children's (parent, action) lists in parent order, *d_next_count = number of children (clipped to capacity, then
+ *     *d_overflow = 1). Terminal nodes (bit 19 of the step word) have no children.
+ *   coup_vec_fork_counted: coup_vec_fork for the first min(*d_count, max_count) children.
+ *   coup_vec_pack_records: the nodes [0, *d_count) of a slab as packed records (meta: node index, seat<<31 | step word).
+ *   coup_cfr_backward: the return path of `_traverse_game_tree` (deep_cfr.py:468-480, 492-497) for one level: values
+ *     (double) from the next level's values, and the sampled regrets [capacity][18] of the traverser's nodes. */
+int coup_vec_information_state_tensor_prefix(coup_vec_env* env, const uint32_t* d_count, uint32_t max_count, int player, int dtype,
+                                             void* d_out, uint32_t row_stride, void* stream);
+int coup_cfr_level(const float* d_advantages, const uint32_t* d_step_words, const uint32_t* d_count, uint32_t capacity,
+                   int traverser, int external, uint32_t outcome_factor, float e_outcome, float expl, uint64_t seed,
+                   uint64_t counter, float* d_strategy_out, uint32_t* d_expand_out, uint32_t* d_offset_out,
+                   uint32_t* d_parent_out, uint8_t* d_action_out, uint32_t* d_next_count, uint32_t* d_overflow, void* stream);
+int coup_vec_fork_counted(coup_vec_env* dst, const coup_vec_env* src, const uint32_t* d_parent, const uint8_t* d_actions,
+                          const uint32_t* d_count, uint32_t max_count, void* stream);
+int coup_vec_pack_records(coup_vec_env* env, const uint32_t* d_count, uint32_t* d_records_out, void* stream);
+int coup_cfr_backward(const uint32_t* d_step_words, const uint32_t* d_count, uint32_t capacity, int traverser,
+                      const float* d_strategy, const uint32_t* d_expand, const uint32_t* d_offset, const double* d_child_value,
+                      double* d_value_out, float* d_regret_out, void* stream);
+
 /* Single-env accessors with HOST buffers, following rust_open_spiel.h one to one (GameNewInitialState :41,
  * StateApplyAction :62, StateClone :49, StateInformationStateTensor / StateObservationTensor :73-76: tensors
  * are written into a caller-provided buffer of explicit length). `slot` indexes an env of the handle; these

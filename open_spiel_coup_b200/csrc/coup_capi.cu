@@ -382,10 +382,76 @@ int coup_vec_fork(coup_vec_env* dst, const coup_vec_env* src, const uint32_t* d_
     D.flags &= ~static_cast<uint32_t>(COUP_FLAG_AUTO_RESET);
     D.ring = nullptr;   // children stay terminal and readable in place: nothing to hand over
     k_fork<<<blocks_for(count), kBlockThreads, 0, S(stream)>>>(D, src->A.state, src->A.history, src->A.n, d_parent, d_actions,
-                                                             d_forced_chance, count, dst->step_counter);
+                                                             d_forced_chance, count, dst->step_counter, nullptr);
   }
   dst->step_counter++;
   return launch_status("k_fork");
+}
+
+// ---- a traversal level without the host in the loop: node counts stay in device memory ---------------------------------
+int coup_vec_fork_counted(coup_vec_env* dst, const coup_vec_env* src, const uint32_t* d_parent, const uint8_t* d_actions,
+                          const uint32_t* d_count, uint32_t max_count, void* stream) {
+  if (!dst || !src || dst == src || !d_parent || !d_actions || !d_count)
+    return fail(COUP_ERR_INVALID_ARG, "coup_vec_fork_counted: null argument or dst == src");
+  if (dst->opts.device != src->opts.device) return fail(COUP_ERR_INVALID_ARG, "coup_vec_fork_counted: handles on different devices");
+  max_count = std::min(max_count, dst->A.n);
+  DeviceGuard guard(dst->opts.device);
+  if (max_count) {
+    EnvArrays D = dst->A;
+    D.flags &= ~static_cast<uint32_t>(COUP_FLAG_AUTO_RESET);
+    D.ring = nullptr;
+    k_fork<<<blocks_for(max_count), kBlockThreads, 0, S(stream)>>>(D, src->A.state, src->A.history, src->A.n, d_parent, d_actions,
+                                                                 nullptr, max_count, dst->step_counter, d_count);
+  }
+  dst->step_counter++;
+  return launch_status("k_fork");
+}
+
+int coup_vec_information_state_tensor_prefix(coup_vec_env* env, const uint32_t* d_count, uint32_t max_count, int player, int dtype,
+                                             void* d_out, uint32_t row_stride, void* stream) {
+  if (!env || !d_out || !d_count || !valid_player_sel(player) || !valid_dtype(dtype) || !valid_stride(row_stride))
+    return fail(COUP_ERR_INVALID_ARG, "coup_vec_information_state_tensor_prefix: bad arguments");
+  DeviceGuard guard(env->opts.device);
+  max_count = std::min(max_count, env->A.n);
+  const SlabSource src{env->A.state, env->A.history, nullptr, max_count, d_count};
+  return encode_info_dispatch(env, src, max_count, player, dtype, d_out, row_stride, nullptr, nullptr, S(stream));
+}
+
+int coup_vec_pack_records(coup_vec_env* env, const uint32_t* d_count, uint32_t* d_records_out, void* stream) {
+  if (!env || !d_count || !d_records_out) return fail(COUP_ERR_INVALID_ARG, "coup_vec_pack_records: null argument");
+  DeviceGuard guard(env->opts.device);
+  k_pack_records<<<blocks_for(env->A.n), kBlockThreads, 0, S(stream)>>>(env->A, d_count, d_records_out);
+  return launch_status("k_pack_records");
+}
+
+int coup_cfr_level(const float* d_advantages, const uint32_t* d_step_words, const uint32_t* d_count, uint32_t capacity,
+                   int traverser, int external, uint32_t outcome_factor, float e_outcome, float expl, uint64_t seed,
+                   uint64_t counter, float* d_strategy_out, uint32_t* d_expand_out, uint32_t* d_offset_out,
+                   uint32_t* d_parent_out, uint8_t* d_action_out, uint32_t* d_next_count, uint32_t* d_overflow, void* stream) {
+  if (!d_advantages || !d_step_words || !d_count || !d_strategy_out || !d_expand_out || !d_offset_out || !d_parent_out ||
+      !d_action_out || !d_next_count || !d_overflow || capacity == 0 || outcome_factor == 0 || (traverser != 0 && traverser != 1))
+    return fail(COUP_ERR_INVALID_ARG, "coup_cfr_level: bad arguments");
+  const int dev = device_of(d_advantages);
+  if (dev < 0) return fail(COUP_ERR_INVALID_ARG, "coup_cfr_level: d_advantages is not a device pointer");
+  DeviceGuard guard(dev);
+  k_cfr_level<<<1, kCfrLevelThreads, 0, S(stream)>>>(d_advantages, d_step_words, d_count, capacity, traverser, external,
+                                                     outcome_factor, e_outcome, expl, seed, counter, d_strategy_out, d_expand_out,
+                                                     d_offset_out, d_parent_out, d_action_out, d_next_count, d_overflow);
+  return launch_status("k_cfr_level");
+}
+
+int coup_cfr_backward(const uint32_t* d_step_words, const uint32_t* d_count, uint32_t capacity, int traverser,
+                      const float* d_strategy, const uint32_t* d_expand, const uint32_t* d_offset, const double* d_child_value,
+                      double* d_value_out, float* d_regret_out, void* stream) {
+  if (!d_step_words || !d_count || !d_strategy || !d_expand || !d_offset || !d_child_value || !d_value_out || !d_regret_out ||
+      capacity == 0 || (traverser != 0 && traverser != 1))
+    return fail(COUP_ERR_INVALID_ARG, "coup_cfr_backward: bad arguments");
+  const int dev = device_of(d_step_words);
+  if (dev < 0) return fail(COUP_ERR_INVALID_ARG, "coup_cfr_backward: d_step_words is not a device pointer");
+  DeviceGuard guard(dev);
+  k_cfr_backward<<<blocks_for(capacity), kBlockThreads, 0, S(stream)>>>(d_step_words, d_count, capacity, traverser, d_strategy,
+                                                                       d_expand, d_offset, d_child_value, d_value_out, d_regret_out);
+  return launch_status("k_cfr_backward");
 }
 
 int coup_cfr_expand(const float* d_advantages, const uint32_t* d_step_words, uint32_t count, int traverser, int external,
@@ -558,7 +624,7 @@ int coup_vec_information_state_tensor_gather(coup_vec_env* env, const uint32_t* 
       (count > 0 && !d_env_ids))
     return fail(COUP_ERR_INVALID_ARG, "coup_vec_information_state_tensor_gather: bad arguments");
   DeviceGuard guard(env->opts.device);
-  const SlabSource src{env->A.state, env->A.history, d_env_ids, count};   // count == 0 is an empty gather, not "all envs"
+  const SlabSource src{env->A.state, env->A.history, d_env_ids, count, nullptr};   // count == 0 is an empty gather, not "all envs"
   return encode_info_dispatch(env, src, count, player, dtype, d_out, row_stride, nullptr, nullptr, S(stream));
 }
 
@@ -567,7 +633,7 @@ int coup_vec_information_state_tensor_strided(coup_vec_env* env, int player, int
   if (!env || !d_out || !valid_player_sel(player) || !valid_dtype(dtype) || !valid_stride(row_stride))
     return fail(COUP_ERR_INVALID_ARG, "coup_vec_information_state_tensor: bad arguments");
   DeviceGuard guard(env->opts.device);
-  const SlabSource src{env->A.state, env->A.history, nullptr, env->A.n};
+  const SlabSource src{env->A.state, env->A.history, nullptr, env->A.n, nullptr};
   return encode_info_dispatch(env, src, env->A.n, player, dtype, d_out, row_stride, nullptr, nullptr, S(stream));
 }
 
@@ -656,7 +722,7 @@ int coup_vec_observation_tensor(coup_vec_env* env, int player, int dtype, void* 
   if (!env || !d_out || !valid_player_sel(player) || !valid_dtype(dtype))
     return fail(COUP_ERR_INVALID_ARG, "coup_vec_observation_tensor: bad arguments");
   DeviceGuard guard(env->opts.device);
-  const SlabSource src{env->A.state, env->A.history, nullptr, env->A.n};
+  const SlabSource src{env->A.state, env->A.history, nullptr, env->A.n, nullptr};
   return encode_obs_dispatch(env, src, env->A.n, player, dtype, d_out, nullptr, nullptr, S(stream));
 }
 
@@ -667,7 +733,7 @@ int coup_vec_observer_tensor(coup_vec_env* env, int player, int public_info, int
   DeviceGuard guard(env->opts.device);
   const uint32_t vis = (private_info == 0 ? kVisPrivateNone : private_info == 2 ? kVisPrivateAll : 0u) | (public_info ? 0u : kVisNoPublic);
   const int sel = player | static_cast<int>(vis << 8);
-  const SlabSource src{env->A.state, env->A.history, nullptr, env->A.n};
+  const SlabSource src{env->A.state, env->A.history, nullptr, env->A.n, nullptr};
   if (public_info && perfect_recall)    // the info-state layout (2492), other visibility
     return encode_info_dispatch(env, src, env->A.n, sel, dtype, d_out, COUP_INFO_STATE_SIZE, nullptr, nullptr, S(stream));
   return encode_obs_dispatch(env, src, env->A.n, sel, dtype, d_out, nullptr, nullptr, S(stream));   // 98, or 42 without public info
@@ -678,7 +744,7 @@ int coup_vec_observation_tensor_gather(coup_vec_env* env, const uint32_t* d_env_
   if (!env || !d_out || !valid_player_sel(player) || !valid_dtype(dtype) || (count > 0 && !d_env_ids))
     return fail(COUP_ERR_INVALID_ARG, "coup_vec_observation_tensor_gather: bad arguments");
   DeviceGuard guard(env->opts.device);
-  const SlabSource src{env->A.state, env->A.history, d_env_ids, count};
+  const SlabSource src{env->A.state, env->A.history, d_env_ids, count, nullptr};
   return encode_obs_dispatch(env, src, count, player, dtype, d_out, nullptr, nullptr, S(stream));
 }
 

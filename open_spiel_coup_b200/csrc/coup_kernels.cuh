@@ -544,12 +544,12 @@ __global__ void k_copy_env(EnvArrays A, uint32_t src, uint32_t dst) {
 __global__ void __launch_bounds__(kBlockThreads)
 k_fork(EnvArrays D, const uint4* __restrict__ src_state, const uint32_t* __restrict__ src_history, uint32_t src_n,
        const uint32_t* __restrict__ parent, const uint8_t* __restrict__ actions, const uint8_t* __restrict__ forced,
-       uint32_t count, uint64_t step) {
+       uint32_t count, uint64_t step, const uint32_t* __restrict__ count_ptr) {
   __shared__ uint32_t s_stats[COUP_STATS_LEN];
   BlockStats st;
   st.init(s_stats);
   const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool active = e < count;
+  const bool active = e < (count_ptr ? min(count, *count_ptr) : count);   // device-side child count of a traversal level
   const uint32_t p = active ? parent[e] : 0xFFFFFFFFu;
   const bool valid = active && p < src_n;                  // out-of-range parents set the child's error bit
   uint32_t* hist_row = D.history + static_cast<size_t>(e) * kHistoryWords;
@@ -1223,7 +1223,8 @@ struct SlabSource {
   const uint32_t* history;
   const uint32_t* ids;
   uint32_t n;
-  __device__ __forceinline__ uint32_t rows() const { return n; }
+  const uint32_t* count_ptr;   // optional: only the first *count_ptr rows (a level of a traversal)
+  __device__ __forceinline__ uint32_t rows() const { return count_ptr ? min(n, *count_ptr) : n; }
   __device__ __forceinline__ void locate(uint32_t e, const uint4*& sp, const uint32_t*& hp, uint32_t& id, int& sel) const {
     id = ids ? ids[e] : e;
     sp = state + id;

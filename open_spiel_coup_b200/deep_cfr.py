@@ -228,7 +228,7 @@ class DeepCFRSolver:
     per-level bookkeeping of the last batch in `last_tree` for inspection and tests)."""
 
     def __init__(self, game=None, device=0, seed=0, max_nodes=1 << 18, roots_per_batch=None, max_tree_nodes=1 << 26,
-                 record_tree=False, fused_expand=True, **reference_args):
+                 record_tree=False, fused_expand=True, device_levels=True, **reference_args):
         self.cfg = cfg = DeepCFRConfig(**reference_args)          # the reference's keyword arguments, validated
         self._game = game
         self.device = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
@@ -237,6 +237,11 @@ class DeepCFRSolver:
         self._environment_steps = 0
         self._record_tree = record_tree
         self._fused_expand = fused_expand       # regret matching + child selection in one CUDA kernel (coup_cfr_expand)
+        # Outcome-sampling trees stay narrow: their levels are expanded by cfr_traversal.DeviceTreeTraverser, which keeps the
+        # level sizes on the device (no host read-back per level). External sampling (levels wider than a slab) and
+        # record_tree use the host-driven engine below.
+        self._device_levels = bool(device_levels) and cfg.sampling_method != "external" and not record_tree
+        self._traverser = None
         self._expand_seed, self._expand_counter = seed * 2654435761 % (1 << 63) + 17, 0
         self.last_tree = None
         policy_network_layers, advantage_network_layers = cfg.policy_network_layers, cfg.advantage_network_layers
@@ -371,11 +376,40 @@ class DeepCFRSolver:
         done, total_value, total_nodes = 0, 0.0, 0
         while done < num_traversals:
             r = min(self._roots_per_batch, num_traversals - done)
-            values, nodes = self._traverse_batch(player, r)
+            values, nodes = (self._traverse_batch_device if self._device_levels else self._traverse_batch)(player, r)
             total_value += float(values.sum())
             total_nodes += nodes
             done += r
         return total_value / max(num_traversals, 1), total_nodes
+
+    @torch.no_grad()
+    def _advantages_both(self, rows_u8, cur_player):
+        """Both networks on every row, then select: no data-dependent shapes, so nothing waits for the host."""
+        x = rows_u8.float()
+        return torch.where((cur_player == 0).view(-1, 1), self._advantage_networks[0](x), self._advantage_networks[1](x))
+
+    def _traverse_batch_device(self, player, num_roots):
+        """One batch of traversals with the level sizes kept on the device (cfr_traversal.DeviceTreeTraverser)."""
+        from .cfr_traversal import DeviceTreeTraverser
+        cfg = self.cfg
+        if self._traverser is None:
+            self._traverser = DeviceTreeTraverser(self._max_nodes, self._advantages_both, device=self.device.index or 0,
+                                                  seed=self._expand_seed % (1 << 31), sampling_method=cfg.sampling_method,
+                                                  outcome_factor=cfg.outcome_factor, e_outcome=cfg.e_outcome,
+                                                  outcome_samp_expl=cfg.outcome_samp_expl)
+        tr = self._traverser
+        chance_before = [int(s.stats_device[1]) for s in tr.slabs]
+        res = tr.traverse(player, num_roots)
+        adv, strat = tr.memory_records(res, player)
+        it = lambda k: torch.full((k,), self._iteration, device=self.device)
+        self._advantage_memories[player].add(info_state=adv["info_state"], advantage=adv["advantage"], action=adv["action"],
+                                             iteration=it(adv["action"].numel()))
+        self._strategy_memories.add(info_state=strat["info_state"], strategy_action_probs=strat["strategy_action_probs"],
+                                    iteration=it(strat["info_state"].shape[0]))
+        chance = sum(int(s.stats_device[1]) - b for s, b in zip(tr.slabs, chance_before))
+        self._environment_steps += res["nodes"] + chance
+        self.last_level_widths = res["sizes"]
+        return res["root_values"], res["nodes"]
 
     @torch.no_grad()
     def _advantages(self, rows_u8, cur_player):
