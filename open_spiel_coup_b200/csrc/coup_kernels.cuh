@@ -1783,105 +1783,50 @@ k_rollout_ws(EnvArrays A, uint64_t step, int player_sel, T* __restrict__ out, ui
 // the history rows of the moves made in this step (1 player move + <= 3 deals, or the 4 deals of a re-dealt
 // episode) and, when an episode was re-dealt in place, zeros over the rows the finished episode had used.
 // ~0.9 KB of stores per env-step instead of 2 x 9 968 B; the buffer always equals what the dense encoder would write.
-//
-// Mapping. The owner thread of an env steps it (history row held in shared memory, as in the other fused kernels) and
-// leaves an 8-word update record. Then the warp walks its touched envs; for each, the two half-warps take the two views.
-// Every store is a 16-byte unit and every span of units starts and ends on a 32-BYTE SECTOR boundary of the buffer:
-// a span that changed ([0, 62) and [62 + 18 first, 62 + 18 len), or one span from 0 to the end of the finished episode
-// after a re-deal) is widened to whole sectors, and the elements the widening touches are recomputed, not read -- the
-// tail of the previous row (always zero: history rows >= 91 are never used), the row before the first new one, row 0,
-// zeros past the last move. Partial-sector writes make the L2 fetch the sector from DRAM before it can merge
-// (ncu: 0.25 GB of DRAM reads per step for a kernel that reads 0.08 GB, and the store path backs up behind those fills);
-// rows of the reference layout are 9 968 B apart, so every second row starts in the middle of a sector. Measured on one
-// B200, 2^20 envs, f32: 0.52 ms per step with 8/16-byte stores at their natural offsets, 0.40 ms with 32-byte aligned
-// rows (stride 2496) -- see profiles/README.md for the sector-exact numbers.
-// Two earlier mappings: whole warp per (env, view) with one store per row and the dense encoder's 21-word records:
-// 0.556 ms (246 warp-instructions per env-step, the serial walk was the bound); every thread storing its own env's
-// units: 0.950 ms (32 different 32-byte sectors per store instruction).
+// Mapping. The owner thread of an env steps it and leaves an 7-word update record in shared memory (both head masks,
+// coins, the codes of the <= 4 new history rows, the range to zero after an in-place re-deal). Then the warp walks
+// its touched envs; for each, the two half-warps take the two views and write, with one store instruction each:
+// the head as 16 four-element units (the last one also carries the first two elements of history row 0), and the
+// new rows as two-element units (9 per row). Two earlier mappings, measured on one B200 at 2^20 envs, fp32:
+// whole warp per (env, view) with one store per row and the dense encoder's 21-word records: 0.556 ms (246
+// warp-instructions per env-step, the serial walk was the bound: 43 % issue, DRAM at 29 %); every thread storing its
+// own env's units: 0.950 ms (32 different 32-byte sectors per store instruction).
+template <typename T> struct Unit2;  // two consecutive tensor elements
+template <> struct Unit2<float> {
+  using type = float2;
+  static __device__ __forceinline__ type make(uint32_t a, uint32_t b) { return make_float2(static_cast<float>(a), static_cast<float>(b)); }
+};
+template <> struct Unit2<uint8_t> {
+  using type = uint16_t;
+  static __device__ __forceinline__ type make(uint32_t a, uint32_t b) { return static_cast<uint16_t>(a | (b << 8)); }
+};
+template <> struct Unit2<__nv_bfloat16> {
+  using type = uint32_t;
+  static __device__ __forceinline__ type make(uint32_t a, uint32_t b) {
+    return Unit4<__nv_bfloat16>::bits(a) | (Unit4<__nv_bfloat16>::bits(b) << 16);
+  }
+};
+
 constexpr int kIncRecWords = 8;
-constexpr int kIncRowPitch = kHistoryWords + 1;   // conflict-free per-lane rows in shared memory
-
-// 192 one-bit elements: the 0/1 content of a span of a row, bit t = element (span start + t).
-struct Bits192 {
-  unsigned long long w0, w1, w2;
-  __device__ __forceinline__ void set(int t) {                        // ignores t outside [0, 192)
-    const unsigned long long m = 1ull << (t & 63);
-    w0 |= (t >= 0 && t < 64) ? m : 0ull;
-    w1 |= (t >= 64 && t < 128) ? m : 0ull;
-    w2 |= (t >= 128 && t < 192) ? m : 0ull;
-  }
-  __device__ __forceinline__ void or64(unsigned long long v, int t) {  // v at offset t, 0 <= t < 64
-    w0 |= v << t;
-    w1 |= t ? v >> (64 - t) : 0ull;
-  }
-  __device__ __forceinline__ uint32_t get16(uint32_t o) const {        // bits o .. o+15, zeros past the end
-    const uint32_t w = o >> 6, sh = o & 63u;
-    const unsigned long long a = w == 0 ? w0 : w == 1 ? w1 : w == 2 ? w2 : 0ull;
-    const unsigned long long b = w == 0 ? w1 : w == 1 ? w2 : 0ull;
-    return static_cast<uint32_t>((a >> sh) | (sh ? b << (64u - sh) : 0ull)) & 0xFFFFu;
-  }
-};
-
-// Sixteen bytes of consecutive tensor elements: from 0/1 bits, or from small-integer values.
-template <typename T> struct Pack16;
-template <> struct Pack16<float> {
-  static constexpr int kElems = 4;
-  static __device__ __forceinline__ uint4 from_bits(uint32_t b) {
-    return make_uint4((b & 1u) * 0x3F800000u, ((b >> 1) & 1u) * 0x3F800000u, ((b >> 2) & 1u) * 0x3F800000u, ((b >> 3) & 1u) * 0x3F800000u);
-  }
-  template <typename F> static __device__ __forceinline__ uint4 make(F value) {
-    return make_uint4(__float_as_uint(static_cast<float>(value(0))), __float_as_uint(static_cast<float>(value(1))),
-                      __float_as_uint(static_cast<float>(value(2))), __float_as_uint(static_cast<float>(value(3))));
-  }
-};
-template <> struct Pack16<__nv_bfloat16> {
-  static constexpr int kElems = 8;
-  static __device__ __forceinline__ uint4 from_bits(uint32_t b) {
-    uint32_t w[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) w[k] = ((b >> (2 * k)) & 1u) * 0x3F80u + ((b >> (2 * k + 1)) & 1u) * 0x3F800000u;
-    return make_uint4(w[0], w[1], w[2], w[3]);
-  }
-  template <typename F> static __device__ __forceinline__ uint4 make(F value) {
-    uint32_t w[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) w[k] = Unit4<__nv_bfloat16>::bits(value(2 * k)) | (Unit4<__nv_bfloat16>::bits(value(2 * k + 1)) << 16);
-    return make_uint4(w[0], w[1], w[2], w[3]);
-  }
-};
-template <> struct Pack16<uint8_t> {
-  static constexpr int kElems = 16;
-  static __device__ __forceinline__ uint4 from_bits(uint32_t b) {
-    uint32_t w[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) w[k] = (((b >> (4 * k)) & 15u) * 0x00204081u) & 0x01010101u;   // four bits -> four bytes
-    return make_uint4(w[0], w[1], w[2], w[3]);
-  }
-  template <typename F> static __device__ __forceinline__ uint4 make(F value) {
-    uint32_t w[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) w[k] = value(4 * k) | (value(4 * k + 1) << 8) | (value(4 * k + 2) << 16) | (value(4 * k + 3) << 24);
-    return make_uint4(w[0], w[1], w[2], w[3]);
-  }
-};
 
 template <typename T>
 __global__ void __launch_bounds__(kBlockThreads)
 k_rollout_incremental(EnvArrays A, uint64_t step, T* __restrict__ buf, uint32_t stride) {
+  using U4 = typename Unit4<T>::type;
+  using U2 = typename Unit2<T>::type;
   __shared__ uint32_t s_stats[COUP_STATS_LEN];
   __shared__ uint32_t s_rec[kWarpsPerBlock][32][kIncRecWords];
-  __shared__ uint32_t s_row[kWarpsPerBlock][32][kIncRowPitch];
+  __shared__ uint32_t s_row[kWarpsPerBlock][32][kHistoryWords + 1];   // the env's history row, as in the other fused kernels
   BlockStats st;
   st.init(s_stats);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
   const bool active = e < A.n;
   Env s = {};
-  uint32_t* hist_row = A.history + static_cast<size_t>(e) * kHistoryWords;
-  uint32_t* row_copy = s_row[warp][lane];
-  if (active) s = load_env_and_row(A, e, row_copy);
+  uint32_t* hist_row = s_row[warp][lane];              // read, updated and read again here; written through to HBM
+  if (active) s = load_env_and_row(A, e, hist_row);
   const uint32_t old_len = c_moves(s.c);
-  const StepResult r = step_env<true>(s, HistRow{row_copy, hist_row}, 0, nullptr, A, e, step, active);
+  const StepResult r = step_env<true>(s, HistRow{hist_row, A.history + static_cast<size_t>(e) * kHistoryWords}, 0, nullptr, A, e, step, active);
   if (active) {
     store_env(A.state + e, s);
     write_outputs(A, e, r);
@@ -1890,79 +1835,53 @@ k_rollout_incremental(EnvArrays A, uint64_t step, T* __restrict__ buf, uint32_t 
       const bool redealt = r.finished && new_len < r.final_moves + 1 && (A.flags & COUP_FLAG_AUTO_RESET);
       const uint32_t first = redealt ? 0u : old_len;   // rows [first, new_len) are (re)written, at most 4
       const bool term = is_terminal(s);
-      auto code_at = [&](uint32_t i) {                  // 31 = no such row
-        const uint32_t w = min(i, 95u) / 6u;
-        return i < new_len ? (row_copy[w] >> (5u * (i - 6u * w))) & 31u : 31u;
-      };
-      // 5-bit codes of rows 0..3 (next to the head) and of rows first-2 .. first+3 (around the new rows)
-      uint32_t lead = 0, tail = 0;
-#pragma unroll
-      for (uint32_t k = 0; k < 4; ++k) lead |= code_at(k) << (5u * k);
-#pragma unroll
-      for (uint32_t k = 0; k < 6; ++k) tail |= (first + k >= 2u ? code_at(first + k - 2u) : 31u) << (5u * k);
+      uint32_t codes = (new_len ? (hist_row[0] & 31u) : 31u) << 20;
+      for (uint32_t i = first, k = 0; i < new_len; ++i, ++k) {
+        const uint32_t w = i / 6u;
+        codes |= ((hist_row[w] >> (5u * (i - 6u * w))) & 31u) << (5u * k);
+      }
       uint32_t* rec = s_rec[warp][lane];
       const uint64_t m0 = head_mask(s, 0u, term), m1 = head_mask(s, 1u, term);
       rec[0] = static_cast<uint32_t>(m0); rec[1] = static_cast<uint32_t>(m0 >> 32);
       rec[2] = static_cast<uint32_t>(m1); rec[3] = static_cast<uint32_t>(m1 >> 32);
       rec[4] = pw_coins(s.p[0]) | (pw_coins(s.p[1]) << 8) | (first << 16) | ((new_len - first) << 24);
-      rec[5] = lead;
-      rec[6] = tail;
-      // after a re-deal everything from element 0 to the end of the finished episode's rows is one span
-      rec[7] = redealt ? max(r.final_moves, new_len) : 0u;
+      rec[5] = codes;
+      // elements both views must zero: the rows the finished episode had used beyond the new episode's deals
+      rec[6] = (redealt && r.final_moves > new_len) ? (62u + 18u * new_len) | ((62u + 18u * r.final_moves) << 16) : 0u;
     }
   }
   account(st, r, active);
   uint32_t touched = __ballot_sync(0xffffffffu, active && r.stepped);
   __syncwarp();
-  constexpr uint32_t kEl = Pack16<T>::kElems;            // elements per 16-byte unit
-  constexpr uint32_t kSector = 2u * kEl;                  // elements per 32-byte sector
   const uint32_t view = static_cast<uint32_t>(lane) >> 4, l = static_cast<uint32_t>(lane) & 15u;
   const uint32_t e0 = e - lane;
   while (touched) {
     const int j = __ffs(touched) - 1;
     touched &= touched - 1;
     const uint32_t* rec = s_rec[warp][j];
-    const uint32_t mlo = rec[2 * view], mhi = rec[2 * view + 1], meta = rec[4], lead = rec[5], tail = rec[6], span_end = rec[7];
-    const uint32_t first = (meta >> 16) & 255u, n_new = meta >> 24;
-    const uint32_t coin0 = meta & 255u, coin1 = (meta >> 8) & 255u;
-    const size_t row_base = (static_cast<size_t>(e0 + j) * 2 + view) * stride;       // absolute index of element 0 of the row
-    // two spans in row elements: [0, 62) and the new rows -- or one span after a re-deal
-#pragma unroll
-    for (int sp = 0; sp < 2; ++sp) {
-      const uint32_t lo = sp == 0 ? 0u : 62u + 18u * first;
-      const uint32_t hi = sp == 0 ? (span_end ? 62u + 18u * span_end : 62u) : (span_end ? lo : lo + 18u * n_new);
-      if (hi <= lo) continue;
-      const size_t abs_lo = (row_base + lo) / kSector * kSector;                      // widened to whole sectors
-      const size_t abs_hi = (row_base + hi + kSector - 1u) / kSector * kSector;
-      const uint32_t units = static_cast<uint32_t>((abs_hi - abs_lo) / kEl);
-      const int p_start = static_cast<int>(static_cast<long long>(abs_lo) - static_cast<long long>(row_base));   // >= -31
-      // the 0/1 content of the span and of what the widening touches: the previous row's tail and everything past the
-      // last move are zeros; next to the head, rows 0..3; around the new rows, rows first-2 .. first+3
-      Bits192 bm{0ull, 0ull, 0ull};
-      if (sp == 0) {
-        bm.or64((static_cast<unsigned long long>(mhi) << 32) | mlo, -p_start);        // -p_start in [0, 31]
-#pragma unroll
-        for (uint32_t k = 0; k < 4; ++k) {
-          const uint32_t col = history_column((lead >> (5u * k)) & 31u, view);
-          if (col != 31u) bm.set(62 + 18 * static_cast<int>(k) + static_cast<int>(col) - p_start);
-        }
-      } else {
-#pragma unroll
-        for (uint32_t k = 0; k < 6; ++k) {
-          const uint32_t col = history_column((tail >> (5u * k)) & 31u, view);
-          if (col != 31u) bm.set(62 + 18 * (static_cast<int>(first + k) - 2) + static_cast<int>(col) - p_start);
-        }
-      }
-      uint4* dst = reinterpret_cast<uint4*>(buf + abs_lo);
-      for (uint32_t u = l; u < units; u += 16u) {
-        const uint32_t o = u * kEl;
-        const uint32_t bits = bm.get16(o);
-        const int p = p_start + static_cast<int>(o);            // row element of the unit's first element
-        uint4 v = Pack16<T>::from_bits(bits);
-        if (sp == 0 && p <= 61 && p + static_cast<int>(kEl) > 60)   // the unit that holds the raw coin counts (207-213)
-          v = Pack16<T>::make([&](int k) { return p + k == 60 ? coin0 : p + k == 61 ? coin1 : (bits >> k) & 1u; });
-        dst[u] = v;
-      }
+    const uint32_t mlo = rec[2 * view], mhi = rec[2 * view + 1], meta = rec[4], codes = rec[5], clr = rec[6];
+    T* row = buf + (static_cast<size_t>(e0 + j) * 2 + view) * stride;
+    // head: unit l holds elements 4l .. 4l+3; unit 15 = coins (60, 61) and the first two elements of history row 0
+    uint32_t a, b, c, d;
+    if (l < 15u) {
+      const uint32_t bits = (l < 8u ? mlo >> (4u * l) : mhi >> (4u * l - 32u)) & 15u;
+      a = bits & 1u; b = (bits >> 1) & 1u; c = (bits >> 2) & 1u; d = bits >> 3;
+    } else {
+      const uint32_t col0 = history_column((codes >> 20) & 31u, view);
+      a = meta & 255u; b = (meta >> 8) & 255u; c = col0 == 0u ? 1u : 0u; d = col0 == 1u ? 1u : 0u;
+    }
+    reinterpret_cast<U4*>(row)[l] = Unit4<T>::make(a, b, c, d);
+    // new rows: 9 two-element units each, contiguous from element 62 + 18 * first (an even offset)
+    const uint32_t first = (meta >> 16) & 255u, npairs = 9u * (meta >> 24);
+    U2* row2 = reinterpret_cast<U2*>(row);
+    for (uint32_t p = l; p < npairs; p += 16u) {
+      const uint32_t k = p / 9u, u = p - 9u * k;
+      const uint32_t col = history_column((codes >> (5u * k)) & 31u, view);
+      row2[31u + 9u * first + p] = Unit2<T>::make(col == 2u * u ? 1u : 0u, col == 2u * u + 1u ? 1u : 0u);
+    }
+    if (clr) {
+      const U2 zero = Unit2<T>::make(0u, 0u);
+      for (uint32_t q = ((clr & 0xffffu) >> 1) + l; q < (clr >> 17); q += 16u) row2[q] = zero;
     }
   }
   st.flush(A.stats);

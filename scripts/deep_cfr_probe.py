@@ -12,10 +12,10 @@ sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 from open_spiel_coup_b200.deep_cfr import DeepCFRSolver  # noqa: E402
 
 
-def run(method, factor, roots, layers, max_nodes, reps=3):
+def run(method, factor, roots, layers, max_nodes, reps=3, device_levels=True, e_outcome=0.0):
     solver = DeepCFRSolver(policy_network_layers=layers, advantage_network_layers=layers, sampling_method=method,
-                           outcome_factor=factor, memory_capacity=1 << 22, max_nodes=max_nodes, roots_per_batch=roots,
-                           seed=1, max_tree_nodes=1 << 25)
+                           outcome_factor=factor, e_outcome=e_outcome, memory_capacity=1 << 22, max_nodes=max_nodes,
+                           roots_per_batch=roots, seed=1, max_tree_nodes=1 << 25, device_levels=device_levels)
     solver.traverse(0, roots)                                  # warm-up + tree shape
     widths = solver.last_level_widths
     torch.cuda.synchronize()
@@ -26,6 +26,7 @@ def run(method, factor, roots, layers, max_nodes, reps=3):
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     print(json.dumps({"method": method, "outcome_factor": factor, "roots": roots, "levels": len(widths),
+                      "engine": "device-side level sizes (cfr_traversal)" if solver._device_levels else "host-driven levels",
                       "widest_level": max(widths), "nodes_per_traversal_batch": sum(widths),
                       "nodes_per_root": sum(widths) / roots, "seconds_per_batch": dt / reps,
                       "nodes_per_s": nodes / dt, "traversals_per_s": roots * reps / dt,
@@ -40,9 +41,16 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--layers", default="128,128")
     ap.add_argument("--external-roots", type=int, default=0, help="also time full-width external-sampling traversals of this many deals")
+    ap.add_argument("--thesis-batch", action="store_true",
+                    help="the thesis configuration (deep_cfr-final4.cfg): 1500 roots, e-outcome, outcome_factor 2, e 0.2, "
+                         "advantage networks 512-512, with both engines")
     args = ap.parse_args()
     layers = tuple(int(x) for x in args.layers.split(","))
-    if args.external_roots:
+    if args.thesis_batch:
+        for dl in (False, True):
+            run("e-outcome", 2, 1500, (512, 512), 1 << 15, reps=5, device_levels=dl, e_outcome=0.2)
+            run("outcome", 1, 1500, (512, 512), 1 << 15, reps=5, device_levels=dl)
+    elif args.external_roots:
         run("external", 1, args.external_roots, layers, 1 << 21, reps=1)
     else:
         run("outcome", 1, 1 << 14, layers, 1 << 18)
