@@ -399,12 +399,17 @@ def main():
     torch.cuda.synchronize()
 
     def e2e_steps(k):
+        # One host thread drives all sub-slabs: a sub-slab's step is queued without waiting (step_host_packed_async), and
+        # its step words are awaited only when its next actions are about to be chosen, one round later.
         for _ in range(k):
             for ev, h_act, h_words, t_out, stream, offset in slabs:
+                ev.host_outputs_wait()
                 rc = lib.coup_host_sample_uniform(C.c_void_p(h_words.data_ptr()), ns, args.seed, offset,
                                                   ev.step_counter, C.c_void_p(h_act.data_ptr()), threads)
                 assert rc == 0
-                ev.step_host_packed(h_act, h_words, tensor_out=t_out, stream=stream)
+                ev.step_host_packed_async(h_act, h_words, tensor_out=t_out, stream=stream)
+        for sl in slabs:
+            sl[0].host_outputs_wait()
 
     Ke = max(3, min(K, 200))
     e2e_steps(3)

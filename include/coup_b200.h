@@ -391,6 +391,14 @@ int coup_vec_step_host(coup_vec_env* env, const uint8_t* h_actions, uint32_t* h_
 int coup_vec_step_host_packed(coup_vec_env* env, const uint8_t* h_actions, uint32_t* h_step_words, int dtype,
                               void* d_tensor_out, void* stream);
 
+/* The same call in two halves, for callers that drive several handles (sub-slabs, one stream each) from one host thread:
+ * _async queues the copies, the step and the encoder and returns at once; coup_vec_host_outputs_wait blocks until the
+ * h_step_words of the handle's LAST _async call are filled. Waiting for a sub-slab only right before its next actions are
+ * chosen keeps the host off the device's critical path (bench.py's e2e leg). The host buffers must stay valid until then. */
+int coup_vec_step_host_packed_async(coup_vec_env* env, const uint8_t* h_actions, uint32_t* h_step_words, int dtype,
+                                    void* d_tensor_out, void* stream);
+int coup_vec_host_outputs_wait(coup_vec_env* env);
+
 /* Host-side uniform-random POLICY for callers that keep their policy on the host (the host analogue of
  * benchmark_game.cc:96-99): for every env picks the k-th set bit of h_legal_mask[i], k drawn from the same
  * Philox stream coup_vec_sample_uniform would use at step counter `step`; 0xFF where the mask is 0.

@@ -49,7 +49,7 @@ EXPORTED_SYMBOLS = [
     "coup_vec_finished_ring_enable", "coup_vec_finished_ring", "coup_vec_finished_ring_ctrl", "coup_vec_finished_ring_capacity",
     "coup_vec_finished_drain", "coup_vec_finished_information_state_tensor", "coup_records_information_state_tensor",
     "coup_vec_finished_observation_tensor", "coup_records_observation_tensor", "coup_vec_observation_tensor_gather",
-    "coup_vec_step_record", "coup_vec_observer_tensor", "coup_vec_information_state_tensor_prefix", "coup_cfr_level",
+    "coup_vec_step_record", "coup_vec_observer_tensor", "coup_vec_step_host_packed_async", "coup_vec_host_outputs_wait", "coup_vec_information_state_tensor_prefix", "coup_cfr_level",
     "coup_vec_fork_counted", "coup_vec_pack_records", "coup_cfr_backward",
     "coup_tensor_row_hash", "coup_vec_snapshot_size", "coup_vec_snapshot", "coup_vec_restore", "coup_vec_step_counter", "coup_vec_set_step_counter",
 ]
@@ -149,6 +149,8 @@ def load():
     lib.coup_vec_observation_tensor.argtypes = [vp, C.c_int, C.c_int, vp, vp]
     lib.coup_vec_step_host.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int, vp, vp]
     lib.coup_vec_step_host_packed.argtypes = [vp, vp, vp, C.c_int, vp, vp]
+    lib.coup_vec_step_host_packed_async.argtypes = [vp, vp, vp, C.c_int, vp, vp]
+    lib.coup_vec_host_outputs_wait.argtypes = [vp]
     lib.coup_host_sample_uniform.argtypes = [vp, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64, vp, C.c_int]
     lib.coup_vec_stats.argtypes = [vp, vp, vp]
     lib.coup_vec_clear_stats.argtypes = [vp, vp]

@@ -14,7 +14,10 @@ memory: every kernel is launched for the capacity of the level buffers and works
   afterwards  coup_cfr_backward, one launch per level    values and sampled regrets
               one host read of the level sizes; memory records are decoded from the packed records of the levels
 
-The host looks at the device only every `check_every` levels ("is the frontier empty?") and once at the end.
+The host never waits for the level it has just queued: the size of level l is copied to pinned memory as soon as it
+exists and is looked at one level later, when it has long arrived. It bounds the next level (a node has at most
+`outcome_factor` children, or 7 with external sampling), which is all the host needs to size the network's GEMMs, and an
+empty level ends the walk.
 """
 import ctypes as C
 
@@ -31,24 +34,29 @@ class DeviceTreeTraverser:
     advantage-network outputs of the player to move. A level may hold at most `capacity` nodes; a wider level raises."""
 
     def __init__(self, capacity, advantages, device=0, seed=0, sampling_method="outcome", outcome_factor=1, e_outcome=0.0,
-                 outcome_samp_expl=0.6, max_levels=96, check_every=8):
+                 outcome_samp_expl=0.6, max_levels=96):
         if sampling_method not in ("external", "outcome", "e-outcome"):
             raise ValueError(f"Unknown sampling method '{sampling_method}'.")
         self.capacity, self.advantages = int(capacity), advantages
         self.method, self.factor, self.e_outcome, self.expl = sampling_method, int(outcome_factor), float(e_outcome), float(outcome_samp_expl)
-        self.max_levels, self.check_every = int(max_levels), int(check_every)
+        self.max_levels = int(max_levels)
         self.slabs = [CoupVectorEnv(self.capacity, seed=seed + 101 + i, device=device, auto_reset=False) for i in range(2)]
         self.device = self.slabs[0].device
         self._lib = self.slabs[0]._lib
         self._seed, self._counter = seed * 2654435761 % (1 << 63) + 17, 0
         w, dev = self.capacity, self.device
         self.counts = torch.zeros(self.max_levels + 2, dtype=torch.int32, device=dev)
+        self.counts_host = torch.zeros(self.max_levels + 2, dtype=torch.int32).pin_memory()
+        self._count_ready = [torch.cuda.Event() for _ in range(self.max_levels + 2)]
+        # children per node: outcome_factor at the traverser's nodes (7 = every legal action with external sampling), 1 at the opponent's
+        self._growth = 7 if sampling_method == "external" else max(1, int(outcome_factor))
         self.overflow = torch.zeros(1, dtype=torch.int32, device=dev)
         self.parent = torch.empty(w, dtype=torch.int32, device=dev)
         self.action = torch.empty(w, dtype=torch.uint8, device=dev)
         self.rows = torch.empty((w, INFO_STATE_SIZE), dtype=torch.uint8, device=dev)
+        self._adv = torch.zeros((w, NUM_DISTINCT_ACTIONS), dtype=torch.float32, device=dev)
         self._levels = []          # per-level buffers, allocated on first use and kept
-        self.launches_per_level = 6   # ours; the networks' GEMMs are PyTorch's
+        self.launches_per_level = 6   # ours (pack, copy, encode, level, count copy, fork); the networks' GEMMs are PyTorch's
 
     def _level(self, l):
         while len(self._levels) <= l:
@@ -84,24 +92,38 @@ class DeviceTreeTraverser:
         self.overflow.zero_()
         e_outcome = self.e_outcome if self.method == "e-outcome" else -1.0
         depth = 0
+        bound = num_roots                      # upper bound of the size of the level about to be expanded
+        self.counts_host[0] = num_roots
         for l in range(self.max_levels):
+            if l >= 2:                         # the size of level l - 1 was queued for copy a whole level ago
+                self._count_ready[l - 1].synchronize()
+                prev = int(self.counts_host[l - 1])
+                if prev == 0:
+                    break                      # level l - 1 was already empty: nothing to expand
+                bound = min(w, prev * self._growth)
+            elif l == 1:
+                bound = min(w, num_roots * self._growth)
+            rows_now = min(w, -(-bound // 8) * 8)
             lvl, cnt = self._level(l), self.counts[l:l + 1]
             check(lib.coup_vec_pack_records(cur._h, ptr(cnt), ptr(lvl["records"]), stream))
             lvl["words"].copy_(cur.step_word)
-            check(lib.coup_vec_information_state_tensor_prefix(cur._h, ptr(cnt), w, PLAYER_CURRENT, _lib.DTYPE_U8, ptr(self.rows),
+            check(lib.coup_vec_information_state_tensor_prefix(cur._h, ptr(cnt), rows_now, PLAYER_CURRENT, _lib.DTYPE_U8, ptr(self.rows),
                                                                 INFO_STATE_SIZE, stream))
-            adv = self.advantages(self.rows, (lvl["words"] >> 18) & 1).contiguous()
+            adv = self._adv
+            adv[:rows_now] = self.advantages(self.rows[:rows_now], (lvl["words"][:rows_now] >> 18) & 1)
             check(lib.coup_cfr_level(ptr(adv), ptr(lvl["words"]), ptr(cnt), w, player, int(self.method == "external"), self.factor,
                                      e_outcome, self.expl, self._seed, self._counter, ptr(lvl["strategy"]), ptr(lvl["expand"]),
                                      ptr(lvl["offset"]), ptr(self.parent), ptr(self.action), ptr(self.counts[l + 1:l + 2]),
                                      ptr(self.overflow), stream))
             self._counter += 1
-            check(lib.coup_vec_fork_counted(nxt._h, cur._h, ptr(self.parent), ptr(self.action), ptr(self.counts[l + 1:l + 2]), w, stream))
+            self.counts_host[l + 1:l + 2].copy_(self.counts[l + 1:l + 2], non_blocking=True)
+            self._count_ready[l + 1].record()
+            check(lib.coup_vec_fork_counted(nxt._h, cur._h, ptr(self.parent), ptr(self.action), ptr(self.counts[l + 1:l + 2]),
+                                            min(w, bound * self._growth), stream))
             cur, nxt = nxt, cur
             depth = l + 1
-            if depth % self.check_every == 0 and int(self.counts[depth]) == 0:      # the only look at the device in the loop
-                break
         else:
+            torch.cuda.synchronize(dev)
             if int(self.counts[self.max_levels]) != 0:
                 raise RuntimeError("traversal deeper than max_levels")
         # ---- backward sweep (:468-480): values of level l from the values of level l + 1 ----

@@ -790,8 +790,8 @@ int coup_vec_step_host(coup_vec_env* env, const uint8_t* h_actions, uint32_t* h_
   return COUP_OK;
 }
 
-int coup_vec_step_host_packed(coup_vec_env* env, const uint8_t* h_actions, uint32_t* h_step_words, int dtype,
-                              void* d_tensor_out, void* stream) {
+int coup_vec_step_host_packed_async(coup_vec_env* env, const uint8_t* h_actions, uint32_t* h_step_words, int dtype,
+                                    void* d_tensor_out, void* stream) {
   if (!env || !h_actions || !h_step_words) return fail(COUP_ERR_INVALID_ARG, "coup_vec_step_host_packed: null argument");
   DeviceGuard guard(env->opts.device);
   cudaStream_t st = S(stream);
@@ -805,8 +805,20 @@ int coup_vec_step_host_packed(coup_vec_env* env, const uint8_t* h_actions, uint3
     rc = coup_vec_information_state_tensor(env, COUP_PLAYER_CURRENT, dtype, d_tensor_out, stream);
     if (rc != COUP_OK) return rc;
   }
+  return COUP_OK;
+}
+
+int coup_vec_host_outputs_wait(coup_vec_env* env) {
+  if (!env) return fail(COUP_ERR_INVALID_ARG, "null handle");
+  DeviceGuard guard(env->opts.device);
   CUDA_TRY(cudaEventSynchronize(env->host_outputs_ready));
   return COUP_OK;
+}
+
+int coup_vec_step_host_packed(coup_vec_env* env, const uint8_t* h_actions, uint32_t* h_step_words, int dtype,
+                              void* d_tensor_out, void* stream) {
+  const int rc = coup_vec_step_host_packed_async(env, h_actions, h_step_words, dtype, d_tensor_out, stream);
+  return rc != COUP_OK ? rc : coup_vec_host_outputs_wait(env);
 }
 
 int coup_host_sample_uniform(const uint32_t* h_legal_mask, uint32_t n, uint64_t seed, uint64_t global_env_offset,

@@ -199,6 +199,16 @@ class CoupVectorEnv:
         check(self._lib.coup_vec_step_host_packed(self._h, C.c_void_p(h_actions.data_ptr()),
                                                   C.c_void_p(h_step_words.data_ptr()), dt, self._ptr(tensor_out), sp))
 
+    def step_host_packed_async(self, h_actions, h_step_words, tensor_out=None, stream=None):
+        """`step_host_packed` without the final wait; `host_outputs_wait()` blocks until `h_step_words` is filled."""
+        dt = _TORCH_TO_DTYPE[tensor_out.dtype] if tensor_out is not None else 0
+        sp = _stream_ptr(self.device) if stream is None else C.c_void_p(stream.cuda_stream)
+        check(self._lib.coup_vec_step_host_packed_async(self._h, C.c_void_p(h_actions.data_ptr()),
+                                                        C.c_void_p(h_step_words.data_ptr()), dt, self._ptr(tensor_out), sp))
+
+    def host_outputs_wait(self):
+        check(self._lib.coup_vec_host_outputs_wait(self._h))
+
     # ---- observations ---------------------------------------------------------------------------
     def information_state_tensor(self, player=PLAYER_CURRENT, out=None, dtype=torch.float32):
         """CoupState::InformationStateTensor (coup.cc:1044-1049) for every env; [rows, 2492]."""

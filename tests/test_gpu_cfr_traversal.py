@@ -49,7 +49,7 @@ def _as_recorded_tree(result, player, traverser):
     return tree
 
 
-@pytest.mark.parametrize("method,factor,roots", [("outcome", 1, 200), ("outcome", 2, 16), ("e-outcome", 2, 64), ("e-outcome", 3, 16)])
+@pytest.mark.parametrize("method,factor,roots", [("outcome", 1, 200), ("outcome", 2, 3), ("e-outcome", 2, 64), ("e-outcome", 3, 16)])
 def test_device_traversal_matches_recursion_on_oracle(oracle, method, factor, roots):
     torch.manual_seed(3)
     nets = [MLP(2492, [32], 18).cuda() for _ in range(2)]
@@ -58,10 +58,10 @@ def test_device_traversal_matches_recursion_on_oracle(oracle, method, factor, ro
         x = rows.float()
         return torch.where((cur == 0).view(-1, 1), nets[0](x), nets[1](x))
 
-    tr = DeviceTreeTraverser(1 << 14, advantages, seed=11, sampling_method=method, outcome_factor=factor, e_outcome=0.25)
+    tr = DeviceTreeTraverser(1 << 16, advantages, seed=11, sampling_method=method, outcome_factor=factor, e_outcome=0.25)
     rng = np.random.default_rng(0)
     done = 0
-    for attempt in range(10):
+    for attempt in range(20):
         player = attempt & 1
         try:
             res = tr.traverse(player, roots)
