@@ -60,11 +60,23 @@ def test_device_traversal_matches_recursion_on_oracle(oracle, method, factor, ro
 
     tr = DeviceTreeTraverser(1 << 16, advantages, seed=11, sampling_method=method, outcome_factor=factor, e_outcome=0.25)
     rng = np.random.default_rng(0)
+    start = None
+    if method == "outcome" and factor > 1:
+        # two children at EVERY traverser node: 2^(traverser decisions) leaves per root, so these trees are grown from
+        # positions late in random games (as the external-sampling test of the host-driven engine does)
+        from open_spiel_coup_b200.vector_env import CoupVectorEnv
+        late = CoupVectorEnv(256, seed=21)
+        late.rollout(22)
+        alive = (late.done == 0).nonzero(as_tuple=True)[0]
+        assert alive.numel() >= 10 * roots
     done = 0
     for attempt in range(20):
         player = attempt & 1
+        if method == "outcome" and factor > 1:
+            pick = alive[attempt * roots:(attempt + 1) * roots]
+            start = late.state[pick].clone(), late.history[pick].clone(), late.step_word[pick].clone()
         try:
-            res = tr.traverse(player, roots)
+            res = tr.traverse(player, roots, roots=start)
         except RuntimeError as err:               # a multi-outcome tree of a long game can outgrow the capacity: draw again
             assert "capacity" in str(err) and factor > 1
             continue
