@@ -592,7 +592,8 @@ int coup_vec_rollout(coup_vec_env* env, int n_steps, int encode_player, int dtyp
 int coup_vec_rollout_incremental(coup_vec_env* env, int n_steps, int dtype, void* d_buf, uint32_t row_stride, void* stream) {
   if (!env || n_steps < 0 || !d_buf || !valid_dtype(dtype) || !valid_stride(row_stride))
     return fail(COUP_ERR_INVALID_ARG, "coup_vec_rollout_incremental: bad arguments");
-  if (!aligned_for(dtype, d_buf)) return fail(COUP_ERR_INVALID_ARG, kMisaligned);
+  if (reinterpret_cast<uintptr_t>(d_buf) % 32u != 0)   // the kernel writes whole 32-byte sectors
+    return fail(COUP_ERR_INVALID_ARG, "coup_vec_rollout_incremental: the buffer must be 32-byte aligned");
   DeviceGuard guard(env->opts.device);
   switch (dtype) {
     case COUP_DTYPE_F32: return rollout_incremental_typed<float>(env, n_steps, d_buf, row_stride, S(stream));

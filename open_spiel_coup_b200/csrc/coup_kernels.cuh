@@ -1501,15 +1501,33 @@ k_encode_obs(Src src, int player_sel, T* __restrict__ out, int use_bulk, uint32_
   for (uint32_t q = lane; q < span_elems * sizeof(T) / 16u; q += 32u) reinterpret_cast<uint4*>(stage)[q] = make_uint4(0u, 0u, 0u, 0u);
   __syncwarp();
   const uint32_t n_groups = (n + 31u) / 32u;
-  for (uint32_t g = blockIdx.x * kObsWarps + warp; g < n_groups; g += gridDim.x * kObsWarps) {
+  // The state word of the NEXT group is requested before this group's bulk store is waited for, so the load's round trip
+  // (microseconds next to a saturated store stream) overlaps the engine's read of the buffer and the erase.
+  auto fetch = [&](uint32_t g, uint4& sv, uint32_t& id, int& sel) {
+    const uint32_t e = g * 32u + lane;
+    sel = player_sel;
+    if (g < n_groups && e < n) {
+      const uint4* sp; const uint32_t* hp;
+      src.locate(e, sp, hp, id, sel);
+      sv = *sp;
+    }
+  };
+  uint4 sv_next = make_uint4(0u, 0u, 0u, 0u);
+  uint32_t id_next = 0;
+  int sel_next = player_sel;
+  const uint32_t g_first = blockIdx.x * kObsWarps + warp, g_step = gridDim.x * kObsWarps;
+  fetch(g_first, sv_next, id_next, sel_next);
+  for (uint32_t g = g_first; g < n_groups; g += g_step) {
     const uint32_t e0 = g * 32u, e = e0 + lane;
     const uint32_t nrec = min(32u, n - e0);
+    const uint4 sv = sv_next;
+    const uint32_t id = id_next;
+    const int sel = sel_next;
     uint64_t head_a = 0, head_b = 0, la = 0;
     uint32_t coins = 0;
     if (e < n) {
-      const uint4* sp; const uint32_t* hp; uint32_t id; int sel = player_sel;
-      src.locate(e, sp, hp, id, sel);
-      const Env s = load_env(sp);
+      Env s;
+      s.p[0] = sv.x; s.p[1] = sv.y; s.g = sv.z; s.c = sv.w;
       const bool term = is_terminal(s);
       const int who = sel & 7;
       const uint32_t obs_a = who == COUP_PLAYER_1 ? 1u : who == COUP_PLAYER_CURRENT ? g_mover(s.g) : 0u;
@@ -1523,20 +1541,19 @@ k_encode_obs(Src src, int player_sel, T* __restrict__ out, int use_bulk, uint32_
       if (both) poke_obs_row<T>(row + row_len, head_b, la, coins, true, pub);
     }
     T* dst = out + static_cast<size_t>(e0) * views * row_len;
-    if (use_bulk && nrec == 32u) {
+    const bool bulk = use_bulk && nrec == 32u;
+    if (bulk) {
       tma_store_fence();
       __syncwarp();
-      if (lane == 0) {
-        tma_bulk_store(dst, stage, span_elems * static_cast<uint32_t>(sizeof(T)));
-        tma_wait_read_all();
-      }
-      __syncwarp();
+      if (lane == 0) tma_bulk_store(dst, stage, span_elems * static_cast<uint32_t>(sizeof(T)));
     } else {
       __syncwarp();
       const uint32_t total = nrec * views * row_len;
       for (uint32_t i = lane; i < total; i += 32u) dst[i] = stage[i];
-      __syncwarp();
     }
+    fetch(g + g_step, sv_next, id_next, sel_next);
+    if (bulk && lane == 0) tma_wait_read_all();
+    __syncwarp();
     if (e < n) {
       T* row = stage + static_cast<size_t>(lane) * views * row_len;
       poke_obs_row<T>(row, head_a, la, coins, false, pub);
@@ -1783,50 +1800,95 @@ k_rollout_ws(EnvArrays A, uint64_t step, int player_sel, T* __restrict__ out, ui
 // the history rows of the moves made in this step (1 player move + <= 3 deals, or the 4 deals of a re-dealt
 // episode) and, when an episode was re-dealt in place, zeros over the rows the finished episode had used.
 // ~0.9 KB of stores per env-step instead of 2 x 9 968 B; the buffer always equals what the dense encoder would write.
-// Mapping. The owner thread of an env steps it and leaves an 7-word update record in shared memory (both head masks,
-// coins, the codes of the <= 4 new history rows, the range to zero after an in-place re-deal). Then the warp walks
-// its touched envs; for each, the two half-warps take the two views and write, with one store instruction each:
-// the head as 16 four-element units (the last one also carries the first two elements of history row 0), and the
-// new rows as two-element units (9 per row). Two earlier mappings, measured on one B200 at 2^20 envs, fp32:
-// whole warp per (env, view) with one store per row and the dense encoder's 21-word records: 0.556 ms (246
-// warp-instructions per env-step, the serial walk was the bound: 43 % issue, DRAM at 29 %); every thread storing its
-// own env's units: 0.950 ms (32 different 32-byte sectors per store instruction).
-template <typename T> struct Unit2;  // two consecutive tensor elements
-template <> struct Unit2<float> {
-  using type = float2;
-  static __device__ __forceinline__ type make(uint32_t a, uint32_t b) { return make_float2(static_cast<float>(a), static_cast<float>(b)); }
+//
+// Every store is a 16-byte unit and every run of units starts and ends on a 32-BYTE SECTOR boundary of the buffer. A
+// store that covers part of a sector makes the L2 fetch the rest from DRAM before it can merge, and the store path backs up
+// behind those fills: with 8/16-byte stores at their natural offsets ncu shows 0.25 GB of DRAM reads per step for a kernel
+// that reads 0.08 GB, 9.6 long-scoreboard stall cycles per issued instruction and 30 % issue activity (0.52 ms per step,
+// 2^20 envs, f32). Rows of the reference layout are 9 968 B apart, so every second row even starts in the middle of a
+// sector. So a span that changed -- [0, 62) and [62 + 18 first, 62 + 18 len), or one span from 0 to the end of the finished
+// episode after a re-deal -- is widened to whole sectors, and what the widening touches is recomputed, not read: the tail
+// of the previous row (always zero: history rows >= 91 are never used), rows 0..3 next to the head, the two rows before
+// the first new one, zeros past the last move.
+//
+// Mapping. The owner lane of an env steps it (history row in shared memory, as in the other fused kernels) and leaves, per
+// view, the two spans as BITMAPS of their 0/1 content (192 bits each, bit t = element span_start + t) plus where they start
+// and how many units they have. Then the warp walks its touched envs; for each, the two half-warps take the two views and
+// every lane turns 4 / 8 / 16 bits of a bitmap into one 16-byte unit (the unit holding the raw coin counts is patched).
+// Earlier mappings, measured on one B200 at 2^20 envs, fp32: natural-offset 8/16-byte stores 0.52 ms; whole-sector stores
+// with the content recomputed per element inside the walk 0.75-1.06 ms (3.5x the instructions, no fills any more); whole
+// warp per (env, view) with one store per row 0.556 ms; every thread storing its own env's units 0.950 ms.
+constexpr int kIncViewWords = 14;                      // per view: 2 span headers + 6 + 6 bitmap words
+constexpr int kIncRecWords = 1 + 2 * kIncViewWords;    // + the coin word; 29: an odd pitch, conflict-free per-lane access
+constexpr int kIncRowPitch = kHistoryWords + 1;
+
+// Sixteen bytes of consecutive tensor elements: from 0/1 bits, or from small-integer values.
+template <typename T> struct Pack16;
+template <> struct Pack16<float> {
+  static constexpr int kElems = 4;
+  static __device__ __forceinline__ uint4 from_bits(uint32_t b) {
+    return make_uint4((b & 1u) * 0x3F800000u, ((b >> 1) & 1u) * 0x3F800000u, ((b >> 2) & 1u) * 0x3F800000u, ((b >> 3) & 1u) * 0x3F800000u);
+  }
+  template <typename F> static __device__ __forceinline__ uint4 make(F value) {
+    return make_uint4(__float_as_uint(static_cast<float>(value(0))), __float_as_uint(static_cast<float>(value(1))),
+                      __float_as_uint(static_cast<float>(value(2))), __float_as_uint(static_cast<float>(value(3))));
+  }
 };
-template <> struct Unit2<uint8_t> {
-  using type = uint16_t;
-  static __device__ __forceinline__ type make(uint32_t a, uint32_t b) { return static_cast<uint16_t>(a | (b << 8)); }
+template <> struct Pack16<__nv_bfloat16> {
+  static constexpr int kElems = 8;
+  static __device__ __forceinline__ uint4 from_bits(uint32_t b) {
+    uint32_t w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) w[k] = ((b >> (2 * k)) & 1u) * 0x3F80u + ((b >> (2 * k + 1)) & 1u) * 0x3F800000u;
+    return make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  template <typename F> static __device__ __forceinline__ uint4 make(F value) {
+    uint32_t w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) w[k] = Unit4<__nv_bfloat16>::bits(value(2 * k)) | (Unit4<__nv_bfloat16>::bits(value(2 * k + 1)) << 16);
+    return make_uint4(w[0], w[1], w[2], w[3]);
+  }
 };
-template <> struct Unit2<__nv_bfloat16> {
-  using type = uint32_t;
-  static __device__ __forceinline__ type make(uint32_t a, uint32_t b) {
-    return Unit4<__nv_bfloat16>::bits(a) | (Unit4<__nv_bfloat16>::bits(b) << 16);
+template <> struct Pack16<uint8_t> {
+  static constexpr int kElems = 16;
+  static __device__ __forceinline__ uint4 from_bits(uint32_t b) {
+    uint32_t w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) w[k] = (((b >> (4 * k)) & 15u) * 0x00204081u) & 0x01010101u;   // four bits -> four bytes
+    return make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  template <typename F> static __device__ __forceinline__ uint4 make(F value) {
+    uint32_t w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) w[k] = value(4 * k) | (value(4 * k + 1) << 8) | (value(4 * k + 2) << 16) | (value(4 * k + 3) << 24);
+    return make_uint4(w[0], w[1], w[2], w[3]);
   }
 };
 
-constexpr int kIncRecWords = 8;
+// Sets bit t of a 192-bit bitmap kept as six words in shared memory; t outside [0, 192) is ignored.
+__device__ __forceinline__ void bitmap_set(uint32_t* words, int t) {
+  if (t >= 0 && t < 192) words[t >> 5] |= 1u << (t & 31);
+}
 
 template <typename T>
 __global__ void __launch_bounds__(kBlockThreads)
 k_rollout_incremental(EnvArrays A, uint64_t step, T* __restrict__ buf, uint32_t stride) {
-  using U4 = typename Unit4<T>::type;
-  using U2 = typename Unit2<T>::type;
   __shared__ uint32_t s_stats[COUP_STATS_LEN];
   __shared__ uint32_t s_rec[kWarpsPerBlock][32][kIncRecWords];
-  __shared__ uint32_t s_row[kWarpsPerBlock][32][kHistoryWords + 1];   // the env's history row, as in the other fused kernels
+  __shared__ uint32_t s_row[kWarpsPerBlock][32][kIncRowPitch];
+  constexpr uint32_t kEl = Pack16<T>::kElems;            // elements per 16-byte unit
+  constexpr uint32_t kSector = 2u * kEl;                  // elements per 32-byte sector
   BlockStats st;
   st.init(s_stats);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
   const bool active = e < A.n;
   Env s = {};
-  uint32_t* hist_row = s_row[warp][lane];              // read, updated and read again here; written through to HBM
-  if (active) s = load_env_and_row(A, e, hist_row);
+  uint32_t* hist_row = A.history + static_cast<size_t>(e) * kHistoryWords;
+  uint32_t* row_copy = s_row[warp][lane];
+  if (active) s = load_env_and_row(A, e, row_copy);
   const uint32_t old_len = c_moves(s.c);
-  const StepResult r = step_env<true>(s, HistRow{hist_row, A.history + static_cast<size_t>(e) * kHistoryWords}, 0, nullptr, A, e, step, active);
+  const StepResult r = step_env<true>(s, HistRow{row_copy, hist_row}, 0, nullptr, A, e, step, active);
   if (active) {
     store_env(A.state + e, s);
     write_outputs(A, e, r);
@@ -1835,19 +1897,47 @@ k_rollout_incremental(EnvArrays A, uint64_t step, T* __restrict__ buf, uint32_t 
       const bool redealt = r.finished && new_len < r.final_moves + 1 && (A.flags & COUP_FLAG_AUTO_RESET);
       const uint32_t first = redealt ? 0u : old_len;   // rows [first, new_len) are (re)written, at most 4
       const bool term = is_terminal(s);
-      uint32_t codes = (new_len ? (hist_row[0] & 31u) : 31u) << 20;
-      for (uint32_t i = first, k = 0; i < new_len; ++i, ++k) {
-        const uint32_t w = i / 6u;
-        codes |= ((hist_row[w] >> (5u * (i - 6u * w))) & 31u) << (5u * k);
-      }
+      auto code_at = [&](uint32_t i) {                  // 31 = no such row
+        const uint32_t w = min(i, 95u) / 6u;
+        return i < new_len ? (row_copy[w] >> (5u * (i - 6u * w))) & 31u : 31u;
+      };
       uint32_t* rec = s_rec[warp][lane];
-      const uint64_t m0 = head_mask(s, 0u, term), m1 = head_mask(s, 1u, term);
-      rec[0] = static_cast<uint32_t>(m0); rec[1] = static_cast<uint32_t>(m0 >> 32);
-      rec[2] = static_cast<uint32_t>(m1); rec[3] = static_cast<uint32_t>(m1 >> 32);
-      rec[4] = pw_coins(s.p[0]) | (pw_coins(s.p[1]) << 8) | (first << 16) | ((new_len - first) << 24);
-      rec[5] = codes;
-      // elements both views must zero: the rows the finished episode had used beyond the new episode's deals
-      rec[6] = (redealt && r.final_moves > new_len) ? (62u + 18u * new_len) | ((62u + 18u * r.final_moves) << 16) : 0u;
+      rec[0] = pw_coins(s.p[0]) | (pw_coins(s.p[1]) << 8);
+      // span 0: the head -- or, after a re-deal, everything from element 0 to the end of the finished episode's rows;
+      // span 1: the new rows (none after a re-deal: they are part of span 0)
+      const uint32_t hi0 = redealt ? 62u + 18u * max(r.final_moves, new_len) : 62u;
+      const uint32_t lo1 = 62u + 18u * first, hi1 = redealt ? lo1 : lo1 + 18u * (new_len - first);
+#pragma unroll
+      for (uint32_t view = 0; view < 2; ++view) {
+        uint32_t* vr = rec + 1 + view * kIncViewWords;
+        const size_t row_base = (static_cast<size_t>(e) * 2 + view) * stride;         // absolute index of element 0 of the row
+        const size_t a0 = row_base / kSector * kSector, b0 = (row_base + hi0 + kSector - 1u) / kSector * kSector;
+        const int back0 = static_cast<int>(row_base - a0);                             // span 0 starts `back0` elements early
+        vr[0] = static_cast<uint32_t>(back0) | (static_cast<uint32_t>((b0 - a0) / kEl) << 8);
+        const size_t a1 = (row_base + lo1) / kSector * kSector, b1 = (row_base + hi1 + kSector - 1u) / kSector * kSector;
+        const int start1 = static_cast<int>(a1 - row_base);                            // row element where span 1 starts
+        vr[1] = static_cast<uint32_t>(start1) | ((hi1 > lo1 ? static_cast<uint32_t>((b1 - a1) / kEl) : 0u) << 16);
+        // bitmaps: bit t = element (span start + t)
+        uint32_t* bm0 = vr + 2;
+        uint32_t* bm1 = vr + 8;
+        const uint64_t head = head_mask(s, view, term);
+        const unsigned long long lo = head << back0, hi = back0 ? head >> (64 - back0) : 0ull;   // back0 <= 31
+        bm0[0] = static_cast<uint32_t>(lo); bm0[1] = static_cast<uint32_t>(lo >> 32); bm0[2] = static_cast<uint32_t>(hi);
+        bm0[3] = bm0[4] = bm0[5] = 0u;
+#pragma unroll
+        for (uint32_t k = 0; k < 4; ++k) {                                             // rows 0..3, next to the head
+          const uint32_t col = history_column(code_at(k), view);
+          if (col != 31u) bitmap_set(bm0, 62 + 18 * static_cast<int>(k) + static_cast<int>(col) + back0);
+        }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) bm1[k] = 0u;
+#pragma unroll
+        for (uint32_t k = 0; k < 6; ++k) {                                             // rows first-2 .. first+3, around the new rows
+          const uint32_t i = first + k;
+          const uint32_t col = i >= 2u ? history_column(code_at(i - 2u), view) : 31u;
+          if (col != 31u) bitmap_set(bm1, 62 + 18 * (static_cast<int>(i) - 2) + static_cast<int>(col) - start1);
+        }
+      }
     }
   }
   account(st, r, active);
@@ -1859,29 +1949,26 @@ k_rollout_incremental(EnvArrays A, uint64_t step, T* __restrict__ buf, uint32_t 
     const int j = __ffs(touched) - 1;
     touched &= touched - 1;
     const uint32_t* rec = s_rec[warp][j];
-    const uint32_t mlo = rec[2 * view], mhi = rec[2 * view + 1], meta = rec[4], codes = rec[5], clr = rec[6];
-    T* row = buf + (static_cast<size_t>(e0 + j) * 2 + view) * stride;
-    // head: unit l holds elements 4l .. 4l+3; unit 15 = coins (60, 61) and the first two elements of history row 0
-    uint32_t a, b, c, d;
-    if (l < 15u) {
-      const uint32_t bits = (l < 8u ? mlo >> (4u * l) : mhi >> (4u * l - 32u)) & 15u;
-      a = bits & 1u; b = (bits >> 1) & 1u; c = (bits >> 2) & 1u; d = bits >> 3;
-    } else {
-      const uint32_t col0 = history_column((codes >> 20) & 31u, view);
-      a = meta & 255u; b = (meta >> 8) & 255u; c = col0 == 0u ? 1u : 0u; d = col0 == 1u ? 1u : 0u;
-    }
-    reinterpret_cast<U4*>(row)[l] = Unit4<T>::make(a, b, c, d);
-    // new rows: 9 two-element units each, contiguous from element 62 + 18 * first (an even offset)
-    const uint32_t first = (meta >> 16) & 255u, npairs = 9u * (meta >> 24);
-    U2* row2 = reinterpret_cast<U2*>(row);
-    for (uint32_t p = l; p < npairs; p += 16u) {
-      const uint32_t k = p / 9u, u = p - 9u * k;
-      const uint32_t col = history_column((codes >> (5u * k)) & 31u, view);
-      row2[31u + 9u * first + p] = Unit2<T>::make(col == 2u * u ? 1u : 0u, col == 2u * u + 1u ? 1u : 0u);
-    }
-    if (clr) {
-      const U2 zero = Unit2<T>::make(0u, 0u);
-      for (uint32_t q = ((clr & 0xffffu) >> 1) + l; q < (clr >> 17); q += 16u) row2[q] = zero;
+    const uint32_t* vr = rec + 1 + view * kIncViewWords;
+    const uint32_t hdr0 = vr[0], hdr1 = vr[1];
+    const size_t row_base = (static_cast<size_t>(e0 + j) * 2 + view) * stride;
+#pragma unroll
+    for (int sp = 0; sp < 2; ++sp) {
+      const int start = sp == 0 ? -static_cast<int>(hdr0 & 255u) : static_cast<int>(hdr1 & 0xFFFFu);   // row element of unit 0
+      const uint32_t units = sp == 0 ? hdr0 >> 8 : hdr1 >> 16;
+      const uint32_t* bm = vr + (sp == 0 ? 2 : 8);
+      uint4* dst = reinterpret_cast<uint4*>(buf + (row_base + start));               // size_t + int: start may be negative
+      for (uint32_t u = l; u < units; u += 16u) {
+        const uint32_t o = u * kEl;                                                    // never straddles a 32-bit word
+        const uint32_t bits = o < 192u ? (bm[o >> 5] >> (o & 31u)) & ((1u << kEl) - 1u) : 0u;
+        uint4 v = Pack16<T>::from_bits(bits);
+        const int p = start + static_cast<int>(o);
+        if (sp == 0 && p <= 61 && p + static_cast<int>(kEl) > 60) {                   // the unit with the raw coin counts (207-213)
+          const uint32_t coins = rec[0];
+          v = Pack16<T>::make([&](int k) { return p + k == 60 ? coins & 255u : p + k == 61 ? coins >> 8 : (bits >> k) & 1u; });
+        }
+        dst[u] = v;
+      }
     }
   }
   st.flush(A.stats);

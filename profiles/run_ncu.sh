@@ -1,8 +1,8 @@
 #!/bin/bash
 # Profiling pass (run under gpurun, one GPU): profiles/run_ncu.sh <tag>
 # 1. plain run of the exact command (must exit 0), 2. launch list of the same command, 3. one --set full capture of each
-# kernel the bench line talks about. The .ncu-rep files come back in gpurun_out/; scripts/ncu_export.sh turns them into the
-# CSVs committed under profiles/.
+# kernel the bench line talks about, exported on the box to the raw / details CSVs that are committed under profiles/
+# (gpurun brings back at most 64 MiB, so only the reports listed in KEEP_REPS travel as .ncu-rep for source-level analysis).
 set -u
 TAG=${1:-r09}
 OUT=gpurun_out
@@ -16,7 +16,11 @@ full() {  # name, kernel regex, skip, command...
   "$@" > $OUT/ncu_plain_${name}_$TAG.log 2>&1 || { echo "plain $name failed"; return; }
   ncu --set full --clock-control none --import-source on -k regex:$regex -s $skip -c 1 -f -o $OUT/prof_${TAG}_$name "$@" > $OUT/ncu_full_${name}_$TAG.log 2>&1
   echo "full $name rc=$?"
+  ncu -i $OUT/prof_${TAG}_$name.ncu-rep --page raw --csv > $OUT/${TAG}_${name}_raw.csv 2>/dev/null
+  ncu -i $OUT/prof_${TAG}_$name.ncu-rep --page details --csv > $OUT/${TAG}_${name}_details.csv 2>/dev/null
+  case " $KEEP_REPS " in *" $name "*) ;; *) rm -f $OUT/prof_${TAG}_$name.ncu-rep ;; esac
 }
+KEEP_REPS=${KEEP_REPS:-"rollout_env kernels_record incremental"}
 full rollout_d32 k_rollout_ws 5 $BASE
 full rollout_d8 k_rollout_ws 5 $BASE --contract d8
 full rollout_bf16 k_rollout_ws 5 $BASE --contract bf16
@@ -29,4 +33,4 @@ full kernels_step k_stepE 2 python scripts/kernel_probe.py step
 full kernels_record k_step_record 2 python scripts/kernel_probe.py record
 full kernels_fork k_fork 2 python scripts/kernel_probe.py fork
 cp open_spiel_coup_b200/libcoup_b200.so $OUT/libcoup_b200_$TAG.so   # for scripts/ncu_hotspots.py / ncu_functions.py (SASS <-> source lines)
-ls -la $OUT | tail -30
+du -sh $OUT; ls -la $OUT | tail -40
