@@ -214,9 +214,11 @@ int encode_obs_dispatch(coup_vec_env* env, const Src& src, uint32_t max_groups, 
 template <typename T>
 int rollout_incremental_typed(coup_vec_env* env, int n_steps, void* d_buf, uint32_t stride, cudaStream_t st) {
   const unsigned grid = blocks_for(env->A.n);
+  cudaError_t err = cudaFuncSetAttribute(k_rollout_incremental<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kIncSmemBytes);
+  if (err != cudaSuccess) return fail(COUP_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(err));
   for (int i = 0; i < n_steps; ++i) {
     step_prologue(env, false, st);
-    k_rollout_incremental<T><<<grid, kBlockThreads, 0, st>>>(env->A, env->step_counter, static_cast<T*>(d_buf), stride);
+    k_rollout_incremental<T><<<grid, kBlockThreads, kIncSmemBytes, st>>>(env->A, env->step_counter, static_cast<T*>(d_buf), stride);
     env->step_counter++;
   }
   return launch_status("k_rollout_incremental");

@@ -1818,9 +1818,10 @@ k_rollout_ws(EnvArrays A, uint64_t step, int player_sel, T* __restrict__ out, ui
 // Earlier mappings, measured on one B200 at 2^20 envs, fp32: natural-offset 8/16-byte stores 0.52 ms; whole-sector stores
 // with the content recomputed per element inside the walk 0.75-1.06 ms (3.5x the instructions, no fills any more); whole
 // warp per (env, view) with one store per row 0.556 ms; every thread storing its own env's units 0.950 ms.
-constexpr int kIncViewWords = 14;                      // per view: 2 span headers + 6 + 6 bitmap words
-constexpr int kIncRecWords = 1 + 2 * kIncViewWords;    // + the coin word; 29: an odd pitch, conflict-free per-lane access
+constexpr int kIncViewWords = 19;                      // per view: 2 span headers, 6 + 6 bitmap words, coin unit (index + 4 words)
+constexpr int kIncRecWords = 1 + 2 * kIncViewWords;    // 39: an odd pitch, conflict-free per-lane access
 constexpr int kIncRowPitch = kHistoryWords + 1;
+constexpr int kIncSmemBytes = kBlockThreads * (kIncRecWords + kIncRowPitch) * 4;   // 57 344: dynamic (above the 48 KB static limit)
 
 // Sixteen bytes of consecutive tensor elements: from 0/1 bits, or from small-integer values.
 template <typename T> struct Pack16;
@@ -1874,8 +1875,9 @@ template <typename T>
 __global__ void __launch_bounds__(kBlockThreads)
 k_rollout_incremental(EnvArrays A, uint64_t step, T* __restrict__ buf, uint32_t stride) {
   __shared__ uint32_t s_stats[COUP_STATS_LEN];
-  __shared__ uint32_t s_rec[kWarpsPerBlock][32][kIncRecWords];
-  __shared__ uint32_t s_row[kWarpsPerBlock][32][kIncRowPitch];
+  extern __shared__ __align__(16) uint32_t s_dyn[];      // kIncSmemBytes: [256][kIncRecWords] records, [256][kIncRowPitch] rows
+  uint32_t (*s_rec)[32][kIncRecWords] = reinterpret_cast<uint32_t (*)[32][kIncRecWords]>(s_dyn);
+  uint32_t (*s_row)[32][kIncRowPitch] = reinterpret_cast<uint32_t (*)[32][kIncRowPitch]>(s_dyn + kBlockThreads * kIncRecWords);
   constexpr uint32_t kEl = Pack16<T>::kElems;            // elements per 16-byte unit
   constexpr uint32_t kSector = 2u * kEl;                  // elements per 32-byte sector
   BlockStats st;
@@ -1902,7 +1904,7 @@ k_rollout_incremental(EnvArrays A, uint64_t step, T* __restrict__ buf, uint32_t 
         return i < new_len ? (row_copy[w] >> (5u * (i - 6u * w))) & 31u : 31u;
       };
       uint32_t* rec = s_rec[warp][lane];
-      rec[0] = pw_coins(s.p[0]) | (pw_coins(s.p[1]) << 8);
+      const uint32_t coin0 = pw_coins(s.p[0]), coin1 = pw_coins(s.p[1]);
       // span 0: the head -- or, after a re-deal, everything from element 0 to the end of the finished episode's rows;
       // span 1: the new rows (none after a re-deal: they are part of span 0)
       const uint32_t hi0 = redealt ? 62u + 18u * max(r.final_moves, new_len) : 62u;
@@ -1929,6 +1931,13 @@ k_rollout_incremental(EnvArrays A, uint64_t step, T* __restrict__ buf, uint32_t 
           const uint32_t col = history_column(code_at(k), view);
           if (col != 31u) bitmap_set(bm0, 62 + 18 * static_cast<int>(k) + static_cast<int>(col) + back0);
         }
+        // the one unit of span 0 that is not 0/1: it holds the raw coin counts (elements 60, 61; 207-213). Rows start on
+        // multiples of four elements, so both counts are always in the same unit.
+        const uint32_t uc = (60u + static_cast<uint32_t>(back0)) / kEl;
+        const int pc = static_cast<int>(uc * kEl) - back0;                             // row element of the unit's first element
+        const uint32_t cbits = (bm0[(uc * kEl) >> 5] >> ((uc * kEl) & 31u)) & ((1u << kEl) - 1u);
+        const uint4 cu = Pack16<T>::make([&](int k) { return pc + k == 60 ? coin0 : pc + k == 61 ? coin1 : (cbits >> k) & 1u; });
+        vr[14] = uc; vr[15] = cu.x; vr[16] = cu.y; vr[17] = cu.z; vr[18] = cu.w;
 #pragma unroll
         for (int k = 0; k < 6; ++k) bm1[k] = 0u;
 #pragma unroll
@@ -1962,11 +1971,7 @@ k_rollout_incremental(EnvArrays A, uint64_t step, T* __restrict__ buf, uint32_t 
         const uint32_t o = u * kEl;                                                    // never straddles a 32-bit word
         const uint32_t bits = o < 192u ? (bm[o >> 5] >> (o & 31u)) & ((1u << kEl) - 1u) : 0u;
         uint4 v = Pack16<T>::from_bits(bits);
-        const int p = start + static_cast<int>(o);
-        if (sp == 0 && p <= 61 && p + static_cast<int>(kEl) > 60) {                   // the unit with the raw coin counts (207-213)
-          const uint32_t coins = rec[0];
-          v = Pack16<T>::make([&](int k) { return p + k == 60 ? coins & 255u : p + k == 61 ? coins >> 8 : (bits >> k) & 1u; });
-        }
+        if (sp == 0 && u == vr[14]) v = make_uint4(vr[15], vr[16], vr[17], vr[18]);   // the unit with the raw coin counts
         dst[u] = v;
       }
     }
