@@ -214,6 +214,8 @@ int encode_obs_dispatch(coup_vec_env* env, const Src& src, uint32_t max_groups, 
 template <typename T>
 int rollout_incremental_typed(coup_vec_env* env, int n_steps, void* d_buf, uint32_t stride, cudaStream_t st) {
   const unsigned grid = blocks_for(env->A.n);
+  constexpr int kIncSmemBytes = kIncSmemWords * 4 + UnitLut<T>::kBytes;
+  static_assert(kIncSmemBytes <= kIncSmemBytesMax, "unit table larger than reserved");
   cudaError_t err = cudaFuncSetAttribute(k_rollout_incremental<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kIncSmemBytes);
   if (err != cudaSuccess) return fail(COUP_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(err));
   for (int i = 0; i < n_steps; ++i) {

@@ -1821,7 +1821,8 @@ k_rollout_ws(EnvArrays A, uint64_t step, int player_sel, T* __restrict__ out, ui
 constexpr int kIncViewWords = 19;                      // per view: 2 span headers, 6 + 6 bitmap words, coin unit (index + 4 words)
 constexpr int kIncRecWords = 1 + 2 * kIncViewWords;    // 39: an odd pitch, conflict-free per-lane access
 constexpr int kIncRowPitch = kHistoryWords + 1;
-constexpr int kIncSmemBytes = kBlockThreads * (kIncRecWords + kIncRowPitch) * 4;   // 57 344: dynamic (above the 48 KB static limit)
+constexpr int kIncSmemWords = kBlockThreads * (kIncRecWords + kIncRowPitch);       // records + rows; the unit table follows
+constexpr int kIncSmemBytesMax = kIncSmemWords * 4 + 4096;                          // dynamic (above the 48 KB static limit)
 
 // Sixteen bytes of consecutive tensor elements: from 0/1 bits, or from small-integer values.
 template <typename T> struct Pack16;
@@ -1866,6 +1867,37 @@ template <> struct Pack16<uint8_t> {
   }
 };
 
+// bits -> 16-byte unit through a small table in shared memory (one or two loads instead of a dozen ALU instructions):
+// 16 entries for f32 (4 elements per unit), 256 for bf16 (8), 256 eight-byte entries looked up twice for u8 (16).
+template <typename T> struct UnitLut;
+template <> struct UnitLut<float> {
+  static constexpr int kBytes = 16 * 16;
+  static __device__ __forceinline__ void init(void* lut, int tid) {
+    if (tid < 16) reinterpret_cast<uint4*>(lut)[tid] = Pack16<float>::from_bits(tid);
+  }
+  static __device__ __forceinline__ uint4 lookup(const void* lut, uint32_t bits) { return reinterpret_cast<const uint4*>(lut)[bits]; }
+};
+template <> struct UnitLut<__nv_bfloat16> {
+  static constexpr int kBytes = 256 * 16;
+  static __device__ __forceinline__ void init(void* lut, int tid) {
+    if (tid < 256) reinterpret_cast<uint4*>(lut)[tid] = Pack16<__nv_bfloat16>::from_bits(tid);
+  }
+  static __device__ __forceinline__ uint4 lookup(const void* lut, uint32_t bits) { return reinterpret_cast<const uint4*>(lut)[bits]; }
+};
+template <> struct UnitLut<uint8_t> {
+  static constexpr int kBytes = 256 * 8;
+  static __device__ __forceinline__ void init(void* lut, int tid) {
+    if (tid < 256) {
+      const uint4 v = Pack16<uint8_t>::from_bits(tid);     // the low 8 bits fill x, y
+      reinterpret_cast<uint2*>(lut)[tid] = make_uint2(v.x, v.y);
+    }
+  }
+  static __device__ __forceinline__ uint4 lookup(const void* lut, uint32_t bits) {
+    const uint2 a = reinterpret_cast<const uint2*>(lut)[bits & 255u], b = reinterpret_cast<const uint2*>(lut)[bits >> 8];
+    return make_uint4(a.x, a.y, b.x, b.y);
+  }
+};
+
 // Sets bit t of a 192-bit bitmap kept as six words in shared memory; t outside [0, 192) is ignored.
 __device__ __forceinline__ void bitmap_set(uint32_t* words, int t) {
   if (t >= 0 && t < 192) words[t >> 5] |= 1u << (t & 31);
@@ -1878,6 +1910,8 @@ k_rollout_incremental(EnvArrays A, uint64_t step, T* __restrict__ buf, uint32_t 
   extern __shared__ __align__(16) uint32_t s_dyn[];      // kIncSmemBytes: [256][kIncRecWords] records, [256][kIncRowPitch] rows
   uint32_t (*s_rec)[32][kIncRecWords] = reinterpret_cast<uint32_t (*)[32][kIncRecWords]>(s_dyn);
   uint32_t (*s_row)[32][kIncRowPitch] = reinterpret_cast<uint32_t (*)[32][kIncRowPitch]>(s_dyn + kBlockThreads * kIncRecWords);
+  void* const lut = s_dyn + kIncSmemWords;               // 16-byte aligned: kIncSmemWords is a multiple of 4
+  UnitLut<T>::init(lut, threadIdx.x);                    // made visible by the __syncthreads of st.init below
   constexpr uint32_t kEl = Pack16<T>::kElems;            // elements per 16-byte unit
   constexpr uint32_t kSector = 2u * kEl;                  // elements per 32-byte sector
   BlockStats st;
@@ -1959,21 +1993,21 @@ k_rollout_incremental(EnvArrays A, uint64_t step, T* __restrict__ buf, uint32_t 
     touched &= touched - 1;
     const uint32_t* rec = s_rec[warp][j];
     const uint32_t* vr = rec + 1 + view * kIncViewWords;
-    const uint32_t hdr0 = vr[0], hdr1 = vr[1];
+    const uint32_t hdr0 = vr[0], hdr1 = vr[1], coin_unit = vr[14];
     const size_t row_base = (static_cast<size_t>(e0 + j) * 2 + view) * stride;
-#pragma unroll
-    for (int sp = 0; sp < 2; ++sp) {
-      const int start = sp == 0 ? -static_cast<int>(hdr0 & 255u) : static_cast<int>(hdr1 & 0xFFFFu);   // row element of unit 0
-      const uint32_t units = sp == 0 ? hdr0 >> 8 : hdr1 >> 16;
-      const uint32_t* bm = vr + (sp == 0 ? 2 : 8);
-      uint4* dst = reinterpret_cast<uint4*>(buf + (row_base + start));               // size_t + int: start may be negative
-      for (uint32_t u = l; u < units; u += 16u) {
-        const uint32_t o = u * kEl;                                                    // never straddles a 32-bit word
-        const uint32_t bits = o < 192u ? (bm[o >> 5] >> (o & 31u)) & ((1u << kEl) - 1u) : 0u;
-        uint4 v = Pack16<T>::from_bits(bits);
-        if (sp == 0 && u == vr[14]) v = make_uint4(vr[15], vr[16], vr[17], vr[18]);   // the unit with the raw coin counts
-        dst[u] = v;
-      }
+    // both spans as one list of units: [0, n0) span 0, [n0, n0 + n1) span 1
+    const uint32_t n0 = hdr0 >> 8, n1 = hdr1 >> 16;
+    uint4* const dst0 = reinterpret_cast<uint4*>(buf + (row_base - (hdr0 & 255u)));
+    uint4* const dst1 = reinterpret_cast<uint4*>(buf + (row_base + (hdr1 & 0xFFFFu)));
+    for (uint32_t k = l; k < n0 + n1; k += 16u) {
+      const bool second = k >= n0;
+      const uint32_t u = second ? k - n0 : k;
+      const uint32_t o = u * kEl;                                                    // never straddles a 32-bit word
+      const uint32_t word = o < 192u ? vr[(second ? 8u : 2u) + (o >> 5)] : 0u;
+      const uint32_t bits = (word >> (o & 31u)) & ((1u << kEl) - 1u);
+      uint4 v = UnitLut<T>::lookup(lut, bits);
+      if (!second && u == coin_unit) v = make_uint4(vr[15], vr[16], vr[17], vr[18]);   // the unit with the raw coin counts
+      (second ? dst1 : dst0)[u] = v;
     }
   }
   st.flush(A.stats);
