@@ -1818,8 +1818,8 @@ k_rollout_ws(EnvArrays A, uint64_t step, int player_sel, T* __restrict__ out, ui
 // Earlier mappings, measured on one B200 at 2^20 envs, fp32: natural-offset 8/16-byte stores 0.52 ms; whole-sector stores
 // with the content recomputed per element inside the walk 0.75-1.06 ms (3.5x the instructions, no fills any more); whole
 // warp per (env, view) with one store per row 0.556 ms; every thread storing its own env's units 0.950 ms.
-constexpr int kIncViewWords = 19;                      // per view: 2 span headers, 6 + 6 bitmap words, coin unit (index + 4 words)
-constexpr int kIncRecWords = 1 + 2 * kIncViewWords;    // 39: an odd pitch, conflict-free per-lane access
+constexpr int kIncViewWords = 18;                      // per view: 2 span headers, 6 + 6 bitmap words, the 4 words of the coin unit
+constexpr int kIncRecWords = 1 + 2 * kIncViewWords;    // 37: an odd pitch, conflict-free per-lane access; 4 CTAs fit an SM
 constexpr int kIncRowPitch = kHistoryWords + 1;
 constexpr int kIncSmemWords = kBlockThreads * (kIncRecWords + kIncRowPitch);       // records + rows; the unit table follows
 constexpr int kIncSmemBytesMax = kIncSmemWords * 4 + 4096;                          // dynamic (above the 48 KB static limit)
@@ -1903,8 +1903,11 @@ __device__ __forceinline__ void bitmap_set(uint32_t* words, int t) {
   if (t >= 0 && t < 192) words[t >> 5] |= 1u << (t & 31);
 }
 
+#ifndef COUP_INC_BLOCKS
+#define COUP_INC_BLOCKS 4   // resident CTAs per SM the kernel is compiled for (registers <= 64; shared memory allows 3-4)
+#endif
 template <typename T>
-__global__ void __launch_bounds__(kBlockThreads)
+__global__ void __launch_bounds__(kBlockThreads, COUP_INC_BLOCKS)
 k_rollout_incremental(EnvArrays A, uint64_t step, T* __restrict__ buf, uint32_t stride) {
   __shared__ uint32_t s_stats[COUP_STATS_LEN];
   extern __shared__ __align__(16) uint32_t s_dyn[];      // kIncSmemBytes: [256][kIncRecWords] records, [256][kIncRowPitch] rows
@@ -1971,7 +1974,7 @@ k_rollout_incremental(EnvArrays A, uint64_t step, T* __restrict__ buf, uint32_t 
         const int pc = static_cast<int>(uc * kEl) - back0;                             // row element of the unit's first element
         const uint32_t cbits = (bm0[(uc * kEl) >> 5] >> ((uc * kEl) & 31u)) & ((1u << kEl) - 1u);
         const uint4 cu = Pack16<T>::make([&](int k) { return pc + k == 60 ? coin0 : pc + k == 61 ? coin1 : (cbits >> k) & 1u; });
-        vr[14] = uc; vr[15] = cu.x; vr[16] = cu.y; vr[17] = cu.z; vr[18] = cu.w;
+        vr[14] = cu.x; vr[15] = cu.y; vr[16] = cu.z; vr[17] = cu.w;
 #pragma unroll
         for (int k = 0; k < 6; ++k) bm1[k] = 0u;
 #pragma unroll
@@ -1993,7 +1996,7 @@ k_rollout_incremental(EnvArrays A, uint64_t step, T* __restrict__ buf, uint32_t 
     touched &= touched - 1;
     const uint32_t* rec = s_rec[warp][j];
     const uint32_t* vr = rec + 1 + view * kIncViewWords;
-    const uint32_t hdr0 = vr[0], hdr1 = vr[1], coin_unit = vr[14];
+    const uint32_t hdr0 = vr[0], hdr1 = vr[1], coin_unit = (60u + (hdr0 & 255u)) / kEl;
     const size_t row_base = (static_cast<size_t>(e0 + j) * 2 + view) * stride;
     // both spans as one list of units: [0, n0) span 0, [n0, n0 + n1) span 1
     const uint32_t n0 = hdr0 >> 8, n1 = hdr1 >> 16;
@@ -2006,7 +2009,7 @@ k_rollout_incremental(EnvArrays A, uint64_t step, T* __restrict__ buf, uint32_t 
       const uint32_t word = o < 192u ? vr[(second ? 8u : 2u) + (o >> 5)] : 0u;
       const uint32_t bits = (word >> (o & 31u)) & ((1u << kEl) - 1u);
       uint4 v = UnitLut<T>::lookup(lut, bits);
-      if (!second && u == coin_unit) v = make_uint4(vr[15], vr[16], vr[17], vr[18]);   // the unit with the raw coin counts
+      if (!second && u == coin_unit) v = make_uint4(vr[14], vr[15], vr[16], vr[17]);   // the unit with the raw coin counts
       (second ? dst1 : dst0)[u] = v;
     }
   }
