@@ -29,7 +29,7 @@ full incremental k_rollout_incremental 3 python scripts/incremental_probe.py 20
 full kernels_obs k_encode_obs 2 python scripts/kernel_probe.py obs
 full kernels_policy k_sample_policy 2 python scripts/kernel_probe.py policy
 full kernels_mask k_legal_actions_mask 2 python scripts/kernel_probe.py mask
-full kernels_step k_stepE 2 python scripts/kernel_probe.py step
+full kernels_step "^k_step$" 2 python scripts/kernel_probe.py step
 full kernels_record k_step_record 2 python scripts/kernel_probe.py record
 full kernels_fork k_fork 2 python scripts/kernel_probe.py fork
 cp open_spiel_coup_b200/libcoup_b200.so $OUT/libcoup_b200_$TAG.so   # for scripts/ncu_hotspots.py / ncu_functions.py (SASS <-> source lines)
