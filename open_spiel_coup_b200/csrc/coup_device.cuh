@@ -41,6 +41,11 @@ COUP_FN uint32_t umin32(uint32_t a, uint32_t b) { return min(a, b); }
 COUP_FN uint32_t umax32(uint32_t a, uint32_t b) { return max(a, b); }
 #endif
 
+// x >> C for a compile-time C. (Issuing these as the high half of a multiply by 2^(32-C), to move them off the busy ALU
+// pipe, was measured and is slower: env-only 33.7 -> 35.2 us per 2^20-env step.)
+template <uint32_t C>
+COUP_FN uint32_t rsh(uint32_t x) { return x >> C; }
+
 // ---- action / card ids (coup.h:50-85) ---------------------------------------------------------
 enum : uint32_t {
   kIncome = 0, kForeignAid = 1, kCoup = 2, kTax = 3, kAssassinate = 4, kExchange = 5, kSteal = 6,
@@ -73,9 +78,9 @@ COUP_FN void set_p(Env& s, uint32_t i, uint32_t v) {
 
 // player word
 COUP_FN uint32_t pw_hand(uint32_t w) { return w & 0xFFFFu; }
-COUP_FN uint32_t pw_coins(uint32_t w) { return (w >> 16) & 31u; }
-COUP_FN uint32_t pw_last(uint32_t w) { return (w >> 21) & 31u; }
-COUP_FN uint32_t pw_lost(uint32_t w) { return (w >> 26) & 1u; }
+COUP_FN uint32_t pw_coins(uint32_t w) { return rsh<16>(w) & 31u; }
+COUP_FN uint32_t pw_last(uint32_t w) { return rsh<21>(w) & 31u; }
+COUP_FN uint32_t pw_lost(uint32_t w) { return rsh<26>(w) & 1u; }
 COUP_FN uint32_t pw_set_hand(uint32_t w, uint32_t h) { return (w & ~0xFFFFu) | (h & 0xFFFFu); }
 COUP_FN uint32_t pw_add_coins(uint32_t w, int d) { return w + (static_cast<uint32_t>(d) << 16); }
 COUP_FN uint32_t pw_set_last(uint32_t w, uint32_t a) { return (w & ~(31u << 21)) | (a << 21); }
@@ -86,16 +91,16 @@ constexpr uint32_t kBitTurn = 1u << 20, kBitMover = 1u << 21, kBitTurnBegin = 1u
                    kBitChance = 1u << 23, kBitQInitial = 1u << 27, kBitQPlayer = 1u << 28,
                    kBitError = 1u << 29;
 COUP_FN uint32_t g_deck(uint32_t g, uint32_t c) { return (g >> (4 * c)) & 15u; }
-COUP_FN uint32_t g_turn(uint32_t g) { return (g >> 20) & 1u; }
-COUP_FN uint32_t g_mover(uint32_t g) { return (g >> 21) & 1u; }
-COUP_FN uint32_t g_turn_begin(uint32_t g) { return (g >> 22) & 1u; }
-COUP_FN uint32_t g_chance(uint32_t g) { return (g >> 23) & 1u; }
-COUP_FN uint32_t g_qn(uint32_t g) { return (g >> 24) & 7u; }
+COUP_FN uint32_t g_turn(uint32_t g) { return rsh<20>(g) & 1u; }
+COUP_FN uint32_t g_mover(uint32_t g) { return rsh<21>(g) & 1u; }
+COUP_FN uint32_t g_turn_begin(uint32_t g) { return rsh<22>(g) & 1u; }
+COUP_FN uint32_t g_chance(uint32_t g) { return rsh<23>(g) & 1u; }
+COUP_FN uint32_t g_qn(uint32_t g) { return rsh<24>(g) & 7u; }
 
 // counter word
 COUP_FN uint32_t c_moves(uint32_t c) { return c & 127u; }
-COUP_FN uint32_t c_turns(uint32_t c) { return (c >> 7) & 127u; }
-COUP_FN int c_reward0(uint32_t c) { return static_cast<int>((c >> 14) & 7u) - 2; }
+COUP_FN uint32_t c_turns(uint32_t c) { return rsh<7>(c) & 127u; }
+COUP_FN int c_reward0(uint32_t c) { return static_cast<int>(rsh<14>(c) & 7u) - 2; }
 COUP_FN uint32_t c_set_reward0(uint32_t c, int r) {
   return (c & ~(7u << 14)) | (static_cast<uint32_t>(r + 2) << 14);
 }
@@ -104,7 +109,7 @@ COUP_FN uint32_t c_set_reward0(uint32_t c, int r) {
 // Sorted ascending == CoupCard::operator< order (coup.h:91-94), so a hand is always what
 // CoupPlayer::SortCards (389-391) would leave.
 COUP_FN uint32_t hand_slot(uint32_t h, uint32_t i) { return (h >> (4 * i)) & 15u; }
-COUP_FN uint32_t hand_empty_mask(uint32_t h) { return (h >> 3) & (h >> 2) & 0x1111u; }
+COUP_FN uint32_t hand_empty_mask(uint32_t h) { return rsh<3>(h) & rsh<2>(h) & 0x1111u; }
 COUP_FN uint32_t hand_count(uint32_t h) { return 4u - popc32(hand_empty_mask(h)); }
 COUP_FN uint32_t hand_down_mask(uint32_t h) { return ~h & 0x1111u; }  // empties have bit0 set
 COUP_FN uint32_t hand_face_up_count(uint32_t h) {
@@ -144,10 +149,19 @@ COUP_FN uint32_t hand_find(uint32_t h, uint32_t key) {
 // ---- phase queries ----------------------------------------------------------------------------
 // CoupState::IsTerminal, 989-1010.
 COUP_FN bool is_terminal(const Env& s) {
+  // A player is out when he holds at least two cards and none of them is face down (995-999). Empty slots sort last and
+  // have bit 0 set, so "no face-down card" is bit 0 of all four slots, and "at least two cards" is slot 1 not empty
+  // (bits 2 and 3 of a card slot are never both set: values are 0..4).
+#ifdef COUP_AB_OLD_TERMINAL
   const uint32_t h0 = pw_hand(s.p[0]), h1 = pw_hand(s.p[1]);
   const bool alive0 = hand_count(h0) < 2 || hand_down_mask(h0) != 0;
   const bool alive1 = hand_count(h1) < 2 || hand_down_mask(h1) != 0;
   return c_moves(s.c) > kMaxGameLength || !(alive0 && alive1);
+#else
+  const bool out0 = (s.p[0] & 0x1111u) == 0x1111u && (s.p[0] & 0xC0u) != 0xC0u;
+  const bool out1 = (s.p[1] & 0x1111u) == 0x1111u && (s.p[1] & 0xC0u) != 0xC0u;
+  return c_moves(s.c) > kMaxGameLength || out0 || out1;
+#endif
 }
 
 // LegalLoseCardActions, 811-822: slot 0 / slot 1 face down -> bit kLoseCard1 / kLoseCard2.
@@ -203,8 +217,10 @@ COUP_FN uint32_t legal_mask_chance(const Env& s) {
 
 // CoupState::Returns, 1016-1032: returns[0] = faceUp(P2) - faceUp(P1).
 COUP_FN int returns_p0(const Env& s) {
-  return static_cast<int>(hand_face_up_count(pw_hand(s.p[1]))) -
-         static_cast<int>(hand_face_up_count(pw_hand(s.p[0])));
+  // both hands side by side in one word: bit 0 of a slot is set for face-up cards and for empty slots
+  const uint32_t hh = pw_hand(s.p[0]) | (s.p[1] << 16);
+  const uint32_t up = hh & ~(rsh<3>(hh) & rsh<2>(hh)) & 0x11111111u;
+  return static_cast<int>(popc32(rsh<16>(up))) - static_cast<int>(popc32(up & 0xFFFFu));
 }
 
 // ---- history log --------------------------------------------------------------------------------
@@ -323,16 +339,16 @@ COUP_FN void apply_player_action(Env& s, uint32_t a) {
   const uint32_t d = kEventTable[ev];
 
   // ---- coins ---------------------------------------------------------------------------------------
-  const uint32_t transfer = (d >> 6) & 3u;
+  const uint32_t transfer = rsh<6>(d) & 3u;
   const uint32_t victim_coins = transfer == 1u ? pw_coins(op) : pw_coins(cp);
   const int k = transfer ? (victim_coins > 1u ? 2 : 1) : 0;
   const int to_mover = transfer == 1u ? k : -k;
   cp = pw_add_coins(cp, static_cast<int>(d & 15u) - 8 + to_mover);
-  op = pw_add_coins(op, static_cast<int>((d >> 4) & 3u) - to_mover);
+  op = pw_add_coins(op, static_cast<int>(rsh<4>(d) & 3u) - to_mover);
 
   // ---- cards ---------------------------------------------------------------------------------------
   const bool lose = (d >> 17) & 1u, give_back = (d >> 18) & 1u, replace = (d >> 13) & 1u;
-  const uint32_t flip = (d >> 15) & 3u;
+  const uint32_t flip = rsh<15>(d) & 3u;
   // LoseCard k: slot k turns FaceUp, then SortCards (608-613). A player who has to lose a card holds exactly two
   // (a hand of four is always followed by ExchangeReturn first), so sorting is one min/max of the two slots.
   const uint32_t lk = (a - kLoseCard1) & 1u;
@@ -363,19 +379,19 @@ COUP_FN void apply_player_action(Env& s, uint32_t a) {
 
   // ---- flags, last action ----------------------------------------------------------------------------
   cp = pw_set_last(cp, a);                                   // every branch of the reference does this first
-  cp |= ((d >> 8) & 1u) << 26;
-  cp &= ~(((d >> 10) & 1u) << 26);
-  op |= ((d >> 9) & 1u) << 26;
+  cp |= (d << 18) & (1u << 26);              // bit 8 -> bit 26
+  cp &= ~((d << 16) & (1u << 26));           // bit 10
+  op |= (d << 17) & (1u << 26);              // bit 9
 
   // ---- who moves next --------------------------------------------------------------------------------
-  uint32_t advance = (d >> 11) & 3u;
+  uint32_t advance = rsh<11>(d) & 3u;
   advance = advance == 3u ? (pw_lost(op) ? 1u : 2u) : advance;
   const uint32_t t = g_turn(g) ^ 1u;
   const uint32_t g_next_turn = (g & ~(kBitTurn | kBitMover)) | (t << 20) | (t << 21) | kBitTurnBegin;   // 1079-1086
   const uint32_t g_next_move = (g ^ kBitMover) & ~kBitTurnBegin;                                        // 1088-1092
   g = advance == 2u ? g_next_turn : (advance == 1u ? g_next_move : g);
   // deals: one per replaced card, two for an Exchange draw, all to the other player (480 / 583-584)
-  const uint32_t deals = (replace ? 1u : 0u) + 2u * ((d >> 14) & 1u);
+  const uint32_t deals = (replace ? 1u : 0u) + (rsh<13>(d) & 2u);
   const uint32_t g_queued = (g & ~((7u << 24) | kBitQInitial | kBitQPlayer)) | (deals << 24) | (o << 28) | kBitChance;
   g = deals ? g_queued : g;
   s.g = g;
@@ -405,11 +421,23 @@ COUP_FN uint32_t apply_chance(Env& s, uint32_t card) {
 // 32-bit word: r = floor(u * total / 2^32), then the first c whose running count exceeds r. The five 4-bit counts
 // never sum past 15 (there are 15 cards in the game; the slot-indexed returns of 789-795 move counts between types but
 // conserve the total), so one multiply by 0x11111 leaves all five running counts side by side in nibbles 0..4.
-COUP_FN uint32_t sample_card(const Env& s, uint32_t u) {
-  const uint32_t run = ((s.g & 0xFFFFFu) * 0x11111u) & 0xFFFFFu;     // nibble c = deck_[0] + .. + deck_[c]
+// The comparison runs on four byte lanes at once: the counts of types 0..3 are spread to bytes, one multiply by
+// 0x01010101 leaves byte c = deck_[0] + .. + deck_[c], and (0x10 + r - run_c) keeps bit 4 exactly when run_c <= r
+// (r <= 14, run_c <= 15: no borrow between bytes).
+COUP_FN uint32_t sample_card_g(uint32_t g, uint32_t u) {
+#ifdef COUP_AB_OLD_SAMPLE_CARD
+  const uint32_t run = ((g & 0xFFFFFu) * 0x11111u) & 0xFFFFFu;       // nibble c = deck_[0] + .. + deck_[c]
   const uint32_t r = umulhi32(u, run >> 16);
   return (r >= (run & 15u)) + (r >= ((run >> 4) & 15u)) + (r >= ((run >> 8) & 15u)) + (r >= ((run >> 12) & 15u));
+#else
+  uint32_t x = ((g & 0xFFFFu) | (g << 8)) & 0x00FF00FFu;
+  x = (x | (x << 4)) & 0x0F0F0F0Fu;                                   // byte c = deck_[c], c < 4
+  const uint32_t run = x * 0x01010101u;
+  const uint32_t r = umulhi32(u, (run >> 24) + ((g >> 16) & 15u));
+  return popc32(((r * 0x01010101u + 0x10101010u) - run) & 0x10101010u);
+#endif
 }
+COUP_FN uint32_t sample_card(const Env& s, uint32_t u) { return sample_card_g(s.g, u); }
 
 // CoupState::CoupState, 393-428.
 COUP_FN Env initial_state() {

@@ -186,9 +186,10 @@ __device__ __forceinline__ StepResult step_env(Env& s, HistRow row, uint32_t act
   r.chance_moves = 0; r.truncated = false; r.final_moves = 0;
   const uint64_t genv = A.global_env_offset + e;
   const bool auto_reset = (A.flags & COUP_FLAG_AUTO_RESET) != 0;
-  const bool term0 = is_terminal(s);
+  // kLegalKnown: the caller still holds the mask the previous step returned for this very state; that mask is empty
+  // exactly when the state is terminal (a decision node always has a legal action, a chance node a card to deal)
+  const bool term0 = kLegalKnown ? legal_known == 0u : is_terminal(s);
   const bool chance0 = g_chance(s.g) != 0;
-  // kLegalKnown: the caller still holds the mask the previous step returned for this very state
   const uint32_t legal0 = kLegalKnown ? legal_known : legal_mask_decision(s);
   const uint4 rnd = env_random(A.seed, genv, step, 0);
   const uint32_t a = kSample ? sample_action(legal0, rnd.x) : action_in;
@@ -203,9 +204,10 @@ __device__ __forceinline__ StepResult step_env(Env& s, HistRow row, uint32_t act
   bool fin = false;       // an episode ended in this call
   bool term = term0;      // the state left in `s` is terminal
   // Rewards() / Returns() of the stepped state: deals change neither, and an env that does not step keeps its own.
-  r.reward0 = c_reward0(s.c);
-  r.return0 = returns_p0(s);
-  if (__any_sync(kFull, go)) {
+  if (!__any_sync(kFull, go)) {
+    r.reward0 = c_reward0(s.c);
+    r.return0 = returns_p0(s);
+  } else {
     Env t = s;
     apply_player_action(t, a);
     s.p[0] = go ? t.p[0] : s.p[0]; s.p[1] = go ? t.p[1] : s.p[1]; s.g = go ? t.g : s.g; s.c = go ? t.c : s.c;
@@ -247,6 +249,37 @@ __device__ __forceinline__ StepResult step_env(Env& s, HistRow row, uint32_t act
     // The deals that follow the action (at most three: Exchange after a lost challenge). Deals never change who is
     // alive, so inside the loop only the move cap (coup.cc:990) can end the game; a freshly dealt or finished env has
     // nothing pending.
+#ifndef COUP_AB_OLD_DEAL_LOOP
+    // All deals queued by a player action go to ONE player (apply_player_action: bit 28), so the loop works on that
+    // player's hand and the deck only; queue count, chance flag, move number and the player word are settled once after
+    // it. nd = deals this lane makes: the whole queue, cut short by the move cap.
+    const uint32_t target = (s.g >> 28) & 1u, qn = g_qn(s.g);
+    const uint32_t room = static_cast<uint32_t>(kMaxGameLength + 1) - umin32(c_moves(s.c), kMaxGameLength + 1);
+    const uint32_t nd = (go && g_chance(s.g)) ? umin32(qn, room) : 0u;
+    const uint32_t tw = get_p(s, target);
+    uint32_t hand = pw_hand(tw), g = s.g;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const bool pend = static_cast<uint32_t>(k) < nd;
+      if (!__any_sync(kFull, pend)) break;
+      uint32_t card = sample_card_g(g, k == 0 ? rnd.y : k == 1 ? rnd.z : rnd.w);
+      if (forced != nullptr) {
+        const uint32_t f = pend ? forced[k] : 0xFFu;   // lanes without an env must not touch the array
+        card = (f < 5u && g_deck(g, f) != 0) ? f : card;
+      }
+      g -= pend ? 1u << (4u * card) : 0u;                                  // deck_[card] -= 1 (coup.cc:491-520)
+      hand = pend ? hand_insert(hand, card << 1) : hand;
+      // a lane that deals has logged exactly its action so far: deal k is code 1 + k of the step
+      codes |= pend ? (18u + 5u * target + card) << (5u * (k + 1)) : 0u;
+    }
+    g -= nd << 24;                                                         // pop
+    g &= (nd != 0u && nd == qn) ? ~(kBitChance | kBitQInitial) : ~0u;      // queue empty: is_chance_ = false (520)
+    s.g = g;
+    set_p(s, target, nd ? pw_set_hand(tw, hand) : tw);
+    s.c += nd;                                                             // ++move_number_ per deal
+    n_codes += nd;
+    r.chance_moves += nd;
+#else
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       const bool pend = go && g_chance(s.g) && c_moves(s.c) <= kMaxGameLength;
@@ -263,6 +296,7 @@ __device__ __forceinline__ StepResult step_env(Env& s, HistRow row, uint32_t act
       n_codes += pend ? 1u : 0u;
       r.chance_moves += pend ? 1u : 0u;
     }
+#endif
     if (any_fin && fin) ring_write(A, ticket, e, r.final_state, row.work, step, r.truncated);   // before word 0 is re-dealt
     if (n_codes) history_commit(row.work, first, codes, n_codes, row.mirror);
     if (go && !fin && c_moves(s.c) > kMaxGameLength) {
@@ -541,35 +575,47 @@ __global__ void k_copy_env(EnvArrays A, uint32_t src, uint32_t dst) {
 // ---- batched state.child(action): dst[i] = step(copy of src[parent[i]], action[i]) without auto-reset ------
 // One thread per child: 16 B state + 64 B history row gathered from the parent slab (four 16 B loads), stepped in
 // registers, written to the child's own row. D.flags arrives with COUP_FLAG_AUTO_RESET cleared.
-__global__ void __launch_bounds__(kBlockThreads)
+#ifndef COUP_FORK_BLOCKS
+#define COUP_FORK_BLOCKS 3
+#endif
+__global__ void __launch_bounds__(kBlockThreads, COUP_FORK_BLOCKS)
 k_fork(EnvArrays D, const uint4* __restrict__ src_state, const uint32_t* __restrict__ src_history, uint32_t src_n,
        const uint32_t* __restrict__ parent, const uint8_t* __restrict__ actions, const uint8_t* __restrict__ forced,
        uint32_t count, uint64_t step, const uint32_t* __restrict__ count_ptr) {
   __shared__ uint32_t s_stats[COUP_STATS_LEN];
+  // The child's history row is built in shared memory (odd pitch: conflict-free per-lane access) from the parent's row and
+  // written to the child slab once, after the step: no read-modify-write of global memory inside the step.
+  __shared__ uint32_t s_row[kBlockThreads][kHistoryWords + 1];
   BlockStats st;
   st.init(s_stats);
   const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
   const bool active = e < (count_ptr ? min(count, *count_ptr) : count);   // device-side child count of a traversal level
   const uint32_t p = active ? parent[e] : 0xFFFFFFFFu;
   const bool valid = active && p < src_n;                  // out-of-range parents set the child's error bit
-  uint32_t* hist_row = D.history + static_cast<size_t>(e) * kHistoryWords;
+  uint32_t* const row = s_row[threadIdx.x];
   Env s = initial_state();
   bool parent_terminal = false;
   if (valid) {
     const uint4* src_row = reinterpret_cast<const uint4*>(src_history + static_cast<size_t>(p) * kHistoryWords);
-    uint4* dst_row = reinterpret_cast<uint4*>(hist_row);
-#pragma unroll
-    for (int k = 0; k < kHistoryWords / 4; ++k) dst_row[k] = src_row[k];
-    s = load_env(src_state + p);
+    const uint4 sv = src_state[p];
+    const uint4 h0 = src_row[0], h1 = src_row[1], h2 = src_row[2], h3 = src_row[3];
+    row[0] = h0.x; row[1] = h0.y; row[2] = h0.z; row[3] = h0.w; row[4] = h1.x; row[5] = h1.y; row[6] = h1.z; row[7] = h1.w;
+    row[8] = h2.x; row[9] = h2.y; row[10] = h2.z; row[11] = h2.w; row[12] = h3.x; row[13] = h3.y; row[14] = h3.z; row[15] = h3.w;
+    s.p[0] = sv.x; s.p[1] = sv.y; s.g = sv.z; s.c = sv.w;
     parent_terminal = is_terminal(s);
   }
-  StepResult r = step_env<false>(s, global_row(hist_row), valid ? actions[e] : 0xFFu, forced ? forced + static_cast<size_t>(e) * 4 : nullptr,
+  StepResult r = step_env<false>(s, global_row(row), valid ? actions[e] : 0xFFu, forced ? forced + static_cast<size_t>(e) * 4 : nullptr,
                                  D, e, step, valid);
   if (active) {
     if (parent_terminal) { s.g |= kBitError; r.illegal = true; }   // a terminal state has no children
     if (!valid) {
       s.g |= kBitError;
       r.illegal = true; r.done = false; r.legal = 0; r.cur_player = COUP_CHANCE_PLAYER_ID;
+    }
+    if (valid) {
+      uint4* dst_row = reinterpret_cast<uint4*>(D.history + static_cast<size_t>(e) * kHistoryWords);
+#pragma unroll
+      for (int k = 0; k < kHistoryWords / 4; ++k) dst_row[k] = make_uint4(row[4 * k], row[4 * k + 1], row[4 * k + 2], row[4 * k + 3]);
     }
     store_env(D.state + e, s);
     write_outputs(D, e, r);
@@ -1612,7 +1658,8 @@ k_rollout_env_multi(EnvArrays A, uint64_t step, int n_steps) {
   uint32_t* hist_row = A.history + static_cast<size_t>(active ? e : 0) * kHistoryWords;
   if (active) s = load_env(A.state + e);
   StepResult r = {};
-  r.legal = is_terminal(s) ? 0u : legal_mask_decision(s);   // from then on every step hands the next one its mask
+  // the mask of the loaded state; from then on every step hands the next one its mask
+  r.legal = is_terminal(s) ? 0u : (g_chance(s.g) ? legal_mask_chance(s) : legal_mask_decision(s));
   StatAcc acc;
   acc.clear();
   for (int k = 0; k < n_steps; ++k) {                       // n_steps <= StatAcc::kMaxAdds (the host launches in chunks of 64)

@@ -21,6 +21,11 @@ from ._lib import INFO_STATE_SIZE, NUM_DISTINCT_ACTIONS, PLAYER_CURRENT, PLAYER_
 # takes a bf16 cuBLAS GEMM off its fast path (5.2 ms vs 0.93 ms for [2^18, K] x [K, 1024] on B200); the encoder
 # writes zeros into the four pad columns (coup_vec_information_state_tensor_strided).
 PADDED_INFO_STATE_SIZE = 2496
+# History rows 91..134 of the info-state tensor can never be set (a game has at most 91 moves, chance nodes included:
+# MaxGameLength 90, coup.h:219, termination at move_number_ > 90, coup.cc:990; the tensor reserves 135 rows, coup.cc:1104-1116),
+# so elements >= 62 + 18 * 91 = 1700 are always zero and the first layer's product over them is exactly zero. On the
+# inference path the first GEMM therefore runs over the first 1728 columns only (1700 rounded up to 64 elements).
+LIVE_INFO_STATE_SIZE = 1728
 from .vector_env import CoupVectorEnv
 
 
@@ -51,11 +56,14 @@ class MLPPolicy(nn.Module):
         i = 0
         while i < len(layers):
             lin = layers[i]
+            w = lin.weight
+            if i == 0 and getattr(self, "input_size", None) == INFO_STATE_SIZE and x.shape[1] > LIVE_INFO_STATE_SIZE:
+                x, w = x[:, :LIVE_INFO_STATE_SIZE], w[:, :LIVE_INFO_STATE_SIZE]     # views: lda / ldb stay the row stride
             if i + 1 < len(layers) and isinstance(layers[i + 1], nn.ReLU):
-                x = torch._addmm_activation(lin.bias, x, lin.weight.t())
+                x = torch._addmm_activation(lin.bias, x, w.t())
                 i += 2
             else:
-                x = torch.addmm(lin.bias, x, lin.weight.t())
+                x = torch.addmm(lin.bias, x, w.t())
                 i += 1
         return x
 

@@ -1,10 +1,14 @@
 """GPU tests (-m gpu) of the on-device masked policy sampling and the self-play data generator. The sampling
 kernel is floating point: it is compared with a plain PyTorch fp32 statement of the reference rule
 (nfsp.py:154-167) with tolerance 1e-6 on the probabilities."""
+import os
+import sys
+
 import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 torch = pytest.importorskip("torch")
 if not torch.cuda.is_available():  # pragma: no cover
@@ -287,3 +291,29 @@ def test_bucketed_first_layer_equals_dense_forward(dtype, tol):
     cols = torch.arange(PADDED_INFO_STATE_SIZE, device="cuda").view(1, -1)
     beyond = cols >= (62 + 18 * env.move_numbers()).view(-1, 1)
     assert float(dense_in.float()[beyond].abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-4), (torch.bfloat16, 6e-2)])
+def test_live_column_first_layer_equals_dense_forward(dtype, tol):
+    """The inference path of MLPPolicy runs the first layer over the first LIVE_INFO_STATE_SIZE columns only. Everything
+    beyond element 62 + 18 * 91 = 1700 is zero in every reachable state (steered 91-move games included), so the logits
+    equal the dense nn.Sequential forward up to summation order (2e-4 in fp32, 6e-2 for bf16 logits of magnitude ~1)."""
+    from open_spiel_coup_b200.selfplay import LIVE_INFO_STATE_SIZE, PADDED_INFO_STATE_SIZE
+    assert LIVE_INFO_STATE_SIZE >= 62 + 18 * 91 and LIVE_INFO_STATE_SIZE % 8 == 0
+    n = 8192
+    env = CoupVectorEnv(n, seed=5, auto_reset=False)
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    from replay_check import steering_policy      # prefers Exchange / Pass / ExchangeReturn: reaches the move cap
+    for _ in range(100):
+        env.step(steering_policy(env))
+    assert int(env.move_numbers().max()) == 91
+    x = torch.zeros((n, PADDED_INFO_STATE_SIZE), dtype=dtype, device="cuda")
+    env.information_state_tensor(_lib.PLAYER_0, out=x)
+    assert float(x[:, 62 + 18 * 91:].float().abs().sum()) == 0.0
+    assert float(x[:, 62 + 18 * 90: 62 + 18 * 91].float().abs().sum()) > 0.0       # row 90 (move 91) is in use
+    torch.manual_seed(1)
+    policy = MLPPolicy(hidden_sizes=(256, 128), padded_input_size=PADDED_INFO_STATE_SIZE).to("cuda", dtype).eval()
+    with torch.no_grad():
+        fast = policy(x)                  # live columns, bias + ReLU in the GEMM epilogue
+        ref = policy.net(x)               # plain nn.Sequential over all 2496 columns
+    assert float((fast.float() - ref.float()).abs().max()) < tol
