@@ -276,16 +276,22 @@ def main():
 
     # Context for the roofline: what a pure zero-fill of the same output buffer reaches on this GPU right now (the
     # driver's peak is a COPY, half reads; this path only writes). Not a denominator, just reported beside `frac`.
-    write_only_gbs = None
-    if out is not None and rank == 0:
-        out.zero_()
+    def zero_fill_gbs(t):
+        # the same BYTES zero-filled as 32-bit words (torch's fill of 1- and 2-byte elements is itself far from the
+        # write ceiling: 3.9 TB/s on this buffer shape)
+        flat = t.view(-1).view(torch.int32) if (t.numel() * t.element_size()) % 4 == 0 else t
+        flat.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(10):
-            out.zero_()
+            flat.zero_()
         e1.record()
         torch.cuda.synchronize()
-        write_only_gbs = out.numel() * out.element_size() * 10 / (e0.elapsed_time(e1) * 1e-3) / 1e9
+        return t.numel() * t.element_size() * 10 / (e0.elapsed_time(e1) * 1e-3) / 1e9
+
+    write_only_gbs = None
+    if out is not None and rank == 0:
+        write_only_gbs = zero_fill_gbs(out)
 
     # Other contracts on the same slab (short runs), reported beside the headline.
     extra = {}
@@ -302,6 +308,9 @@ def main():
             m2 = timed(lambda k: env.rollout(k, s2, out=buf), kk)
             v2 = kk * n * world / (m2 * 1e-3)
             extra[name] = {"steps_per_s": v2, "hbm_gbs": BYTES_PER_STEP[name] * v2 / world / 1e9}
+            if buf is not None and rank == 0:      # the write ceiling for THIS buffer size (smaller buffers fill a little slower)
+                fill = zero_fill_gbs(buf)
+                extra[name].update(write_only_fill_gbs=fill, frac_of_write_only_fill=extra[name]["hbm_gbs"] / fill)
             del buf
         # contract I: persistent fp32 buffer with both views of every env, updated in place
         if out is not None:
