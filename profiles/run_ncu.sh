@@ -4,7 +4,7 @@
 # kernel the bench line talks about, exported on the box to the raw / details CSVs that are committed under profiles/
 # (gpurun brings back at most 64 MiB, so only the reports listed in KEEP_REPS travel as .ncu-rep for source-level analysis).
 set -u
-TAG=${1:-r09}
+TAG=${1:-r10}
 OUT=gpurun_out
 mkdir -p $OUT
 BASE="python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-extra-contracts --no-selfplay --no-host-tensor"
