@@ -312,6 +312,19 @@ def main():
                 fill = zero_fill_gbs(buf)
                 extra[name].update(write_only_fill_gbs=fill, frac_of_write_only_fill=extra[name]["hbm_gbs"] / fill)
             del buf
+        # live-prefix contract: fp32 rows of 1728 elements = elements [0, 1728) of the reference row; everything they drop
+        # (history rows 91..134) is zero in every reachable state (COUP_LIVE_INFO_STATE_SIZE, include/coup_b200.h)
+        live_bytes = 42 + 4 * _lib.LIVE_INFO_STATE_SIZE + 11
+        buf = torch.empty((n, _lib.LIVE_INFO_STATE_SIZE), dtype=torch.float32, device=dev)
+        env.rollout(3, _lib.PLAYER_CURRENT, out=buf)
+        m2 = timed(lambda k: env.rollout(k, _lib.PLAYER_CURRENT, out=buf), ke)
+        v2 = ke * n * world / (m2 * 1e-3)
+        extra["d32_live_prefix"] = {"steps_per_s": v2, "hbm_gbs": live_bytes * v2 / world / 1e9, "bytes_per_step": live_bytes,
+                                    "note": "fp32 rows cut after element 1727: the dropped columns are always zero"}
+        if rank == 0:
+            fill = zero_fill_gbs(buf)
+            extra["d32_live_prefix"].update(write_only_fill_gbs=fill, frac_of_write_only_fill=extra["d32_live_prefix"]["hbm_gbs"] / fill)
+        del buf
         # contract I: persistent fp32 buffer with both views of every env, updated in place
         if out is not None:
             del out
@@ -494,7 +507,7 @@ def main():
         rec_bytes = 42 + 64 + 96 + 96 + 192 + 8
         peak_gbs, _ = measured_peak()
         selfplay = {"steps_per_s": k_sp * n_sp * world / (ms_sp * 1e-3), "envs_per_gpu": n_sp, "ms_per_step": ms_sp / k_sp,
-                    "policy": "MLP 2492(+4 zero pad)-1024-1024-18 (bf16, torch), masked softmax sampling fused on device (k_sample_policy)",
+                    "policy": "MLP 2492(+4 zero pad)-1024-1024-18 (bf16, torch; the encoder writes and the first layer reads the 1728 live columns), masked softmax sampling fused on device (k_sample_policy)",
                     "recording": "NFSP reservoir (%d) + DQN replay (%d) kept by the step kernel as packed records (coup_vec_step_record)" % (cap_res, cap_rb),
                     "recording_step": {"kernel": "k_reservoir_claim + k_step_record", "us_per_launch": 1e3 * ms_rec / 50,
                                        "plain_k_step_us": 1e3 * ms_plain / 50, "bytes_per_env": rec_bytes,

@@ -32,6 +32,12 @@ extern "C" {
 #define COUP_MAX_GAME_LENGTH 90
 #define COUP_MAX_CHANCE_NODES_IN_HISTORY 45
 #define COUP_INFO_STATE_SIZE 2492   /* player2 p1_cards20 p2_cards20 cur_move_player2 cards_state16 coins2 history135x18 */
+/* The LIVE PREFIX of an info-state row. A game has at most 91 moves, chance nodes included (MaxGameLength 90, coup.h:219;
+ * terminal at move_number_ > 90, coup.cc:990), while the tensor reserves 135 history rows (coup.cc:1104-1116): elements
+ * >= 62 + 18 * 91 = 1700 are zero in every reachable state. Passing this value as `row_stride` to a *_strided / gather /
+ * records entry point writes rows of 1728 elements (1700 rounded up to 64): the same values as elements [0, 1728) of the
+ * full row, 31 % fewer bytes, nothing lost. */
+#define COUP_LIVE_INFO_STATE_SIZE 1728
 #define COUP_OBSERVATION_SIZE 98    /* ... same 62-float head ... last_action2x18 */
 #define COUP_MIN_UTILITY (-2)
 #define COUP_MAX_UTILITY 2
@@ -294,7 +300,9 @@ int coup_vec_observation_tensor_gather(coup_vec_env* env, const uint32_t* d_env_
                                        void* d_out, void* stream);
 /* Same tensors with a padded row stride (in elements, a multiple of 4, >= 2492): elements
  * [2492, row_stride) of every row are written as zeros. row_stride 2496 keeps the consumer's first GEMM on
- * its aligned (fast) path: K = 2492 is not a multiple of 8 and costs a bf16 cuBLAS GEMM 5.6x on B200. */
+ * its aligned (fast) path: K = 2492 is not a multiple of 8 and costs a bf16 cuBLAS GEMM 5.6x on B200.
+ * row_stride == COUP_LIVE_INFO_STATE_SIZE writes the live prefix of every row instead (see above); every entry point
+ * that takes a row_stride accepts it, except coup_vec_rollout_incremental. */
 int coup_vec_information_state_tensor_strided(coup_vec_env* env, int player, int dtype, void* d_out,
                                               uint32_t row_stride, void* stream);
 int coup_vec_rollout_strided(coup_vec_env* env, int n_steps, int encode_player, int dtype, void* d_tensor_out,

@@ -16,6 +16,7 @@ MAX_CHANCE_OUTCOMES = 5
 MAX_GAME_LENGTH = 90
 MAX_CHANCE_NODES_IN_HISTORY = 45
 INFO_STATE_SIZE = 2492
+LIVE_INFO_STATE_SIZE = 1728      # COUP_LIVE_INFO_STATE_SIZE: elements >= 62 + 18 * 91 = 1700 are always zero
 OBSERVATION_SIZE = 98
 MIN_UTILITY = -2.0
 MAX_UTILITY = 2.0

@@ -85,10 +85,13 @@ bool valid_dtype(int d) { return d == COUP_DTYPE_F32 || d == COUP_DTYPE_U8 || d 
 // not, and a misaligned cp.async.bulk is a sticky fault. Such outputs take the plain-store encoder, which needs only the
 // alignment of its four-element store unit (16 / 8 / 4 bytes for f32 / bf16 / u8); below that the call is rejected.
 bool use_staged_encoder(const coup_vec_env* env, uint32_t stride, const void* d_out) {
-  return (env->opts.flags & COUP_FLAG_PLAIN_STORE_ENCODER) == 0 && (stride == COUP_INFO_STATE_SIZE || stride == 2496u) &&
+  return (env->opts.flags & COUP_FLAG_PLAIN_STORE_ENCODER) == 0 &&
+         (stride == COUP_INFO_STATE_SIZE || stride == 2496u || stride == COUP_LIVE_INFO_STATE_SIZE) &&
          reinterpret_cast<uintptr_t>(d_out) % 16u == 0;
 }
-bool valid_stride(uint32_t stride) { return stride >= COUP_INFO_STATE_SIZE && stride % 4u == 0 && stride <= 4096u; }
+// Full rows (optionally padded), or the live prefix of every row (COUP_LIVE_INFO_STATE_SIZE: see coup_b200.h).
+bool valid_full_stride(uint32_t stride) { return stride >= COUP_INFO_STATE_SIZE && stride % 4u == 0 && stride <= 4096u; }
+bool valid_stride(uint32_t stride) { return stride == COUP_LIVE_INFO_STATE_SIZE || valid_full_stride(stride); }
 size_t unit_bytes(int dtype) { return dtype == COUP_DTYPE_F32 ? 16u : dtype == COUP_DTYPE_BF16 ? 8u : 4u; }
 bool aligned_for(int dtype, const void* p) { return reinterpret_cast<uintptr_t>(p) % unit_bytes(dtype) == 0; }
 const char* kMisaligned = "tensor output must be aligned to 16 (f32) / 8 (bf16) / 4 (u8) bytes";
@@ -594,7 +597,7 @@ int coup_vec_rollout(coup_vec_env* env, int n_steps, int encode_player, int dtyp
 }
 
 int coup_vec_rollout_incremental(coup_vec_env* env, int n_steps, int dtype, void* d_buf, uint32_t row_stride, void* stream) {
-  if (!env || n_steps < 0 || !d_buf || !valid_dtype(dtype) || !valid_stride(row_stride))
+  if (!env || n_steps < 0 || !d_buf || !valid_dtype(dtype) || !valid_full_stride(row_stride))
     return fail(COUP_ERR_INVALID_ARG, "coup_vec_rollout_incremental: bad arguments");
   if (reinterpret_cast<uintptr_t>(d_buf) % 32u != 0)   // the kernel writes whole 32-byte sectors
     return fail(COUP_ERR_INVALID_ARG, "coup_vec_rollout_incremental: the buffer must be 32-byte aligned");

@@ -23,9 +23,10 @@ from ._lib import INFO_STATE_SIZE, NUM_DISTINCT_ACTIONS, PLAYER_CURRENT, PLAYER_
 PADDED_INFO_STATE_SIZE = 2496
 # History rows 91..134 of the info-state tensor can never be set (a game has at most 91 moves, chance nodes included:
 # MaxGameLength 90, coup.h:219, termination at move_number_ > 90, coup.cc:990; the tensor reserves 135 rows, coup.cc:1104-1116),
-# so elements >= 62 + 18 * 91 = 1700 are always zero and the first layer's product over them is exactly zero. On the
-# inference path the first GEMM therefore runs over the first 1728 columns only (1700 rounded up to 64 elements).
-LIVE_INFO_STATE_SIZE = 1728
+# so elements >= 62 + 18 * 91 = 1700 are always zero and the first layer's product over them is exactly zero. The first
+# GEMM therefore runs over the first 1728 columns only (1700 rounded up to 64 elements), and the self-play loop asks the
+# encoder for exactly those columns (COUP_LIVE_INFO_STATE_SIZE rows: 31 % fewer bytes written and read back).
+from ._lib import LIVE_INFO_STATE_SIZE  # noqa: E402
 from .vector_env import CoupVectorEnv
 
 
@@ -47,18 +48,35 @@ class MLPPolicy(nn.Module):
         layers.append(nn.Linear(prev, output_size))
         self.net = nn.Sequential(*layers)
 
+    def _first_layer(self, x):
+        """(input, weight) of the first layer. An info-state input narrower than the weight is a live prefix (or the
+        unpadded row): the weight is cut to its width -- the columns dropped only ever multiply zeros. On the inference
+        path a full-width input is cut to the live prefix as well."""
+        w = self.net[0].weight
+        if self.input_size != INFO_STATE_SIZE:
+            return x, w
+        k = x.shape[-1]
+        if k > LIVE_INFO_STATE_SIZE and not torch.is_grad_enabled():
+            k = LIVE_INFO_STATE_SIZE
+        if k < LIVE_INFO_STATE_SIZE:
+            raise ValueError(f"info-state rows must have at least {LIVE_INFO_STATE_SIZE} columns")
+        return x[..., :k], w[:, :min(k, w.shape[1])]          # views: lda / ldb stay the row strides
+
     def forward(self, info_state):
+        x, w = self._first_layer(info_state)
+        layers = list(self.net)
         if torch.is_grad_enabled() or not info_state.is_cuda or info_state.dim() != 2:
-            return self.net(info_state)
+            x = torch.nn.functional.linear(x, w, layers[0].bias)
+            for layer in layers[1:]:
+                x = layer(x)
+            return x
         # inference on the device: bias + ReLU run in the GEMM epilogue (cuBLASLt) instead of as two more
         # passes over the [num_envs, hidden] activations
-        x, layers = info_state, list(self.net)
         i = 0
         while i < len(layers):
             lin = layers[i]
-            w = lin.weight
-            if i == 0 and getattr(self, "input_size", None) == INFO_STATE_SIZE and x.shape[1] > LIVE_INFO_STATE_SIZE:
-                x, w = x[:, :LIVE_INFO_STATE_SIZE], w[:, :LIVE_INFO_STATE_SIZE]     # views: lda / ldb stay the row stride
+            if i > 0:
+                w = lin.weight
             if i + 1 < len(layers) and isinstance(layers[i + 1], nn.ReLU):
                 x = torch._addmm_activation(lin.bias, x, w.t())
                 i += 2
@@ -207,6 +225,9 @@ _BUCKET_K = tuple(min(PADDED_INFO_STATE_SIZE, -(-(62 + 18 * m) // 64) * 64) for 
 class _Tail:
     """The layers after the first Linear+ReLU of an MLPPolicy, for MLPPolicy.forward's fused path."""
 
+    input_size = None                      # not an info-state input: the first layer takes it as it is
+    _first_layer = MLPPolicy._first_layer
+
     def __init__(self, net):
         self.net = net
 
@@ -265,6 +286,9 @@ class SelfPlayDataGen:
             policy = MLPPolicy(padded_input_size=PADDED_INFO_STATE_SIZE)
         self.policy = policy.to(device=dev, dtype=tensor_dtype).eval()
         width = getattr(policy, "padded_input_size", INFO_STATE_SIZE)
+        if (isinstance(policy, MLPPolicy) and policy.input_size == INFO_STATE_SIZE and not self.bucketed_first_layer
+                and not (reservoir_capacity and torch_reservoir)):
+            width = LIVE_INFO_STATE_SIZE       # the encoder writes the live prefix of every row, the first GEMM reads it
         self.info_state = torch.zeros((num_envs, width), dtype=tensor_dtype, device=dev)
         self.action_probs = torch.empty((num_envs, NUM_DISTINCT_ACTIONS), dtype=torch.float32, device=dev)
         self.actions = torch.empty(num_envs, dtype=torch.uint8, device=dev)

@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import (DTYPE_BF16, DTYPE_F32, DTYPE_U8, FLAG_AUTO_RESET, HISTORY_WORDS, INFO_STATE_SIZE,
+from ._lib import (DTYPE_BF16, DTYPE_F32, DTYPE_U8, FLAG_AUTO_RESET, HISTORY_WORDS, INFO_STATE_SIZE, LIVE_INFO_STATE_SIZE,
                    NUM_DISTINCT_ACTIONS, OBSERVATION_SIZE, PLAYER_0, PLAYER_1, PLAYER_BOTH, PLAYER_CURRENT,
                    RECORD_WORDS, STATE_WORDS, STATS_LEN, TERMINAL_PLAYER_ID, CoupError, check)
 
@@ -107,9 +107,11 @@ class CoupVectorEnv:
 
     @staticmethod
     def _row_stride(out):
-        """Row stride in elements of a [rows, >=2492] output (2496 = padded, GEMM-aligned rows)."""
-        if out.dim() != 2 or out.stride(1) != 1 or out.shape[1] < INFO_STATE_SIZE:
-            raise ValueError("info-state output must be [rows, >=2492] with unit inner stride")
+        """Row stride in elements of a [rows, >=2492] output (2496 = padded, GEMM-aligned rows), or of a contiguous
+        [rows, 1728] output that receives the live prefix of every row (COUP_LIVE_INFO_STATE_SIZE)."""
+        live = out.dim() == 2 and out.shape[1] == LIVE_INFO_STATE_SIZE and out.stride(0) == LIVE_INFO_STATE_SIZE
+        if out.dim() != 2 or out.stride(1) != 1 or (out.shape[1] < INFO_STATE_SIZE and not live):
+            raise ValueError("info-state output must be [rows, >=2492] (or contiguous [rows, 1728]) with unit inner stride")
         unit = 4 * out.element_size()          # the encoders store four elements at a time (coup_b200.h, "Alignment")
         if out.data_ptr() % unit:
             raise ValueError(f"info-state output must be {unit}-byte aligned (got a view at offset {out.data_ptr() % unit})")

@@ -401,6 +401,50 @@ def test_padded_row_stride(plain, dtype, width):
 
 @pytest.mark.parametrize("plain", [False, True], ids=["staged-tma", "plain-stores"])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.uint8])
+def test_live_prefix_rows(plain, dtype):
+    """row_stride == COUP_LIVE_INFO_STATE_SIZE: rows of 1728 elements that equal elements [0, 1728) of the full rows, and the
+    columns they drop are zero in every state -- steered 91-move games included. Every entry point that takes a stride:
+    the encoders (all envs, gathered, from the finished-episode ring) and the fused rollout; guard bands around the
+    narrower output; the incremental contract refuses it."""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts"))
+    from replay_check import steering_policy
+    LIVE = _lib.LIVE_INFO_STATE_SIZE
+    assert LIVE >= 62 + 18 * 91 and LIVE % 64 == 0
+    n = 4096 + 5
+    env = CoupVectorEnv(n, seed=21, auto_reset=False, plain_store_encoder=plain)
+    for _ in range(100):
+        env.step(steering_policy(env))
+    assert int(env.move_numbers().max()) == 91
+    for sel in (_lib.PLAYER_CURRENT, _lib.PLAYER_BOTH):
+        rows = n * (2 if sel == _lib.PLAYER_BOTH else 1)
+        dense = env.information_state_tensor(sel, dtype=dtype)
+        assert float(dense[:, 62 + 18 * 91:].float().abs().sum()) == 0.0
+        assert float(dense[:, 62 + 18 * 90: 62 + 18 * 91].float().abs().sum()) > 0.0     # history row 90 is in use
+        guarded = torch.full((rows + 2, LIVE), 7, dtype=dtype, device=env.device)
+        live = guarded[1:rows + 1]
+        env.information_state_tensor(sel, out=live)
+        assert torch.equal(live, dense[:, :LIVE])
+        assert (guarded[0] == 7).all() and (guarded[rows + 1] == 7).all()
+    ids = torch.randperm(n, device=env.device)[:777].to(torch.int32)
+    got = env.information_state_tensor_gather(ids, _lib.PLAYER_BOTH, out=torch.empty((2 * 777, LIVE), dtype=dtype, device=env.device))
+    assert torch.equal(got, env.information_state_tensor_gather(ids, _lib.PLAYER_BOTH, dtype=dtype)[:, :LIVE])
+    # fused rollout into live-prefix rows, auto-reset on
+    a = CoupVectorEnv(n, seed=9, auto_reset=True, plain_store_encoder=plain)
+    b = CoupVectorEnv(n, seed=9, auto_reset=True, plain_store_encoder=plain)
+    a.rollout(30); b.rollout(30)
+    live = torch.full((n, LIVE), 7, dtype=dtype, device=a.device)
+    a.rollout(1, _lib.PLAYER_CURRENT, out=live)
+    b.rollout(1)
+    assert torch.equal(live, b.information_state_tensor(_lib.PLAYER_CURRENT, dtype=dtype)[:, :LIVE])
+    with pytest.raises(_lib.CoupError):
+        a.rollout_incremental(1, torch.zeros((2 * n, LIVE), dtype=dtype, device=a.device))
+    with pytest.raises(ValueError):
+        a.information_state_tensor(_lib.PLAYER_0, out=torch.empty((n, 2496), dtype=dtype, device=a.device)[:, :LIVE])
+
+
+@pytest.mark.parametrize("plain", [False, True], ids=["staged-tma", "plain-stores"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.uint8])
 @pytest.mark.parametrize("n", [1, 3, 32, 35, 257, 1023])
 def test_encoders_stay_inside_their_output(plain, dtype, n):
     """compute-sanitizer is closed on this pool, so out-of-bounds writes are hunted with guard bands: the

@@ -1,5 +1,6 @@
 """CPU tests of the host-side pieces of the self-play data generator."""
 import numpy as np
+import pytest
 import torch
 
 from open_spiel_coup_b200.selfplay import MLPPolicy, ReservoirBuffer, masked_action_probs
@@ -29,6 +30,30 @@ def test_mlp_policy_shape_follows_thesis_flagfile():
     assert net(torch.zeros(3, 2492)).shape == (3, 18)
     padded = MLPPolicy(padded_input_size=2496)          # GEMM-aligned input rows; pad columns are always zero
     assert padded.net[0].in_features == 2496 and padded(torch.zeros(3, 2496)).shape == (3, 18)
+
+
+def test_mlp_policy_accepts_the_live_prefix():
+    """Rows cut to the live prefix (1728 columns: everything beyond element 1700 is always zero) give the same logits and
+    the same gradients as full rows; anything narrower is refused."""
+    from open_spiel_coup_b200.selfplay import LIVE_INFO_STATE_SIZE
+    torch.manual_seed(0)
+    for pad in (None, 2496):
+        net = MLPPolicy(hidden_sizes=(64, 32), padded_input_size=pad)
+        x = torch.zeros(7, net.padded_input_size)
+        x[:, :1700] = (torch.rand(7, 1700) < 0.02).float()
+        full = net.net(x)
+        assert torch.allclose(net(x), full, atol=1e-6)
+        assert torch.allclose(net(x[:, :LIVE_INFO_STATE_SIZE].contiguous()), full, atol=1e-6)
+        with torch.no_grad():
+            assert torch.allclose(net(x), full, atol=1e-6)            # inference path: cut to the live prefix
+        net.zero_grad()
+        net(x[:, :LIVE_INFO_STATE_SIZE].contiguous()).sum().backward()
+        g_live = net.net[0].weight.grad.clone()
+        net.zero_grad()
+        net.net(x).sum().backward()
+        assert torch.allclose(g_live, net.net[0].weight.grad, atol=1e-6)
+        with pytest.raises(ValueError):
+            net(torch.zeros(2, 1000))
 
 
 def test_reservoir_fills_then_samples_uniformly():
