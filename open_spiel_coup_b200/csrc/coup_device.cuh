@@ -118,11 +118,6 @@ COUP_FN uint32_t hand_face_up_count(uint32_t h) {
 // Insert a card keeping the order. Requires a free slot. The position is the number of slots <= key, counted for all
 // four slots at once: the nibbles are spread to bytes, and (0x10 + key - slot) keeps bit 4 exactly when slot <= key.
 COUP_FN uint32_t hand_insert(uint32_t h, uint32_t key) {
-#ifdef COUP_AB_OLD_INSERT
-  uint32_t pos = (hand_slot(h, 0) <= key) + (hand_slot(h, 1) <= key) + (hand_slot(h, 2) <= key) + (hand_slot(h, 3) <= key);
-  uint32_t sh0 = 4 * pos;
-  return ((h & ((1u << sh0) - 1u)) | (key << sh0) | ((h >> sh0) << (sh0 + 4))) & 0xFFFFu;
-#endif
   uint32_t x = (h | (h << 8)) & 0x00FF00FFu;
   x = (x | (x << 4)) & 0x0F0F0F0Fu;                                   // byte i = slot i
   const uint32_t le = ((key * 0x01010101u + 0x10101010u) - x) & 0x10101010u;
@@ -152,16 +147,9 @@ COUP_FN bool is_terminal(const Env& s) {
   // A player is out when he holds at least two cards and none of them is face down (995-999). Empty slots sort last and
   // have bit 0 set, so "no face-down card" is bit 0 of all four slots, and "at least two cards" is slot 1 not empty
   // (bits 2 and 3 of a card slot are never both set: values are 0..4).
-#ifdef COUP_AB_OLD_TERMINAL
-  const uint32_t h0 = pw_hand(s.p[0]), h1 = pw_hand(s.p[1]);
-  const bool alive0 = hand_count(h0) < 2 || hand_down_mask(h0) != 0;
-  const bool alive1 = hand_count(h1) < 2 || hand_down_mask(h1) != 0;
-  return c_moves(s.c) > kMaxGameLength || !(alive0 && alive1);
-#else
   const bool out0 = (s.p[0] & 0x1111u) == 0x1111u && (s.p[0] & 0xC0u) != 0xC0u;
   const bool out1 = (s.p[1] & 0x1111u) == 0x1111u && (s.p[1] & 0xC0u) != 0xC0u;
   return c_moves(s.c) > kMaxGameLength || out0 || out1;
-#endif
 }
 
 // LegalLoseCardActions, 811-822: slot 0 / slot 1 face down -> bit kLoseCard1 / kLoseCard2.
@@ -425,17 +413,11 @@ COUP_FN uint32_t apply_chance(Env& s, uint32_t card) {
 // 0x01010101 leaves byte c = deck_[0] + .. + deck_[c], and (0x10 + r - run_c) keeps bit 4 exactly when run_c <= r
 // (r <= 14, run_c <= 15: no borrow between bytes).
 COUP_FN uint32_t sample_card_g(uint32_t g, uint32_t u) {
-#ifdef COUP_AB_OLD_SAMPLE_CARD
-  const uint32_t run = ((g & 0xFFFFFu) * 0x11111u) & 0xFFFFFu;       // nibble c = deck_[0] + .. + deck_[c]
-  const uint32_t r = umulhi32(u, run >> 16);
-  return (r >= (run & 15u)) + (r >= ((run >> 4) & 15u)) + (r >= ((run >> 8) & 15u)) + (r >= ((run >> 12) & 15u));
-#else
   uint32_t x = ((g & 0xFFFFu) | (g << 8)) & 0x00FF00FFu;
   x = (x | (x << 4)) & 0x0F0F0F0Fu;                                   // byte c = deck_[c], c < 4
   const uint32_t run = x * 0x01010101u;
   const uint32_t r = umulhi32(u, (run >> 24) + ((g >> 16) & 15u));
   return popc32(((r * 0x01010101u + 0x10101010u) - run) & 0x10101010u);
-#endif
 }
 COUP_FN uint32_t sample_card(const Env& s, uint32_t u) { return sample_card_g(s.g, u); }
 
@@ -486,21 +468,9 @@ COUP_FN uint32_t pick(const uint4& r, int k) {
 // k-th (0-based) set bit of a mask with more than k bits set, k <= 7 (a Coup state has at most 7 legal actions, a deck
 // 5 card types): clear the lowest set bit k times, without a loop-carried branch.
 COUP_FN uint32_t kth_set_bit(uint32_t mask, uint32_t k) {
-#ifdef COUP_AB_KTH_BINARY
-  uint32_t pos = 0;
-#pragma unroll
-  for (uint32_t width = 16; width > 0; width >>= 1) {
-    const uint32_t low = popc32((mask >> pos) & ((1u << width) - 1u));
-    const bool up = k >= low;
-    k -= up ? low : 0u;
-    pos += up ? width : 0u;
-  }
-  return pos;
-#else
 #pragma unroll
   for (uint32_t i = 0; i < 7; ++i) mask = i < k ? mask & (mask - 1u) : mask;
   return ffs32(mask) - 1u;
-#endif
 }
 
 // Uniform legal action (benchmark_game.cc:96-99) from one uniform 32-bit word.

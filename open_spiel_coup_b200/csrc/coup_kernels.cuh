@@ -230,11 +230,7 @@ __device__ __forceinline__ StepResult step_env(Env& s, HistRow row, uint32_t act
       // Re-deal in place with the closed-form deal, computed by the whole warp. An episode that ends AT the action has
       // used none of the three deal words of its step block, so the four cards come from them: y serves two draws
       // (floor(y * 15 / 2^32), then its remainder y * 15 mod 2^32, again uniform), z and w one each.
-#ifdef COUP_AB_RESET_BLOCK
-      const uint4 rr = env_random(A.seed, genv, step, 1);
-#else
       const uint4 rr = make_uint4(rnd.y, rnd.y * 15u, rnd.z, rnd.w);
-#endif
       uint32_t fresh_codes;
       const Env fresh = dealt_initial_state(rr, fresh_codes);
       const bool redeal = fin && auto_reset;
@@ -249,7 +245,6 @@ __device__ __forceinline__ StepResult step_env(Env& s, HistRow row, uint32_t act
     // The deals that follow the action (at most three: Exchange after a lost challenge). Deals never change who is
     // alive, so inside the loop only the move cap (coup.cc:990) can end the game; a freshly dealt or finished env has
     // nothing pending.
-#ifndef COUP_AB_OLD_DEAL_LOOP
     // All deals queued by a player action go to ONE player (apply_player_action: bit 28), so the loop works on that
     // player's hand and the deck only; queue count, chance flag, move number and the player word are settled once after
     // it. nd = deals this lane makes: the whole queue, cut short by the move cap.
@@ -279,24 +274,6 @@ __device__ __forceinline__ StepResult step_env(Env& s, HistRow row, uint32_t act
     s.c += nd;                                                             // ++move_number_ per deal
     n_codes += nd;
     r.chance_moves += nd;
-#else
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const bool pend = go && g_chance(s.g) && c_moves(s.c) <= kMaxGameLength;
-      if (!__any_sync(kFull, pend)) break;
-      uint32_t card = sample_card(s, k == 0 ? rnd.y : k == 1 ? rnd.z : rnd.w);
-      if (forced != nullptr) {
-        const uint32_t f = pend ? forced[k] : 0xFFu;   // lanes without an env must not touch the array
-        card = (f < 5u && g_deck(s.g, f) != 0) ? f : card;
-      }
-      Env t2 = s;
-      const uint32_t code = apply_chance(t2, card);
-      s.p[0] = pend ? t2.p[0] : s.p[0]; s.p[1] = pend ? t2.p[1] : s.p[1]; s.g = pend ? t2.g : s.g; s.c = pend ? t2.c : s.c;
-      codes |= pend ? code << (5u * n_codes) : 0u;
-      n_codes += pend ? 1u : 0u;
-      r.chance_moves += pend ? 1u : 0u;
-    }
-#endif
     if (any_fin && fin) ring_write(A, ticket, e, r.final_state, row.work, step, r.truncated);   // before word 0 is re-dealt
     if (n_codes) history_commit(row.work, first, codes, n_codes, row.mirror);
     if (go && !fin && c_moves(s.c) > kMaxGameLength) {
@@ -1794,11 +1771,7 @@ k_rollout_ws(EnvArrays A, uint64_t step, int player_sel, T* __restrict__ out, ui
           store_env(A.state + e, s);
           write_outputs(A, e, r);
           fill_record(rec, s, rec, player_sel);
-#ifdef COUP_AB_WS_NOSTATS
-          (void)r;
-#else
           account(st, r, true);
-#endif
         }
       }
       __threadfence_block();
