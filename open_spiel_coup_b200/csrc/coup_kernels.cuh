@@ -50,6 +50,22 @@ __device__ __forceinline__ Env load_env(const uint4* p) {
 }
 __device__ __forceinline__ void store_env(uint4* p, const Env& s) { *p = make_uint4(s.p[0], s.p[1], s.g, s.c); }
 
+// The fused step kernels issue ALL the global loads of an env at once -- its state word and its 64-byte history row,
+// the row straight into the env's encoder record in shared memory -- and never load again: the step updates the row in
+// the record and writes the changed words through to HBM. Next to a saturated store stream every dependent global round
+// trip of the rules costs microseconds (scripts/ws_debug_probe.py), so the rules phase is ONE round trip, not four.
+__device__ __forceinline__ Env load_env_and_row(const EnvArrays& A, uint32_t e, uint32_t* rec) {
+  const uint4 sv = A.state[e];
+  const uint4* g4 = reinterpret_cast<const uint4*>(A.history + static_cast<size_t>(e) * 16u);
+  const uint4 h0 = g4[0], h1 = g4[1], h2 = g4[2], h3 = g4[3];
+  rec[0] = h0.x; rec[1] = h0.y; rec[2] = h0.z; rec[3] = h0.w; rec[4] = h1.x; rec[5] = h1.y; rec[6] = h1.z; rec[7] = h1.w;
+  rec[8] = h2.x; rec[9] = h2.y; rec[10] = h2.z; rec[11] = h2.w; rec[12] = h3.x; rec[13] = h3.y; rec[14] = h3.z; rec[15] = h3.w;
+  Env s;
+  s.p[0] = sv.x; s.p[1] = sv.y; s.g = sv.z; s.c = sv.w;
+  return s;
+}
+
+
 // ---- statistics: warp ballots -> shared counters -> one global atomic per counter per block ------
 struct BlockStats {
   uint32_t* sm;  // [COUP_STATS_LEN] in shared memory
@@ -436,11 +452,15 @@ k_step(EnvArrays A, const uint8_t* __restrict__ actions, const uint8_t* __restri
   BlockStats st;
   st.init(s_stats);
   const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  // the env's history row is loaded with its state word, in one round trip, into shared memory (odd pitch: conflict-free);
+  // the step updates it there and writes the changed words through to HBM
+  __shared__ uint32_t s_row[kBlockThreads][kHistoryWords + 1];
   const uint32_t action = e < A.n ? actions[e] : 0xFFu;
   const bool active = action != 0xFFu;   // 0xFF: this env sits the step out, outputs keep their values
   Env s = {};
-  if (active) s = load_env(A.state + e);
-  const StepResult r = step_env<false>(s, global_row(A.history + static_cast<size_t>(e) * kHistoryWords), action,
+  uint32_t* const row = s_row[threadIdx.x];
+  if (active) s = load_env_and_row(A, e, row);
+  const StepResult r = step_env<false>(s, HistRow{row, A.history + static_cast<size_t>(e) * kHistoryWords}, action,
                                        forced ? forced + static_cast<size_t>(e) * 4 : nullptr, A, e, step, active);
   if (active) {
     store_env(A.state + e, s);
@@ -1170,21 +1190,6 @@ __device__ __forceinline__ void fill_record(uint32_t* rec, const Env& s, const u
     rec[18] = static_cast<uint32_t>(mb); rec[19] = static_cast<uint32_t>(mb >> 32);
   }
   rec[20] = c_moves(s.c) | (pw_coins(s.p[0]) << 8) | (pw_coins(s.p[1]) << 16) | (obs_a << 24) | (obs_b << 25);
-}
-
-// The fused step kernels issue ALL the global loads of an env at once -- its state word and its 64-byte history row,
-// the row straight into the env's encoder record in shared memory -- and never load again: the step updates the row in
-// the record and writes the changed words through to HBM. Next to a saturated store stream every dependent global round
-// trip of the rules costs microseconds (scripts/ws_debug_probe.py), so the rules phase is ONE round trip, not four.
-__device__ __forceinline__ Env load_env_and_row(const EnvArrays& A, uint32_t e, uint32_t* rec) {
-  const uint4 sv = A.state[e];
-  const uint4* g4 = reinterpret_cast<const uint4*>(A.history + static_cast<size_t>(e) * kHistoryWords);
-  const uint4 h0 = g4[0], h1 = g4[1], h2 = g4[2], h3 = g4[3];
-  rec[0] = h0.x; rec[1] = h0.y; rec[2] = h0.z; rec[3] = h0.w; rec[4] = h1.x; rec[5] = h1.y; rec[6] = h1.z; rec[7] = h1.w;
-  rec[8] = h2.x; rec[9] = h2.y; rec[10] = h2.z; rec[11] = h2.w; rec[12] = h3.x; rec[13] = h3.y; rec[14] = h3.z; rec[15] = h3.w;
-  Env s;
-  s.p[0] = sv.x; s.p[1] = sv.y; s.g = sv.z; s.c = sv.w;
-  return s;
 }
 
 // Value of info-state element `p` (0..2491) of a record/view. Small non-negative integer.
