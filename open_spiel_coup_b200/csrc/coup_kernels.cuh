@@ -1626,30 +1626,41 @@ k_rollout(EnvArrays A, uint64_t step, int player_sel, T* __restrict__ out, uint3
   st.flush(A.stats);
 }
 
-// Env-only rollout of `n_steps` steps in ONE launch: envs are independent, so a thread keeps its env in registers across
-// steps (one 16-byte load and store, one set of outputs, one launch instead of n_steps of each); the history row and
-// the statistics are updated every step exactly as k_rollout<T, false> does, and step k uses Philox counter step + k.
+// Env-only rollout of `n_steps` steps in ONE launch: envs are independent, so a thread keeps its env in registers and its
+// history row in shared memory across steps (one load and one store of each per launch, one set of outputs, one launch
+// instead of n_steps of each); the statistics are updated every step exactly as k_rollout<T, false> does, and step k uses
+// Philox counter step + k. With the row in shared memory no step waits for a global load: the merge of new move codes
+// into the current word and the copy of a finished episode's log to the ring read it there.
+constexpr int kEnvRowPitch = 20;   // words: rows stay 16-byte aligned (vector access), quarter-warps conflict-free
 __global__ void __launch_bounds__(kBlockThreads, COUP_ENV_BLOCKS)
 k_rollout_env_multi(EnvArrays A, uint64_t step, int n_steps) {
   __shared__ uint32_t s_stats[COUP_STATS_LEN];
+  __shared__ __align__(16) uint32_t s_row[kBlockThreads][kEnvRowPitch];
   BlockStats st;
   st.init(s_stats);
   const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
   const bool active = e < A.n;
   Env s = {};
-  uint32_t* hist_row = A.history + static_cast<size_t>(active ? e : 0) * kHistoryWords;
-  if (active) s = load_env(A.state + e);
+  uint4* const hist_row = reinterpret_cast<uint4*>(A.history + static_cast<size_t>(active ? e : 0) * kHistoryWords);
+  uint4* const row = reinterpret_cast<uint4*>(s_row[threadIdx.x]);
+  if (active) {
+    const uint4 sv = A.state[e];
+    const uint4 h0 = hist_row[0], h1 = hist_row[1], h2 = hist_row[2], h3 = hist_row[3];
+    row[0] = h0; row[1] = h1; row[2] = h2; row[3] = h3;
+    s.p[0] = sv.x; s.p[1] = sv.y; s.g = sv.z; s.c = sv.w;
+  }
   StepResult r = {};
   // the mask of the loaded state; from then on every step hands the next one its mask
   r.legal = is_terminal(s) ? 0u : (g_chance(s.g) ? legal_mask_chance(s) : legal_mask_decision(s));
   StatAcc acc;
   acc.clear();
   for (int k = 0; k < n_steps; ++k) {                       // n_steps <= StatAcc::kMaxAdds (the host launches in chunks of 64)
-    r = step_env<true, true>(s, global_row(hist_row), 0, nullptr, A, e, step + static_cast<uint64_t>(k), active, r.legal);
+    r = step_env<true, true>(s, global_row(s_row[threadIdx.x]), 0, nullptr, A, e, step + static_cast<uint64_t>(k), active, r.legal);
     acc.add(r, active);
   }
   acc.flush(st);
   if (active) {
+    hist_row[0] = row[0]; hist_row[1] = row[1]; hist_row[2] = row[2]; hist_row[3] = row[3];
     store_env(A.state + e, s);
     write_outputs(A, e, r);
   }
