@@ -446,7 +446,10 @@ k_reset(EnvArrays A, const uint8_t* __restrict__ mask, const uint8_t* __restrict
 }
 
 // ---- step with caller-provided actions --------------------------------------------------------------
-__global__ void __launch_bounds__(kBlockThreads, 4)
+#ifndef COUP_STEP_BLOCKS
+#define COUP_STEP_BLOCKS 5   // resident CTAs per SM: 61.5 / 57.4 / 55.5 / 57.5 us per 2^20 envs (with k_sample_uniform) at 3 / 4 / 5 / 6
+#endif
+__global__ void __launch_bounds__(kBlockThreads, COUP_STEP_BLOCKS)
 k_step(EnvArrays A, const uint8_t* __restrict__ actions, const uint8_t* __restrict__ forced, uint64_t step) {
   __shared__ uint32_t s_stats[COUP_STATS_LEN];
   BlockStats st;
