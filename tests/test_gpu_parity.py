@@ -437,6 +437,16 @@ def test_live_prefix_rows(plain, dtype):
     a.rollout(1, _lib.PLAYER_CURRENT, out=live)
     b.rollout(1)
     assert torch.equal(live, b.information_state_tensor(_lib.PLAYER_CURRENT, dtype=dtype)[:, :LIVE])
+    # rows decoded from packed records (the finished-episode ring): same prefix
+    c = CoupVectorEnv(2048, seed=4, auto_reset=True, finished_ring=1 << 14, plain_store_encoder=plain)
+    c.rollout(40)
+    recs, dropped = c.finished_drain()
+    assert dropped == 0 and len(recs) > 1000
+    dev_recs = torch.as_tensor(recs.view(np.int32)).to(c.device)
+    full = c.records_information_state_tensor(dev_recs, None, _lib.PLAYER_BOTH, dtype=dtype)
+    live = c.records_information_state_tensor(dev_recs, None, _lib.PLAYER_BOTH,
+                                              out=torch.full((2 * len(recs), LIVE), 7, dtype=dtype, device=c.device))
+    assert torch.equal(live, full[:, :LIVE]) and float(full[:, LIVE:].float().abs().sum()) == 0.0
     with pytest.raises(_lib.CoupError):
         a.rollout_incremental(1, torch.zeros((2 * n, LIVE), dtype=dtype, device=a.device))
     with pytest.raises(ValueError):
