@@ -12,7 +12,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcoup_b200.so")
 SOURCES = ["coup_capi.cu"]
 HOST_SOURCES = ["coup_host_policy.cc"]   # host compiler only (AVX2 path picked at run time)
-HEADERS = ["coup_host_policy.cc", "coup_device.cuh", "coup_kernels.cuh", os.path.join("..", "..", "include", "coup_b200.h")]
+HEADERS = ["coup_host_policy.cc"] + sorted(f for f in os.listdir(CSRC) if f.endswith(".cuh")) + [os.path.join("..", "..", "include", "coup_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",

@@ -40,7 +40,7 @@ def functions(path):
     return out
 
 
-src = {f: functions(os.path.join(ROOT, "open_spiel_coup_b200", "csrc", f)) for f in ("coup_device.cuh", "coup_kernels.cuh")}
+src = {f: functions(os.path.join(ROOT, "open_spiel_coup_b200", "csrc", f)) for f in sorted(os.listdir(os.path.join(ROOT, "open_spiel_coup_b200", "csrc"))) if f.endswith(".cuh")}
 
 
 def function_of(f, ln):
