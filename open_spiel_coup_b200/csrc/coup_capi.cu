@@ -190,7 +190,9 @@ int encode_obs_typed(coup_vec_env* env, const Src& src, uint32_t max_groups, int
   const uint32_t row_len = ((player >> 8) & kVisNoPublic) ? 42u : COUP_OBSERVATION_SIZE;
   const size_t smem = static_cast<size_t>(kObsWarps) * 32 * ((player & 7) == COUP_PLAYER_BOTH ? 2 : 1) * row_len * sizeof(T);
   int sms = 0;
-  cudaError_t err = cudaFuncSetAttribute(k_encode_obs<T, Src>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  const bool sparse = sizeof(T) == 4 && (player & 7) == COUP_PLAYER_BOTH;   // fp32 rows of both views: poke / erase (coup_encode.cuh)
+  auto kernel = sparse ? k_encode_obs<T, Src, true> : k_encode_obs<T, Src, false>;
+  cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (err == cudaSuccess) err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, env->opts.device);
   if (err != cudaSuccess) return fail(COUP_ERR_CUDA, std::string("k_encode_obs setup: ") + cudaGetErrorString(err));
   // persistent: as many CTAs as fit at once (shared memory bound, at most 8 per SM), never more than there are groups
@@ -198,7 +200,7 @@ int encode_obs_typed(coup_vec_env* env, const Src& src, uint32_t max_groups, int
   const unsigned groups = (max_groups + 31) / 32;
   const unsigned grid = std::max(1u, std::min(static_cast<unsigned>(sms) * per_sm, (groups + kObsWarps - 1) / kObsWarps));
   const int use_bulk = reinterpret_cast<uintptr_t>(d_out) % 16u == 0 && (env->opts.flags & COUP_FLAG_PLAIN_STORE_ENCODER) == 0;
-  k_encode_obs<T, Src><<<grid, kObsThreads, smem, st>>>(src, player, static_cast<T*>(d_out), use_bulk, row_len, d_ids_out, d_count_out);
+  kernel<<<grid, kObsThreads, smem, st>>>(src, player, static_cast<T*>(d_out), use_bulk, row_len, d_ids_out, d_count_out);
   return launch_status("k_encode_obs");
 }
 
