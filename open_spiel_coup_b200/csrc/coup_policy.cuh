@@ -105,36 +105,28 @@ k_sample_policy(EnvArrays A, const T* __restrict__ logits, float* __restrict__ p
 }
 
 // ---- dense legal mask: uint8[n][18] (State::LegalActionsMask, spiel.cc:371-377) ----------------------
-// A warp expands the masks of 32 envs into one contiguous 576-byte span: 36 sixteen-byte stores, each byte's mask fetched
-// from the lane that holds it.
+// Every lane expands its own env's mask into 18 bytes (nine byte-pair stores) in the warp's 576-byte staging span in shared
+// memory; the span then leaves as 36 sixteen-byte stores.
 __global__ void __launch_bounds__(kBlockThreads)
 k_legal_actions_mask(const uint32_t* __restrict__ legal, uint8_t* __restrict__ out, uint32_t n) {
-  const int lane = threadIdx.x & 31;
-  const uint32_t e0 = (blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5)) * 32u;
+  __shared__ __align__(16) uint8_t s_span[kWarpsPerBlock][32 * kNumActions];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t e0 = (blockIdx.x * kWarpsPerBlock + warp) * 32u;
   if (e0 >= n) return;
   const uint32_t mine = e0 + lane < n ? legal[e0 + lane] : 0u;
+  uint16_t* row = reinterpret_cast<uint16_t*>(s_span[warp] + lane * kNumActions);      // 18 * lane is even
+#pragma unroll
+  for (uint32_t k = 0; k < kNumActions / 2; ++k)
+    row[k] = static_cast<uint16_t>(((mine >> (2u * k)) & 1u) | (((mine >> (2u * k + 1u)) & 1u) << 8));
+  __syncwarp();
   const uint32_t span = min(32u, n - e0) * kNumActions;                 // bytes of this warp
   uint8_t* dst = out + static_cast<size_t>(e0) * kNumActions;
-  const bool vector_ok = (reinterpret_cast<uintptr_t>(dst) & 15u) == 0 && span == 32u * kNumActions;
-#pragma unroll
-  for (uint32_t i = 0; i < 2; ++i) {
-    const uint32_t unit = lane + 32u * i;                               // 16-byte unit of the span (36 of them)
-    uint32_t w[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-    for (uint32_t b = 0; b < 16; ++b) {
-      const uint32_t j = min(unit * 16u + b, 32u * kNumActions - 1u);
-      const uint32_t r = (j * 3641u) >> 16;
-      const uint32_t bit = (__shfl_sync(0xffffffffu, mine, static_cast<int>(r)) >> (j - r * kNumActions)) & 1u;
-      w[b >> 2] |= bit << (8u * (b & 3u));
-    }
-    if (unit < 36u) {
-      if (vector_ok) {
-        reinterpret_cast<uint4*>(dst)[unit] = make_uint4(w[0], w[1], w[2], w[3]);
-      } else {
-        for (uint32_t b = 0; b < 16; ++b)
-          if (unit * 16u + b < span) dst[unit * 16u + b] = static_cast<uint8_t>((w[b >> 2] >> (8u * (b & 3u))) & 1u);
-      }
-    }
+  if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0 && span == 32u * kNumActions) {
+    const uint4* src = reinterpret_cast<const uint4*>(s_span[warp]);
+    reinterpret_cast<uint4*>(dst)[lane] = src[lane];
+    if (lane < 4) reinterpret_cast<uint4*>(dst)[32 + lane] = src[32 + lane];
+  } else {
+    for (uint32_t i = lane; i < span; i += 32u) dst[i] = s_span[warp][i];
   }
 }
 
