@@ -84,6 +84,16 @@ bool valid_dtype(int d) { return d == COUP_DTYPE_F32 || d == COUP_DTYPE_U8 || d 
 // Bulk stores also need a 16-byte aligned destination: a torch view such as out[1:] of a uint8 tensor (2492-byte rows) is
 // not, and a misaligned cp.async.bulk is a sticky fault. Such outputs take the plain-store encoder, which needs only the
 // alignment of its four-element store unit (16 / 8 / 4 bytes for f32 / bf16 / u8); below that the call is rejected.
+// Dynamic shared memory of a kernel whose occupancy is planned around it: raises the limit AND asks for the largest
+// shared-memory carveout, so that the planned number of CTAs per SM really fits. (Without the preference the driver picks the
+// carveout itself: k_encode_obs<float>, 50 KB per CTA and planned for 4 per SM, ran at 80 or at 99 us from run to run.)
+template <typename K>
+cudaError_t set_dynamic_smem(K kernel, int bytes) {
+  cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (err == cudaSuccess) err = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  return err;
+}
+
 bool use_staged_encoder(const coup_vec_env* env, uint32_t stride, const void* d_out) {
   return (env->opts.flags & COUP_FLAG_PLAIN_STORE_ENCODER) == 0 &&
          (stride == COUP_INFO_STATE_SIZE || stride == 2496u || stride == COUP_LIVE_INFO_STATE_SIZE) &&
@@ -116,9 +126,9 @@ int rollout_typed(coup_vec_env* env, int n_steps, int encode_player, void* d_out
   const bool specialised = staged && (env->opts.flags & COUP_FLAG_NO_WARP_SPECIALISATION) == 0 && env->A.n >= kWsBatch;
   int sms = 0;
   if (staged) {
-    cudaError_t err = cudaFuncSetAttribute(k_rollout_tma<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmemBytes);
+    cudaError_t err = set_dynamic_smem(k_rollout_tma<T>, kTmaSmemBytes);
     if (err == cudaSuccess && specialised) {
-      err = cudaFuncSetAttribute(k_rollout_ws<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWsSmemBytes);
+      err = set_dynamic_smem(k_rollout_ws<T>, kWsSmemBytes);
       if (err == cudaSuccess) err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, env->opts.device);
     }
     if (err != cudaSuccess) return fail(COUP_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(err));
@@ -163,7 +173,7 @@ int encode_info_typed(coup_vec_env* env, const Src& src, uint32_t max_groups, in
   if (max_groups == 0) return COUP_OK;   // rows to produce (before the x2 of COUP_PLAYER_BOTH), an upper bound for ring sources
   const unsigned grid = (max_groups + 32 * kWarpsPerBlock - 1) / (32 * kWarpsPerBlock);
   if (use_staged_encoder(env, stride, d_out)) {
-    cudaError_t err = cudaFuncSetAttribute(k_encode_info_tma<T, Src>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmemBytes);
+    cudaError_t err = set_dynamic_smem(k_encode_info_tma<T, Src>, kTmaSmemBytes);
     if (err != cudaSuccess) return fail(COUP_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(err));
     k_encode_info_tma<T, Src><<<grid, kTmaBlockThreads, kTmaSmemBytes, st>>>(src, player, static_cast<T*>(d_out), stride, d_ids_out, d_count_out);
   } else {
@@ -190,9 +200,8 @@ int encode_obs_typed(coup_vec_env* env, const Src& src, uint32_t max_groups, int
   const uint32_t row_len = ((player >> 8) & kVisNoPublic) ? 42u : COUP_OBSERVATION_SIZE;
   const size_t smem = static_cast<size_t>(kObsWarps) * 32 * ((player & 7) == COUP_PLAYER_BOTH ? 2 : 1) * row_len * sizeof(T);
   int sms = 0;
-  const bool sparse = sizeof(T) == 4 && (player & 7) == COUP_PLAYER_BOTH;   // fp32 rows of both views: poke / erase (coup_encode.cuh)
-  auto kernel = sparse ? k_encode_obs<T, Src, true> : k_encode_obs<T, Src, false>;
-  cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  auto kernel = k_encode_obs<T, Src, sizeof(T) == 4>;   // fp32 rows: poke / erase; narrower elements: composed pairs (coup_encode.cuh)
+  cudaError_t err = set_dynamic_smem(kernel, static_cast<int>(smem));
   if (err == cudaSuccess) err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, env->opts.device);
   if (err != cudaSuccess) return fail(COUP_ERR_CUDA, std::string("k_encode_obs setup: ") + cudaGetErrorString(err));
   // persistent: as many CTAs as fit at once (shared memory bound, at most 8 per SM), never more than there are groups
@@ -221,7 +230,7 @@ int rollout_incremental_typed(coup_vec_env* env, int n_steps, void* d_buf, uint3
   const unsigned grid = blocks_for(env->A.n);
   constexpr int kIncSmemBytes = kIncSmemWords * 4 + UnitLut<T>::kBytes;
   static_assert(kIncSmemBytes <= kIncSmemBytesMax, "unit table larger than reserved");
-  cudaError_t err = cudaFuncSetAttribute(k_rollout_incremental<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kIncSmemBytes);
+  cudaError_t err = set_dynamic_smem(k_rollout_incremental<T>, kIncSmemBytes);
   if (err != cudaSuccess) return fail(COUP_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(err));
   for (int i = 0; i < n_steps; ++i) {
     step_prologue(env, false, st);

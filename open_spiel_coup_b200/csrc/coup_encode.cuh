@@ -404,9 +404,10 @@ __device__ __forceinline__ void compose_obs_row(T* row, uint64_t head, uint64_t 
   }
 }
 
-// The sparse alternative: pokes (set = true) or erases (set = false) only the ~14 non-zeros of a row. Used for fp32 rows of
-// both views, where the lane pitch of 196 words makes the 49 pair stores of compose_obs_row four-way bank conflicts
-// (139.7 against 151.5 us per 2^20 envs); everywhere else composing is as fast or faster (u8: 45.3 -> 31.0 us).
+// The sparse alternative: pokes (set = true) or erases (set = false) only the ~14 non-zeros of a row. Used for fp32 rows:
+// with both views their lane pitch of 196 words makes the 49 pair stores of compose_obs_row four-way bank conflicts (139.7
+// against 151.5 us per 2^20 envs), and with one view composing was no faster and less steady (80 us, at times 96). For the
+// narrower element types composing wins (u8: 45.3 -> 31.0 us).
 template <typename T>
 __device__ __forceinline__ void poke_obs_row(T* row, uint64_t head, uint64_t last_action, uint32_t coins, bool set, bool pub) {
   const T one = Elem<T>::from(set ? 1u : 0u);
@@ -426,7 +427,7 @@ __device__ __forceinline__ void poke_obs_row(T* row, uint64_t head, uint64_t las
 }
 
 // player_sel: bits 0-2 COUP_PLAYER_*, bits 8.. kVis* (the observer type); row_len = 98, or 42 without public info.
-// kSparse: fp32 rows of both views (see poke_obs_row); a compile-time switch so that every other form carries no trace of it.
+// kSparse: fp32 rows (see poke_obs_row); a compile-time switch so that the other element types carry no trace of it.
 template <typename T, typename Src, bool kSparse>
 __global__ void __launch_bounds__(kObsThreads)
 k_encode_obs(Src src, int player_sel, T* __restrict__ out, int use_bulk, uint32_t row_len, uint32_t* __restrict__ ids_out,
@@ -483,7 +484,7 @@ k_encode_obs(Src src, int player_sel, T* __restrict__ out, int use_bulk, uint32_
       T* row = stage + static_cast<size_t>(lane) * views * row_len;
       if (sparse) {
         poke_obs_row<T>(row, head_a, la, coins, true, pub);
-        poke_obs_row<T>(row + row_len, head_b, la, coins, true, pub);
+        if (both) poke_obs_row<T>(row + row_len, head_b, la, coins, true, pub);
       } else {
         compose_obs_row<T>(row, head_a, la, coins, pub);
         if (both) compose_obs_row<T>(row + row_len, head_b, la, coins, pub);
@@ -506,7 +507,7 @@ k_encode_obs(Src src, int player_sel, T* __restrict__ out, int use_bulk, uint32_
     if (sparse && e < n) {                          // sparse rows are erased again
       T* row = stage + static_cast<size_t>(lane) * views * row_len;
       poke_obs_row<T>(row, head_a, la, coins, false, pub);
-      poke_obs_row<T>(row + row_len, head_b, la, coins, false, pub);
+      if (both) poke_obs_row<T>(row + row_len, head_b, la, coins, false, pub);
     }
   }
   if (lane == 0) tma_wait_all();   // the engine must be done with this warp's shared memory before the CTA exits
