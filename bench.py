@@ -345,7 +345,13 @@ def main():
         kern = {}
 
         def add(name, kernel, fn, bytes_per_env, reps, note=None):
-            fn()
+            # warm-up of ~30 ms: the allocations and frees between the legs leave the GPU idle for milliseconds, and a short
+            # kernel timed right after such a gap can catch the clocks still ramping (80 vs 99 us for the first leg)
+            t_w = time.perf_counter()
+            while time.perf_counter() - t_w < 0.03:
+                for _ in range(10):
+                    fn()
+                torch.cuda.synchronize()
             msk = timed(lambda k: [fn() for _ in range(k)], reps)
             per_s = reps * n * world / (msk * 1e-3)
             gbs = bytes_per_env * per_s / world / 1e9
