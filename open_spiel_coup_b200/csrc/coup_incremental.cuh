@@ -32,7 +32,6 @@ namespace coup {
 constexpr int kIncViewWords = 18;                      // per view: 2 span headers, 6 + 6 bitmap words, the 4 words of the coin unit
 constexpr int kIncRecWords = 1 + 2 * kIncViewWords;    // 37: an odd pitch, conflict-free per-lane access; 4 CTAs fit an SM
 constexpr int kIncRowPitch = kHistoryWords + 1;
-constexpr uint32_t kIncBias = 8;                       // units: span 0 of a warp's first row can start before the row
 constexpr int kIncSmemWords = kBlockThreads * (kIncRecWords + kIncRowPitch);       // records + rows; the unit table follows
 constexpr int kIncSmemBytesMax = kIncSmemWords * 4 + 4096;                          // dynamic (above the 48 KB static limit)
 
@@ -164,16 +163,10 @@ k_rollout_incremental(EnvArrays A, uint64_t step, T* __restrict__ buf, uint32_t 
         const size_t row_base = (static_cast<size_t>(e) * 2 + view) * stride;         // absolute index of element 0 of the row
         const size_t a0 = row_base / kSector * kSector, b0 = (row_base + hi0 + kSector - 1u) / kSector * kSector;
         const int back0 = static_cast<int>(row_base - a0);                             // span 0 starts `back0` elements early
+        vr[0] = static_cast<uint32_t>(back0) | (static_cast<uint32_t>((b0 - a0) / kEl) << 8);
         const size_t a1 = (row_base + lo1) / kSector * kSector, b1 = (row_base + hi1 + kSector - 1u) / kSector * kSector;
         const int start1 = static_cast<int>(a1 - row_base);                            // row element where span 1 starts
-        // Everything the walk needs, decided here once per (env, view) by the owner lane -- in units of 16 bytes:
-        //   word 0: units of span 0 (9 bits) | units of span 1 << 9 (5 bits) | the unit of span 0 with the coin counts << 14
-        //           (6 bits) | distance from the start of span 0 to the start of span 1 << 20 (12 bits)
-        //   word 1: where span 0 starts, relative to the warp's first row (+ kIncBias: it can start up to one sector earlier)
-        const uint32_t n0 = static_cast<uint32_t>((b0 - a0) / kEl), n1 = hi1 > lo1 ? static_cast<uint32_t>((b1 - a1) / kEl) : 0u;
-        const size_t warp_base = static_cast<size_t>(e - lane) * 2 * stride;           // a multiple of 256 elements
-        vr[0] = n0 | (n1 << 9) | (((60u + static_cast<uint32_t>(back0)) / kEl) << 14) | (static_cast<uint32_t>((a1 - a0) / kEl) << 20);
-        vr[1] = static_cast<uint32_t>((a0 + kIncBias * kEl - warp_base) / kEl);
+        vr[1] = static_cast<uint32_t>(start1) | ((hi1 > lo1 ? static_cast<uint32_t>((b1 - a1) / kEl) : 0u) << 16);
         // bitmaps: bit t = element (span start + t)
         uint32_t* bm0 = vr + 2;
         uint32_t* bm1 = vr + 8;
@@ -208,23 +201,27 @@ k_rollout_incremental(EnvArrays A, uint64_t step, T* __restrict__ buf, uint32_t 
   uint32_t touched = __ballot_sync(0xffffffffu, active && r.stepped);
   __syncwarp();
   const uint32_t view = static_cast<uint32_t>(lane) >> 4, l = static_cast<uint32_t>(lane) & 15u;
-  // 16-byte units of the buffer, counted from kIncBias units before the warp's first row (a multiple of 256 elements)
-  uint4* const wbase = reinterpret_cast<uint4*>(buf + static_cast<size_t>(e - lane) * 2 * stride) - kIncBias;
+  const uint32_t e0 = e - lane;
   while (touched) {
     const int j = __ffs(touched) - 1;
     touched &= touched - 1;
-    const uint32_t* vr = s_rec[warp][j] + 1 + view * kIncViewWords;
-    const uint32_t hdr = vr[0], rel = vr[1];
+    const uint32_t* rec = s_rec[warp][j];
+    const uint32_t* vr = rec + 1 + view * kIncViewWords;
+    const uint32_t hdr0 = vr[0], hdr1 = vr[1], coin_unit = (60u + (hdr0 & 255u)) / kEl;
+    const size_t row_base = (static_cast<size_t>(e0 + j) * 2 + view) * stride;
     // both spans as one list of units: [0, n0) span 0, [n0, n0 + n1) span 1
-    const uint32_t n0 = hdr & 511u, n = n0 + ((hdr >> 9) & 31u), coin_k = (hdr >> 14) & 63u, delta1 = hdr >> 20;
-    for (uint32_t k = l; k < n; k += 16u) {
+    const uint32_t n0 = hdr0 >> 8, n1 = hdr1 >> 16;
+    uint4* const dst0 = reinterpret_cast<uint4*>(buf + (row_base - (hdr0 & 255u)));
+    uint4* const dst1 = reinterpret_cast<uint4*>(buf + (row_base + (hdr1 & 0xFFFFu)));
+    for (uint32_t k = l; k < n0 + n1; k += 16u) {
       const bool second = k >= n0;
-      const uint32_t u = second ? k - n0 : k;                                        // unit within its span
+      const uint32_t u = second ? k - n0 : k;
       const uint32_t o = u * kEl;                                                    // never straddles a 32-bit word
       const uint32_t word = o < 192u ? vr[(second ? 8u : 2u) + (o >> 5)] : 0u;
-      uint4 v = UnitLut<T>::lookup(lut, (word >> (o & 31u)) & ((1u << kEl) - 1u));
-      if (k == coin_k) v = make_uint4(vr[14], vr[15], vr[16], vr[17]);               // the unit with the raw coin counts (in span 0)
-      wbase[rel + u + (second ? delta1 : 0u)] = v;
+      const uint32_t bits = (word >> (o & 31u)) & ((1u << kEl) - 1u);
+      uint4 v = UnitLut<T>::lookup(lut, bits);
+      if (!second && u == coin_unit) v = make_uint4(vr[14], vr[15], vr[16], vr[17]);   // the unit with the raw coin counts
+      (second ? dst1 : dst0)[u] = v;
     }
   }
   st.flush(A.stats);
