@@ -314,17 +314,18 @@ def main():
             del buf
         # live-prefix contract: fp32 rows of 1728 elements = elements [0, 1728) of the reference row; everything they drop
         # (history rows 91..134) is zero in every reachable state (COUP_LIVE_INFO_STATE_SIZE, include/coup_b200.h)
-        live_bytes = 42 + 4 * _lib.LIVE_INFO_STATE_SIZE + 11
-        buf = torch.empty((n, _lib.LIVE_INFO_STATE_SIZE), dtype=torch.float32, device=dev)
-        env.rollout(3, _lib.PLAYER_CURRENT, out=buf)
-        m2 = timed(lambda k: env.rollout(k, _lib.PLAYER_CURRENT, out=buf), ke)
-        v2 = ke * n * world / (m2 * 1e-3)
-        extra["d32_live_prefix"] = {"steps_per_s": v2, "hbm_gbs": live_bytes * v2 / world / 1e9, "bytes_per_step": live_bytes,
-                                    "note": "fp32 rows cut after element 1727: the dropped columns are always zero"}
-        if rank == 0:
-            fill = zero_fill_gbs(buf)
-            extra["d32_live_prefix"].update(write_only_fill_gbs=fill, frac_of_write_only_fill=extra["d32_live_prefix"]["hbm_gbs"] / fill)
-        del buf
+        for name, dt in (("d32_live_prefix", torch.float32), ("bf16_live_prefix", torch.bfloat16), ("d8_live_prefix", torch.uint8)):
+            buf = torch.empty((n, _lib.LIVE_INFO_STATE_SIZE), dtype=dt, device=dev)
+            live_bytes = 42 + buf.element_size() * _lib.LIVE_INFO_STATE_SIZE + 11
+            env.rollout(3, _lib.PLAYER_CURRENT, out=buf)
+            m2 = timed(lambda k: env.rollout(k, _lib.PLAYER_CURRENT, out=buf), ke)
+            v2 = ke * n * world / (m2 * 1e-3)
+            extra[name] = {"steps_per_s": v2, "hbm_gbs": live_bytes * v2 / world / 1e9, "bytes_per_step": live_bytes,
+                           "note": "rows cut after element 1727: the dropped columns are always zero"}
+            if rank == 0:
+                fill = zero_fill_gbs(buf)
+                extra[name].update(write_only_fill_gbs=fill, frac_of_write_only_fill=extra[name]["hbm_gbs"] / fill)
+            del buf
         # contract I: persistent fp32 buffer with both views of every env, updated in place
         if out is not None:
             del out
