@@ -312,6 +312,14 @@ def main():
                 fill = zero_fill_gbs(buf)
                 extra[name].update(write_only_fill_gbs=fill, frac_of_write_only_fill=extra[name]["hbm_gbs"] / fill)
             del buf
+            if dt is None and args.ring:
+                # the same env-only rollout without the finished-episode ring (episodes' logs are lost at the re-deal)
+                env.enable_finished_ring(0)
+                env.rollout(3)
+                m2 = timed(lambda k: env.rollout(k), kk)
+                v2 = kk * n * world / (m2 * 1e-3)
+                extra["env_no_ring"] = {"steps_per_s": v2, "hbm_gbs": BYTES_PER_STEP["env"] * v2 / world / 1e9}
+                env.enable_finished_ring(args.ring)
         # live-prefix contract: fp32 rows of 1728 elements = elements [0, 1728) of the reference row; everything they drop
         # (history rows 91..134) is zero in every reachable state (COUP_LIVE_INFO_STATE_SIZE, include/coup_b200.h)
         for name, dt in (("d32_live_prefix", torch.float32), ("bf16_live_prefix", torch.bfloat16), ("d8_live_prefix", torch.uint8)):
